@@ -1,0 +1,91 @@
+"""ctypes binding of libhmsg_b200.so (include/hmsg_b200.h).  No CPU fallback: if the
+library is missing or no B200 is present, every product call fails loudly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libhmsg_b200.so")
+
+_i32, _i64, _f32, _f64, _vp = C.c_int32, C.c_int64, C.c_float, C.c_double, C.c_void_p
+
+
+class VitDesc(C.Structure):
+    _fields_ = [(n, _i32) for n in ("image", "patch", "width", "layers", "heads", "mlp", "out_dim", "quick_gelu")]
+
+
+# name -> (restype, argtypes); mirrors include/hmsg_b200.h one to one
+SIGNATURES = {
+    "hmsg_version": (_i32, []),
+    "hmsg_ctx_create": (_i32, [_i32, C.POINTER(_vp)]),
+    "hmsg_ctx_destroy": (_i32, [_vp]),
+    "hmsg_last_error": (C.c_char_p, [_vp]),
+    "hmsg_sync": (_i32, [_vp]),
+    "hmsg_stream": (_vp, [_vp]),
+    "hmsg_launch_count": (_i64, [_vp]),
+    "hmsg_scene_begin": (_i32, [_vp, _i32, _i32, _vp, _f32, _f64, _i64]),
+    "hmsg_scene_add_frames": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32]),
+    "hmsg_scene_num_frames": (_i64, [_vp]),
+    "hmsg_unproject_frame": (_i32, [_vp, _i64, _vp, _vp, _vp]),
+    "hmsg_voxel_build": (_i32, [_vp, C.POINTER(_i64), _vp]),
+    "hmsg_voxels_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "hmsg_radius_filter": (_i32, [_vp, _i32, _f64, C.POINTER(_i64)]),
+    "hmsg_radius_counts_read": (_i32, [_vp, _vp]),
+    "hmsg_nodes_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
+    "hmsg_num_nodes": (_i64, [_vp]),
+    "hmsg_pixel_to_node": (_i32, [_vp, _i64, _vp, _vp]),
+    "hmsg_points_to_node": (_i32, [_vp, _vp, _i64, _vp, _vp]),
+    "hmsg_features_begin": (_i32, [_vp, _i32]),
+    "hmsg_masks_dense": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32]),
+    "hmsg_masks_boxes": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32]),
+    "hmsg_fuse_scatter": (_i32, [_vp, _i64, _i32, _i32, _vp, _f32, _vp, _i32]),
+    "hmsg_node_feats_finalize": (_i32, [_vp, _vp, _i32]),
+    "hmsg_node_feats_raw": (_i32, [_vp, _vp, _vp]),
+    "hmsg_mask_nodes": (_i32, [_vp, _i64, _f64, _vp, _vp, _vp, _vp]),
+    "hmsg_encoder_load": (_i32, [_vp, C.POINTER(VitDesc), _vp, _i64]),
+    "hmsg_encode_images": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32]),
+    "hmsg_gemm_f16_debug": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32]),
+    "hmsg_make_crops": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "hmsg_index_set": (_i32, [_vp, _vp, _i64, _i32, _i32]),
+    "hmsg_query_topk": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32]),
+    "hmsg_query_object": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),
+    "hmsg_node_feats_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
+}
+
+_lib = None
+
+
+def load(path: str | None = None):
+    """dlopen the library and attach prototypes.  Raises if it has not been built."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(
+            f"{p} is missing: build it with `python -m holoagent_b200.build` (nvcc, sm_100a). "
+            "holoagent_b200 has no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def ptr(a):
+    """void* of a numpy array / torch tensor / int / None."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))

@@ -1,0 +1,189 @@
+// common.cuh - context, error handling and exact-rounding device helpers shared by the
+// sm_100a kernels of libhmsg_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+#include "../../include/hmsg_b200.h"
+
+#define HMSG_CUDA(call)                                                                   \
+  do {                                                                                    \
+    cudaError_t e__ = (call);                                                             \
+    if (e__ != cudaSuccess) {                                                             \
+      return ctx->fail(HMSG_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    }                                                                                     \
+  } while (0)
+
+#define HMSG_LAUNCH_CHECK()                                                               \
+  do {                                                                                    \
+    ctx->launches++;                                                                      \
+    cudaError_t e__ = cudaGetLastError();                                                 \
+    if (e__ != cudaSuccess)                                                               \
+      return ctx->fail(HMSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
+  } while (0)
+
+struct VitState;   // encoder.cu
+struct KnnState;   // knn.cu
+
+struct GridDesc {
+  double vmin[3];     // min_bound - vs/2  (Open3D voxel_min_bound)
+  double vs;
+  int nx, ny, nz, nzp;   // nzp = nz rounded up to a multiple of 32: a bitmap word never spans columns
+  long long nwords;
+};
+
+struct CamDesc {
+  double fx, fy, cx, cy;
+  float scale;
+  int H, W;
+};
+
+struct hmsg_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+
+  // ---- scene
+  CamDesc cam{};
+  double vs = 0.05;
+  int64_t cap = 0, nframes = 0;
+  uint16_t* depth = nullptr;   // [cap,H,W]
+  uint8_t* rgb = nullptr;      // [cap,H,W,3]
+  double* poses = nullptr;     // [cap,16]
+
+  // ---- voxel table (A2)
+  long long* d_bounds = nullptr;   // 6 ordered-int doubles: min xyz, max xyz
+  double min_bound[3]{}, max_bound[3]{};
+  GridDesc grid{};
+  uint32_t* bitmap = nullptr;      // occupancy, 1 bit per cell, k fastest
+  uint32_t* prefix = nullptr;      // exclusive popcount prefix per word
+  uint32_t* blocksums = nullptr;
+  int64_t n_voxels = 0;
+  double* vox_acc = nullptr;       // [n_voxels,6] sum -> mean of xyz, rgb
+  uint32_t* vox_cnt = nullptr;
+  int32_t* vox_ijk = nullptr;
+  uint32_t* rad_cnt = nullptr;
+  bool voxels_built = false;
+
+  // ---- nodes (A3)
+  int64_t n_nodes = 0;
+  uint32_t* nbitmap = nullptr;     // occupancy of kept voxels
+  uint32_t* nprefix = nullptr;
+  double* node_xyz = nullptr;      // [n_nodes,3]
+  double* node_rgb = nullptr;
+  int32_t* node_ijk = nullptr;
+  int64_t* node_vox = nullptr;
+  bool nodes_built = false;
+
+  // ---- features (A5/A6)
+  int d = 0;
+  float* sum_feats = nullptr;      // [n_nodes,d]
+  float* counter = nullptr;        // [n_nodes]
+  // batch scratch
+  int batch_cap = 0;
+  int batch_M = 0, batch_MW = 0;
+  int64_t batch_begin = -1;
+  int batch_n = 0;
+  uint32_t* maskbits = nullptr;    // [batch_cap, H*W, MW]
+  size_t maskbits_bytes = 0;
+  int32_t* pix_idx = nullptr;      // [batch_cap, H*W]
+  size_t pix_idx_bytes = 0;
+  unsigned long long* win = nullptr;   // [batch_cap, n_nodes]
+  size_t win_bytes = 0;
+  uint32_t epoch = 0;
+  float* Fp = nullptr;             // [batch_cap, M, d]
+  size_t Fp_bytes = 0;
+  float* feats_stage = nullptr;    // staging for host-provided encoder outputs
+  size_t feats_stage_bytes = 0;
+  int32_t* boxes_stage = nullptr;
+  size_t boxes_stage_bytes = 0;
+  uint8_t* seg_stage = nullptr;
+  size_t seg_stage_bytes = 0;
+  // generic scratch
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+
+  VitState* vit = nullptr;
+  KnnState* knn = nullptr;
+
+  int32_t fail(int32_t code, const std::string& msg) {
+    err = msg;
+    return code;
+  }
+  // grow-only device buffer
+  template <typename T>
+  int32_t reserve(T** p, size_t* cur_bytes, size_t need_bytes) {
+    if (*cur_bytes >= need_bytes && *p) return HMSG_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cur_bytes = 0;
+    cudaError_t e = cudaMalloc((void**)p, need_bytes);
+    if (e != cudaSuccess) return fail(HMSG_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cur_bytes = need_bytes;
+    return HMSG_OK;
+  }
+};
+
+template <typename T>
+static inline void free_dev(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+// ---------------------------------------------------------------------------------------
+// exact-rounding helpers: every operation is an individually rounded IEEE op (no FMA
+// contraction) so that voxel keys / node indices match the float64 NumPy/Open3D arithmetic
+// of the reference bit for bit.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ long long d2ord(double v) {
+  long long b = __double_as_longlong(v);
+  return b >= 0 ? b : (b ^ 0x7FFFFFFFFFFFFFFFLL);
+}
+static inline double ord2d_host(long long o) {
+  long long b = o >= 0 ? o : (o ^ 0x7FFFFFFFFFFFFFFFLL);
+  double v;
+  memcpy(&v, &b, 8);
+  return v;
+}
+
+struct Pose {
+  double t[16];
+};
+
+// generic.py:111,122-124,137: depth_f32 = u16/scale (float32 division); X=(x-cx)*d/fx ...;
+// Open3D transform: T*[X Y Z 1]^T then divide by w.
+__device__ __forceinline__ void unproject_px(unsigned short dep, int x, int y, const CamDesc& c,
+                                             const double* T, double& wx, double& wy, double& wz) {
+  float df = __fdiv_rn((float)dep, c.scale);
+  double dd = (double)df;
+  double X = __ddiv_rn(__dmul_rn(__dsub_rn((double)x, c.cx), dd), c.fx);
+  double Y = __ddiv_rn(__dmul_rn(__dsub_rn((double)y, c.cy), dd), c.fy);
+  double Z = dd;
+  double w = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[12], X), __dmul_rn(T[13], Y)), __dmul_rn(T[14], Z)), T[15]);
+  double ax = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], X), __dmul_rn(T[1], Y)), __dmul_rn(T[2], Z)), T[3]);
+  double ay = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], X), __dmul_rn(T[5], Y)), __dmul_rn(T[6], Z)), T[7]);
+  double az = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], X), __dmul_rn(T[9], Y)), __dmul_rn(T[10], Z)), T[11]);
+  wx = __ddiv_rn(ax, w);
+  wy = __ddiv_rn(ay, w);
+  wz = __ddiv_rn(az, w);
+}
+
+// Open3D VoxelDownSample: ref = (p - voxel_min_bound) / voxel_size; floor
+__device__ __forceinline__ double cell_coord(double p, double vmin, double vs) {
+  return __ddiv_rn(__dsub_rn(p, vmin), vs);
+}
+
+__device__ __forceinline__ double sqdist3(double ax, double ay, double az, double bx, double by, double bz) {
+  double dx = __dsub_rn(ax, bx), dy = __dsub_rn(ay, by), dz = __dsub_rn(az, bz);
+  return __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+}
+
+// sub-module entry points used by api.cu
+int32_t vit_destroy(hmsg_ctx* ctx);
+int32_t knn_destroy(hmsg_ctx* ctx);

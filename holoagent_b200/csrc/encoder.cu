@@ -1,0 +1,866 @@
+// encoder.cu - A9: open_clip ViT visual tower forward (ViT-B/32 for d=512) on sm_100a.
+// Reference: fsr_vln/memory/hmsg/utils/clip_utils.py:63-94 (encode_image + F.normalize);
+//            model construction fsr_vln/memory/hmsg/graph/graph.py:112-119 (fp16 weights).
+//
+// All dense contractions (patch embedding, QKV, out-proj, MLP fc/proj, final projection) run
+// through ONE persistent warp-specialised GEMM kernel written directly against the Blackwell
+// tensor-core path:  TMA (cp.async.bulk.tensor, 128B swizzle) -> 4-stage smem ring ->
+// tcgen05.mma (cta_group::1, kind::f16, M=128 N=256 K=16) issued by one elected thread ->
+// fp32 accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i
+// overlaps the MMAs of tile i+1 -> tcgen05.ld epilogue with fused bias / GELU / residual.
+//   C[M,N] = A[M,K] (fp16, K-major) x W[N,K]^T (fp16, K-major, torch Linear layout)
+// fp16 operands / fp32 accumulate / fp32 residual stream, LayerNorm and softmax in fp32.
+#include "common.cuh"
+#include <cuda.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded spin: a pipeline bug must surface as a trap (CUDA error), never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  for (uint64_t it = 0; it < (1ull << 28); ++it) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  asm volatile("trap;");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]   (single-CTA, fp16/bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives TMEM lane (base+i)
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   [0,14) start address >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) |
+//   [32,46) SBO >> 4 = 1024 B between 8-row groups | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// ------------------------------------------------------------------------------------------
+// GEMM kernel
+// ------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+enum { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU = 1, EPI_F32_RESIDUAL = 2, EPI_F32_STORE = 3 };
+
+struct GemmArgs {
+  int M, N, K;
+  const float* bias;     // [N] or null
+  void* out;             // fp16 [M,N] (EPI 0,1) or fp32 [M,N] (EPI 2: in-place +=, EPI 3: store)
+  int ldo;               // leading dimension of out in elements
+  int quick_gelu;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float gelu_quick(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+template <int EPI>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint64_t* full = bars;                  // [STAGES]
+  uint64_t* empty = bars + STAGES;        // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;    // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN, k_blocks = g.K / BK;
+  const int num_tiles = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        int mb = tile / n_tiles, nb = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(sA + s * A_STAGE_BYTES, &tmA, kb * BK, mb * BM, &full[s]);
+          tma_load_2d(sB + s * B_STAGE_BYTES, &tmB, kb * BK, nb * BN, &full[s]);
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      // instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=f16, K-major both, N=256, M=128
+      const uint32_t idesc = (1u << 4) | (0u << 7) | (0u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + s * A_STAGE_BYTES));
+          uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            // advance 16 halfs = 32 B along K inside the 128B swizzle atom: +2 in the (addr>>4) field
+            umma_f16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);                       // frees the smem slot when these MMAs retire
+          if (kb == k_blocks - 1) umma_commit(&tfull[as]);   // accumulator complete -> epilogue
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
+    const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may access
+    int as = 0; uint32_t aph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      int mb = tile / n_tiles, nb = tile % n_tiles;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const int row = mb * BM + ew * 32 + lane;
+      const bool row_ok = row < g.M;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; c++) {
+        uint32_t r[32];
+        tmem_ld_32x32(t_addr + (uint32_t)(c * 32), r);
+        tmem_ld_wait();
+        const int col = nb * BN + c * 32;
+        if (row_ok) {
+          if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU) {
+            __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                int i = q * 8 + e * 2;
+                float v0 = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + col + i) : 0.f);
+                float v1 = __uint_as_float(r[i + 1]) + (g.bias ? __ldg(g.bias + col + i + 1) : 0.f);
+                if (EPI == EPI_F16_BIAS_GELU) {
+                  if (g.quick_gelu) { v0 = gelu_quick(v0); v1 = gelu_quick(v1); }
+                  else { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
+                }
+                __half2 h = __floats2half2_rn(v0, v1);
+                pk[e] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              *reinterpret_cast<uint4*>(o + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          } else {
+            float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              float4 v;
+              v.x = __uint_as_float(r[q * 4 + 0]); v.y = __uint_as_float(r[q * 4 + 1]);
+              v.z = __uint_as_float(r[q * 4 + 2]); v.w = __uint_as_float(r[q * 4 + 3]);
+              if (g.bias) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col) + q);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (EPI == EPI_F32_RESIDUAL) {
+                float4 x = reinterpret_cast<float4*>(o)[q];
+                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+              }
+              reinterpret_cast<float4*>(o)[q] = v;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// element-wise / small kernels
+// ------------------------------------------------------------------------------------------
+// fp32 -> fp16 (weights upload), optional transpose [R,C] -> [C,R]
+__global__ void k_f32_to_f16(const float* __restrict__ in, __half* __restrict__ out, long long n) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2half_rn(in[i]);
+}
+__global__ void k_f32_to_f16_T(const float* __restrict__ in, __half* __restrict__ out, int R, int C) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)R * C) return;
+  int r = (int)(i / C), c = (int)(i % C);
+  out[(long long)c * R + r] = __float2half_rn(in[i]);
+}
+// conv weight [W, Kc] -> [W, Kpad] fp16 zero padded
+__global__ void k_pad_weight(const float* __restrict__ in, __half* __restrict__ out, int W, int Kc, int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)W * Kpad) return;
+  int r = (int)(i / Kpad), c = (int)(i % Kpad);
+  out[i] = (c < Kc) ? __float2half_rn(in[(long long)r * Kc + c]) : __float2half_rn(0.f);
+}
+
+// im2col for the stride==patch convolution: x [B,3,S,S] fp32 -> A0 [B*G*G, Kpad] fp16,
+// column = c*P*P + iy*P + ix (conv1.weight flattening).  One block per (b, c, image row).
+__global__ void k_im2col(const float* __restrict__ x, __half* __restrict__ a0, int S, int P, int G, int Kpad) {
+  int rowid = blockIdx.x;            // b*3*S + c*S + y
+  int y = rowid % S; int c = (rowid / S) % 3; int b = rowid / (3 * S);
+  int py = y / P, iy = y % P;
+  if (py >= G) return;
+  const float* src = x + (long long)rowid * S;
+  for (int t = threadIdx.x; t < G * P; t += blockDim.x) {
+    int px = t / P, ix = t % P;
+    a0[((long long)(b * G * G + py * G + px)) * Kpad + c * P * P + iy * P + ix] = __float2half_rn(src[t]);
+  }
+}
+__global__ void k_zero_pad_cols(__half* a0, long long rows, int Kc, int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int padw = Kpad - Kc;
+  if (i >= rows * padw) return;
+  a0[(i / padw) * Kpad + Kc + (i % padw)] = __float2half_rn(0.f);
+}
+
+// warp-per-row LayerNorm helpers; W % 128 == 0, W <= 1536
+template <int NV>   // NV = W/128 float4 per lane
+__device__ __forceinline__ void ln_row(float4* v, const float* __restrict__ gam, const float* __restrict__ bet, int lane, float eps) {
+  constexpr int W = NV * 128;
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) s += v[j].x + v[j].y + v[j].z + v[j].w;
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / (float)W;
+  float q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, d = v[j].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  float rstd = rsqrtf(q / (float)W + eps);
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float4 gm = __ldg(reinterpret_cast<const float4*>(gam) + lane + 32 * j);
+    float4 bt = __ldg(reinterpret_cast<const float4*>(bet) + lane + 32 * j);
+    v[j].x = (v[j].x - mean) * rstd * gm.x + bt.x;
+    v[j].y = (v[j].y - mean) * rstd * gm.y + bt.y;
+    v[j].z = (v[j].z - mean) * rstd * gm.z + bt.z;
+    v[j].w = (v[j].w - mean) * rstd * gm.w + bt.w;
+  }
+}
+
+// tokens: x[b*T + t] = ln_pre( (t==0 ? cls : patch[b*(T-1)+t-1]) + pos[t] )   -> fp32 residual stream
+template <int NV>
+__global__ void __launch_bounds__(256) k_embed_lnpre(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                                     const float* __restrict__ gam, const float* __restrict__ bet, float* __restrict__ x,
+                                                     long long rows, int T) {
+  constexpr int W = NV * 128;
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long b = row / T; int t = (int)(row % T);
+  const float4* src = (t == 0) ? reinterpret_cast<const float4*>(cls) : reinterpret_cast<const float4*>(patch + (b * (T - 1) + t - 1) * W);
+  const float4* pp = reinterpret_cast<const float4*>(pos + (long long)t * W);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float4 a = src[lane + 32 * j], p = __ldg(pp + lane + 32 * j);
+    v[j] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+  ln_row<NV>(v, gam, bet, lane, 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NV; j++) reinterpret_cast<float4*>(x + row * W)[lane + 32 * j] = v[j];
+}
+
+// h = LN(x) as fp16 ; row_stride/row_map: used for ln_post on the class-token rows (stride T)
+template <int NV>
+__global__ void __launch_bounds__(256) k_layernorm_f16(const float* __restrict__ x, const float* __restrict__ gam, const float* __restrict__ bet,
+                                                       __half* __restrict__ h, long long rows, long long in_row_stride) {
+  constexpr int W = NV * 128;
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(x + row * in_row_stride * W);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) v[j] = src[lane + 32 * j];
+  ln_row<NV>(v, gam, bet, lane, 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    __half2 a = __floats2half2_rn(v[j].x, v[j].y), b = __floats2half2_rn(v[j].z, v[j].w);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    reinterpret_cast<uint2*>(h + row * W)[lane + 32 * j] = pk;
+  }
+}
+
+// out[b] = in[b] / max(||in[b]||, 1e-12)   (F.normalize), warp per row, D % 128 == 0
+__global__ void __launch_bounds__(256) k_l2norm_rows(const float* __restrict__ in, float* __restrict__ out, int rows, int D, int do_norm) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + (long long)row * D);
+  float s = 0.f;
+  for (int j = lane; j < D / 4; j += 32) { float4 v = src[j]; s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w; }
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float den = do_norm ? fmaxf(sqrtf(s), 1e-12f) : 1.0f;
+  for (int j = lane; j < D / 4; j += 32) {
+    float4 v = src[j];
+    v.x = __fdiv_rn(v.x, den); v.y = __fdiv_rn(v.y, den); v.z = __fdiv_rn(v.z, den); v.w = __fdiv_rn(v.w, den);
+    reinterpret_cast<float4*>(out + (long long)row * D)[j] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention: T <= 64 tokens, head dim 64.  One warp per (image, head), mma.sync m16n8k16
+// (S = Q K^T and O = P V are 50x50x64 - far below a tcgen05 tile; 1.7 % of the model FLOPs).
+// ------------------------------------------------------------------------------------------
+constexpr int ATT_LD = 72;   // padded row stride in halfs: conflict-free 32-bit fragment loads
+__device__ __forceinline__ void mma_16816(float* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads, int W,
+                                                       float scale) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  long long pair = (long long)blockIdx.x * 4 + warp;       // (image, head)
+  if (pair >= (long long)B * heads) return;
+  int b = (int)(pair / heads), h = (int)(pair % heads);
+  __half* sQ = reinterpret_cast<__half*>(att_smem) + (size_t)warp * 3 * 64 * ATT_LD;
+  __half* sK = sQ + 64 * ATT_LD;
+  __half* sVt = sK + 64 * ATT_LD;      // [dcol][key]
+  const int ld = 3 * W;
+  // ---- load Q, K (row-major) and V (transposed); rows >= T are zero
+  for (int i = lane; i < 64 * 8; i += 32) {
+    int r = i >> 3, ch = i & 7;          // 8 x 16-byte chunks per 64-half row
+    uint4 q = make_uint4(0, 0, 0, 0), k = q, v = q;
+    if (r < T) {
+      const __half* base = qkv + ((long long)b * T + r) * ld + h * 64 + ch * 8;
+      q = *reinterpret_cast<const uint4*>(base);
+      k = *reinterpret_cast<const uint4*>(base + W);
+      v = *reinterpret_cast<const uint4*>(base + 2 * W);
+    }
+    *reinterpret_cast<uint4*>(sQ + r * ATT_LD + ch * 8) = q;
+    *reinterpret_cast<uint4*>(sK + r * ATT_LD + ch * 8) = k;
+    const __half* vh = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+    for (int e = 0; e < 8; e++) sVt[(ch * 8 + e) * ATT_LD + r] = vh[e];
+  }
+  __syncwarp();
+  const int g = lane >> 2, t = lane & 3;
+  const int m_tiles = (T + 15) / 16;
+  for (int mi = 0; mi < m_tiles; mi++) {
+    // ---- S = Q K^T for rows [16mi, 16mi+16), all 64 key columns
+    float s[8][4];
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) {
+      uint32_t a[4];
+      const __half* qa = sQ + (mi * 16 + g) * ATT_LD + ks * 16 + 2 * t;
+      a[0] = *reinterpret_cast<const uint32_t*>(qa);
+      a[1] = *reinterpret_cast<const uint32_t*>(qa + 8 * ATT_LD);
+      a[2] = *reinterpret_cast<const uint32_t*>(qa + 8);
+      a[3] = *reinterpret_cast<const uint32_t*>(qa + 8 * ATT_LD + 8);
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+        uint32_t bb[2];
+        const __half* kb = sK + (ni * 8 + g) * ATT_LD + ks * 16 + 2 * t;
+        bb[0] = *reinterpret_cast<const uint32_t*>(kb);
+        bb[1] = *reinterpret_cast<const uint32_t*>(kb + 8);
+        mma_16816(s[ni], a, bb);
+      }
+    }
+    // ---- softmax over keys (rows g and g+8 of this tile); columns >= T masked
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int col = ni * 8 + 2 * t + e;
+        float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
+        float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
+        s[ni][e] = v0; s[ni][2 + e] = v1;
+        mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        float p0 = __expf(s[ni][e] - mx0), p1 = __expf(s[ni][2 + e] - mx1);
+        s[ni][e] = p0; s[ni][2 + e] = p1;
+        sum0 += p0; sum1 += p1;
+      }
+    }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+    // ---- O = P V : P (fp32, normalised, rounded to fp16) as A fragments
+    float oacc[8][4];
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+#pragma unroll
+    for (int kk = 0; kk < 4; kk++) {
+      uint32_t a[4];
+      __half2 h0 = __floats2half2_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+      __half2 h1 = __floats2half2_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+      __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+      __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+      a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
+      a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+        uint32_t bb[2];
+        const __half* vb = sVt + (ni * 8 + g) * ATT_LD + kk * 16 + 2 * t;
+        bb[0] = *reinterpret_cast<const uint32_t*>(vb);
+        bb[1] = *reinterpret_cast<const uint32_t*>(vb + 8);
+        mma_16816(oacc[ni], a, bb);
+      }
+    }
+    int r0 = mi * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) {
+      int col = h * 64 + ni * 8 + 2 * t;
+      if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0], oacc[ni][1]);
+      if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2], oacc[ni][3]);
+    }
+  }
+}
+
+// straightforward fp32 reference attention (debug: HMSG_ATTN_SIMPLE=1), one block per (image, head)
+__global__ void __launch_bounds__(128) k_attention_simple(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads, int W,
+                                                          float scale) {
+  __shared__ __half sQ[64][66], sK[64][66], sV[64][66];
+  __shared__ float sP[4][64];
+  int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  int ld = 3 * W;
+  for (int i = threadIdx.x; i < T * 64; i += blockDim.x) {
+    int r = i / 64, c = i % 64;
+    const __half* base = qkv + ((long long)b * T + r) * ld + h * 64 + c;
+    sQ[r][c] = base[0]; sK[r][c] = base[W]; sV[r][c] = base[2 * W];
+  }
+  __syncthreads();
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < T; i += 4) {
+    float sc[2]; float mx = -INFINITY;
+    for (int jj = 0; jj < 2; jj++) {
+      int j = lane + 32 * jj; float a = -INFINITY;
+      if (j < T) { a = 0.f; for (int k = 0; k < 64; k++) a += __half2float(sQ[i][k]) * __half2float(sK[j][k]); a *= scale; }
+      sc[jj] = a; mx = fmaxf(mx, a);
+    }
+    for (int of = 16; of > 0; of >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, of));
+    float sum = 0.f;
+    for (int jj = 0; jj < 2; jj++) { int j = lane + 32 * jj; float p = (j < T) ? expf(sc[jj] - mx) : 0.f; sc[jj] = p; sum += p; }
+    for (int of = 16; of > 0; of >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, of);
+    for (int jj = 0; jj < 2; jj++) sP[warp][lane + 32 * jj] = sc[jj] / sum;
+    __syncwarp();
+    for (int dd = 0; dd < 2; dd++) {
+      int dcol = lane + 32 * dd; float a = 0.f;
+      for (int j = 0; j < T; j++) a += sP[warp][j] * __half2float(sV[j][dcol]);
+      o[((long long)b * T + i) * W + h * 64 + dcol] = __float2half_rn(a);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host state
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+struct LayerW {
+  float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *bfc, *bproj;
+  __half *wqkv, *wo, *wfc, *wproj;
+};
+
+struct VitState {
+  hmsg_vit_desc desc{};
+  int T = 0, G = 0, Kc = 0, Kpad = 0;
+  PFN_encodeTiled encode = nullptr;
+  __half* wconv = nullptr;
+  float *cls = nullptr, *pos = nullptr, *lnpre_g = nullptr, *lnpre_b = nullptr, *lnpost_g = nullptr, *lnpost_b = nullptr;
+  __half* wout = nullptr;   // [out_dim, width]
+  std::vector<LayerW> layers;
+  std::vector<void*> allocs;
+  // workspaces for `cap` images
+  int cap = 0;
+  float* x = nullptr;       // [cap*T, W] fp32 residual
+  __half* h = nullptr;      // [cap*T, W]
+  __half* qkv = nullptr;    // [cap*T, 3W]   (aliases: patch-embed output fp32 [cap*(T-1), W])
+  __half* gbuf = nullptr;   // [cap*T, mlp]  (aliases: im2col A0 fp16 [cap*(T-1), Kpad])
+  __half* pooled = nullptr; // [cap, W]
+  float* proj_out = nullptr;// [cap, out_dim]
+  float* in_stage = nullptr; size_t in_stage_bytes = 0;
+  float* out_stage = nullptr; size_t out_stage_bytes = 0;
+  bool attn_simple = false;
+  bool smem_attr_set = false;
+};
+
+static int32_t make_tmap(hmsg_ctx* ctx, VitState* vs, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = vs->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return ctx->fail(HMSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+  return HMSG_OK;
+}
+
+static int32_t get_encoder(hmsg_ctx* ctx, PFN_encodeTiled* out) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || !fn) return ctx->fail(HMSG_ERR_CUDA, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+  *out = (PFN_encodeTiled)fn;
+  return HMSG_OK;
+}
+
+template <int EPI>
+static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_f16<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
+    if (e != cudaSuccess) return ctx->fail(HMSG_ERR_CUDA, std::string("gemm smem attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
+  int grid = std::min(tiles, ctx->sm_count);
+  k_gemm_f16<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(ta, tb, g);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+// C = A[M,K] * Wt[N,K]^T with epilogue
+static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const __half* Wt, int M, int N, int K, const float* bias, void* out,
+                    int ldo) {
+  if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
+  CUtensorMap ta, tb;
+  int32_t rc;
+  if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
+  if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, BN))) return rc;
+  GemmArgs g{M, N, K, bias, out, ldo, vs->desc.quick_gelu};
+  switch (epi) {
+    case EPI_F16_BIAS: return launch_gemm_t<EPI_F16_BIAS>(ctx, ta, tb, g);
+    case EPI_F16_BIAS_GELU: return launch_gemm_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, g);
+    case EPI_F32_RESIDUAL: return launch_gemm_t<EPI_F32_RESIDUAL>(ctx, ta, tb, g);
+    default: return launch_gemm_t<EPI_F32_STORE>(ctx, ta, tb, g);
+  }
+}
+
+int32_t vit_destroy(hmsg_ctx* ctx) {
+  VitState* vs = ctx->vit;
+  if (!vs) return HMSG_OK;
+  for (void* p : vs->allocs) cudaFree(p);
+  free_dev(vs->x); free_dev(vs->h); free_dev(vs->qkv); free_dev(vs->gbuf); free_dev(vs->pooled); free_dev(vs->proj_out);
+  free_dev(vs->in_stage); free_dev(vs->out_stage);
+  delete vs;
+  ctx->vit = nullptr;
+  return HMSG_OK;
+}
+
+template <typename T>
+static int32_t dalloc(hmsg_ctx* ctx, VitState* vs, T** p, size_t n) {
+  HMSG_CUDA(cudaMalloc((void**)p, n * sizeof(T)));
+  vs->allocs.push_back(*p);
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, const float* blob, int64_t blob_floats) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!desc || !blob) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: null argument");
+  const hmsg_vit_desc& d = *desc;
+  if (d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
+      (3 * d.width) % 256 != 0 || d.width % 256 != 0)
+    return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: unsupported ViT shape (need head_dim 64, width/mlp/out_dim multiples of 256)");
+  int G = d.image / d.patch, T = G * G + 1;
+  if (T > 64) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: more than 64 tokens per image is not supported yet (ViT-B/32 has 50)");
+  vit_destroy(ctx);
+  VitState* vs = new VitState();
+  ctx->vit = vs;
+  vs->desc = d; vs->G = G; vs->T = T; vs->Kc = 3 * d.patch * d.patch; vs->Kpad = (vs->Kc + 63) / 64 * 64;
+  int32_t rc = get_encoder(ctx, &vs->encode);
+  if (rc) return rc;
+  const int W = d.width;
+  int64_t expect = (int64_t)W * vs->Kc + W + (int64_t)T * W + 2 * W +
+                   (int64_t)d.layers * (2 * W + 3LL * W * W + 3 * W + (int64_t)W * W + W + 2 * W + (int64_t)d.mlp * W + d.mlp + (int64_t)W * d.mlp + W) +
+                   2 * W + (int64_t)W * d.out_dim;
+  if (blob_floats != expect)
+    return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: blob has " + std::to_string(blob_floats) + " floats, expected " + std::to_string(expect));
+  // stage the whole blob on the device once, then convert / slice
+  float* dblob = nullptr;
+  HMSG_CUDA(cudaMalloc((void**)&dblob, (size_t)blob_floats * 4));
+  vs->allocs.push_back(dblob);   // fp32 vectors are used in place
+  HMSG_CUDA(cudaMemcpyAsync(dblob, blob, (size_t)blob_floats * 4, cudaMemcpyHostToDevice, ctx->stream));
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = dblob + off; off += n; return p; };
+  auto to_f16 = [&](const float* src, __half** dst, size_t n) -> int32_t {
+    int32_t r = dalloc(ctx, vs, dst, n);
+    if (r) return r;
+    k_f32_to_f16<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(src, *dst, (long long)n);
+    HMSG_LAUNCH_CHECK();
+    return HMSG_OK;
+  };
+  {
+    float* cw = take((size_t)W * vs->Kc);
+    if ((rc = dalloc(ctx, vs, &vs->wconv, (size_t)W * vs->Kpad))) return rc;
+    long long n = (long long)W * vs->Kpad;
+    k_pad_weight<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(cw, vs->wconv, W, vs->Kc, vs->Kpad);
+    HMSG_LAUNCH_CHECK();
+  }
+  vs->cls = take(W); vs->pos = take((size_t)T * W); vs->lnpre_g = take(W); vs->lnpre_b = take(W);
+  vs->layers.resize(d.layers);
+  for (int l = 0; l < d.layers; l++) {
+    LayerW& L = vs->layers[l];
+    L.ln1_g = take(W); L.ln1_b = take(W);
+    float* wqkv = take(3LL * W * W); L.bqkv = take(3 * W);
+    float* wo = take((size_t)W * W); L.bo = take(W);
+    L.ln2_g = take(W); L.ln2_b = take(W);
+    float* wfc = take((size_t)d.mlp * W); L.bfc = take(d.mlp);
+    float* wpj = take((size_t)W * d.mlp); L.bproj = take(W);
+    if ((rc = to_f16(wqkv, &L.wqkv, 3LL * W * W))) return rc;
+    if ((rc = to_f16(wo, &L.wo, (size_t)W * W))) return rc;
+    if ((rc = to_f16(wfc, &L.wfc, (size_t)d.mlp * W))) return rc;
+    if ((rc = to_f16(wpj, &L.wproj, (size_t)W * d.mlp))) return rc;
+  }
+  vs->lnpost_g = take(W); vs->lnpost_b = take(W);
+  {
+    float* pj = take((size_t)W * d.out_dim);   // [W, out] (x @ proj) -> [out, W]
+    if ((rc = dalloc(ctx, vs, &vs->wout, (size_t)W * d.out_dim))) return rc;
+    long long n = (long long)W * d.out_dim;
+    k_f32_to_f16_T<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(pj, vs->wout, W, d.out_dim);
+    HMSG_LAUNCH_CHECK();
+  }
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (const char* e = getenv("HMSG_ATTN_SIMPLE")) vs->attn_simple = atoi(e) != 0;
+  return HMSG_OK;
+}
+
+static int32_t ensure_ws(hmsg_ctx* ctx, VitState* vs, int B) {
+  if (B <= vs->cap) return HMSG_OK;
+  free_dev(vs->x); free_dev(vs->h); free_dev(vs->qkv); free_dev(vs->gbuf); free_dev(vs->pooled); free_dev(vs->proj_out);
+  vs->cap = 0;
+  const hmsg_vit_desc& d = vs->desc;
+  size_t R = (size_t)B * vs->T, W = d.width;
+  size_t qkv_bytes = std::max(R * 3 * W * 2, (size_t)B * (vs->T - 1) * W * 4);
+  size_t g_bytes = std::max(R * (size_t)d.mlp * 2, (size_t)B * (vs->T - 1) * vs->Kpad * 2);
+  HMSG_CUDA(cudaMalloc((void**)&vs->x, R * W * 4));
+  HMSG_CUDA(cudaMalloc((void**)&vs->h, R * W * 2));
+  HMSG_CUDA(cudaMalloc((void**)&vs->qkv, qkv_bytes));
+  HMSG_CUDA(cudaMalloc((void**)&vs->gbuf, g_bytes));
+  HMSG_CUDA(cudaMalloc((void**)&vs->pooled, (size_t)B * W * 2));
+  HMSG_CUDA(cudaMalloc((void**)&vs->proj_out, (size_t)B * d.out_dim * 4));
+  vs->cap = B;
+  return HMSG_OK;
+}
+
+template <int NV>
+static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize) {
+  const hmsg_vit_desc& d = vs->desc;
+  const int W = d.width, T = vs->T, G = vs->G;
+  const long long R = (long long)B * T, RP = (long long)B * (T - 1);
+  int32_t rc;
+  __half* a0 = vs->gbuf;
+  float* patch = reinterpret_cast<float*>(vs->qkv);
+  if (vs->Kpad != vs->Kc) {
+    long long n = RP * (vs->Kpad - vs->Kc);
+    k_zero_pad_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a0, RP, vs->Kc, vs->Kpad);
+    HMSG_LAUNCH_CHECK();
+  }
+  k_im2col<<<(unsigned)(B * 3 * d.image), 256, 0, ctx->stream>>>(dx, a0, d.image, d.patch, G, vs->Kpad);
+  HMSG_LAUNCH_CHECK();
+  if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
+  k_embed_lnpre<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->x, R, T);
+  HMSG_LAUNCH_CHECK();
+  const float scale = 1.0f / sqrtf(64.0f);
+  for (int l = 0; l < d.layers; l++) {
+    const LayerW& L = vs->layers[l];
+    k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln1_g, L.ln1_b, vs->h, R, 1);
+    HMSG_LAUNCH_CHECK();
+    if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
+    if (vs->attn_simple) {
+      k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+    } else {
+      size_t sm = (size_t)4 * 3 * 64 * ATT_LD * 2;
+      if (!vs->smem_attr_set) {
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        vs->smem_attr_set = true;
+      }
+      long long pairs = (long long)B * d.heads;
+      k_attention_mma<<<(unsigned)((pairs + 3) / 4), 128, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+    }
+    HMSG_LAUNCH_CHECK();
+    if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->h, L.wo, (int)R, W, W, L.bo, vs->x, W))) return rc;
+    k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln2_g, L.ln2_b, vs->h, R, 1);
+    HMSG_LAUNCH_CHECK();
+    if ((rc = gemm(ctx, vs, EPI_F16_BIAS_GELU, vs->h, L.wfc, (int)R, d.mlp, W, L.bfc, vs->gbuf, d.mlp))) return rc;
+    if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->gbuf, L.wproj, (int)R, W, d.mlp, L.bproj, vs->x, W))) return rc;
+  }
+  // ln_post on the class token of every image, projection, L2 normalisation
+  k_layernorm_f16<NV><<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, vs->lnpost_g, vs->lnpost_b, vs->pooled, B, T);
+  HMSG_LAUNCH_CHECK();
+  if ((rc = gemm(ctx, vs, EPI_F32_STORE, vs->pooled, vs->wout, B, d.out_dim, W, nullptr, vs->proj_out, d.out_dim))) return rc;
+  k_l2norm_rows<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->proj_out, dout, B, d.out_dim, normalize);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+static int32_t forward_chunk(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize) {
+  switch (vs->desc.width / 128) {
+    case 6: return forward_chunk_t<6>(ctx, vs, dx, B, dout, normalize);
+    case 8: return forward_chunk_t<8>(ctx, vs, dx, B, dout, normalize);
+    case 10: return forward_chunk_t<10>(ctx, vs, dx, B, dout, normalize);
+    case 2: return forward_chunk_t<2>(ctx, vs, dx, B, dout, normalize);
+    case 4: return forward_chunk_t<4>(ctx, vs, dx, B, dout, normalize);
+  }
+  return ctx->fail(HMSG_ERR_ARG, "encoder: unsupported width");
+}
+
+// device-pointer entry used by the ingest pipeline (no staging)
+int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, int normalize) {
+  VitState* vs = ctx->vit;
+  if (!vs) return ctx->fail(HMSG_ERR_STATE, "encoder: call hmsg_encoder_load first");
+  int chunk_max = 2080;
+  if (const char* e = getenv("HMSG_ENC_CHUNK")) chunk_max = std::max(1, atoi(e));
+  int32_t rc = ensure_ws(ctx, vs, std::min(B, chunk_max));
+  if (rc) return rc;
+  size_t img = (size_t)3 * vs->desc.image * vs->desc.image;
+  for (int b0 = 0; b0 < B; b0 += chunk_max) {
+    int nb = std::min(chunk_max, B - b0);
+    if ((rc = forward_chunk(ctx, vs, dx + (size_t)b0 * img, nb, dout + (size_t)b0 * vs->desc.out_dim, normalize))) return rc;
+  }
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_encode_images(hmsg_ctx* ctx, const float* nchw, int32_t B, float* out, int32_t normalize, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  VitState* vs = ctx->vit;
+  if (!vs) return ctx->fail(HMSG_ERR_STATE, "hmsg_encode_images: call hmsg_encoder_load first");
+  if (!nchw || !out || B <= 0) return ctx->fail(HMSG_ERR_ARG, "hmsg_encode_images: bad argument");
+  if (on_device) return vit_encode_device(ctx, nchw, B, out, normalize);
+  size_t img = (size_t)3 * vs->desc.image * vs->desc.image;
+  int32_t rc;
+  if ((rc = ctx->reserve(&vs->in_stage, &vs->in_stage_bytes, (size_t)B * img * 4))) return rc;
+  if ((rc = ctx->reserve(&vs->out_stage, &vs->out_stage_bytes, (size_t)B * vs->desc.out_dim * 4))) return rc;
+  HMSG_CUDA(cudaMemcpyAsync(vs->in_stage, nchw, (size_t)B * img * 4, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = vit_encode_device(ctx, vs->in_stage, B, vs->out_stage, normalize))) return rc;
+  HMSG_CUDA(cudaMemcpyAsync(out, vs->out_stage, (size_t)B * vs->desc.out_dim * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_gemm_f16_debug(hmsg_ctx* ctx, const void* A, const void* Wt, float* C, int32_t M, int32_t N, int32_t K) {
+  if (!ctx) return HMSG_ERR_ARG;
+  VitState tmp;
+  int32_t rc = get_encoder(ctx, &tmp.encode);
+  if (rc) return rc;
+  tmp.desc.quick_gelu = 0;
+  rc = gemm(ctx, &tmp, EPI_F32_STORE, (const __half*)A, (const __half*)Wt, M, N, K, nullptr, C, N);
+  if (rc) return rc;
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HMSG_OK;
+}

@@ -1,0 +1,526 @@
+// features.cu - A5/A6/A7 of the HMSG build path: per-mask feature fusion, the per-pixel
+// feature map restricted to node-winning pixels, node feature accumulation, and the
+// per-mask 3-D node sets.
+// Reference: fsr_vln/perception/models/sam_clip_feats_extractor.py:159-190;
+//            fsr_vln/memory/hmsg/graph/graph.py:404-415; dataloader/generic.py:140-190.
+//
+// The reference materialises a dense [H*W,d] fp32 map (629 MB) per frame, normalises it,
+// casts to fp16, copies 315 MB to the host and then keeps ONE row per touched node.  Here
+// the row is computed only for the pixel that wins its node (largest row-major pixel index
+// among the frame's valid pixels mapping to that node == the single-thread index_put_ order,
+// SURVEY H1), straight from the frame's M mask embeddings held in L2.
+#include "common.cuh"
+#include <algorithm>
+
+#define TPB 256
+int32_t geometry_nn_winner(hmsg_ctx* ctx, int64_t frame_begin, int n_frames);
+
+// ----------------------------------------------------------------------------- masks
+// maskbits[fb][p][w]: bit m of word w set iff pixel p belongs to mask 32*w+m
+__global__ void __launch_bounds__(TPB) k_masks_boxes(const uint16_t* depth, long long frame0, int H, int W, float scale, int M, int MW,
+                                                     const int32_t* boxes, uint32_t* maskbits) {
+  extern __shared__ int32_t sb[];
+  int fb = blockIdx.y;
+  for (int i = threadIdx.x; i < M * 4; i += blockDim.x) sb[i] = boxes[(long long)fb * M * 4 + i];
+  __syncthreads();
+  int HW = H * W;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int y = p / W, x = p - y * W;
+  bool ok = __fdiv_rn((float)depth[(frame0 + fb) * HW + p], scale) > 0.0f;
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = 0;
+    if (ok) {
+      int mend = min(32, M - w * 32);
+      for (int m = 0; m < mend; m++) {
+        const int32_t* b = sb + (w * 32 + m) * 4;
+        if (x >= b[0] && x < b[0] + b[2] && y >= b[1] && y < b[1] + b[3]) bits |= 1u << m;
+      }
+    }
+    maskbits[((long long)fb * HW + p) * MW + w] = bits;
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_masks_dense(const uint8_t* seg, int HW, int M, int MW, uint32_t* maskbits) {
+  int fb = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const uint8_t* s = seg + (long long)fb * M * HW + p;
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = 0;
+    int mend = min(32, M - w * 32);
+    for (int m = 0; m < mend; m++) bits |= (s[(long long)(w * 32 + m) * HW] ? 1u : 0u) << m;
+    maskbits[((long long)fb * HW + p) * MW + w] = bits;
+  }
+}
+
+// ----------------------------------------------------------------------------- A5 fuse
+// one block per frame.  feats [n, 2M+1, d]: rows 0..M-1 masked crops, M..2M-1 plain crops,
+// row 2M the full frame (F_g).  extractor.py:159-175.
+template <int DV>   // d = 128*DV ; a lane owns DV float4
+__global__ void __launch_bounds__(TPB) k_fuse(const float* __restrict__ feats, int M, float w_masked, float w_plain, float* __restrict__ Fp) {
+  extern __shared__ float sm[];      // phi[M]
+  const int d = 128 * DV;
+  int fb = blockIdx.x;
+  const float* base = feats + (long long)fb * (2 * M + 1) * d;
+  float* out = Fp + (long long)fb * M * d;
+  int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  float4 g[DV];
+  float gn = 0.f;
+#pragma unroll
+  for (int j = 0; j < DV; j++) {
+    g[j] = reinterpret_cast<const float4*>(base + (long long)(2 * M) * d)[lane + 32 * j];
+    gn += g[j].x * g[j].x + g[j].y * g[j].y + g[j].z * g[j].z + g[j].w * g[j].w;
+  }
+  for (int o = 16; o > 0; o >>= 1) gn += __shfl_xor_sync(0xffffffffu, gn, o);
+  gn = fmaxf(sqrtf(gn), 1e-6f);
+  // pass 1: F_l = normalize(w*masked + (1-w)*plain) -> stored in out ; phi = cos(F_l, F_g)
+  for (int m = wid; m < M; m += nw) {
+    float4 v[DV];
+    float nn = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV; j++) {
+      float4 a = reinterpret_cast<const float4*>(base + (long long)m * d)[lane + 32 * j];
+      float4 b = reinterpret_cast<const float4*>(base + (long long)(M + m) * d)[lane + 32 * j];
+      v[j].x = __fadd_rn(__fmul_rn(w_masked, a.x), __fmul_rn(w_plain, b.x));
+      v[j].y = __fadd_rn(__fmul_rn(w_masked, a.y), __fmul_rn(w_plain, b.y));
+      v[j].z = __fadd_rn(__fmul_rn(w_masked, a.z), __fmul_rn(w_plain, b.z));
+      v[j].w = __fadd_rn(__fmul_rn(w_masked, a.w), __fmul_rn(w_plain, b.w));
+      nn += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    float den = fmaxf(sqrtf(nn), 1e-12f);          // F.normalize eps
+    float dot = 0.f, ln = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV; j++) {
+      v[j].x = __fdiv_rn(v[j].x, den); v[j].y = __fdiv_rn(v[j].y, den); v[j].z = __fdiv_rn(v[j].z, den); v[j].w = __fdiv_rn(v[j].w, den);
+      dot += v[j].x * g[j].x + v[j].y * g[j].y + v[j].z * g[j].z + v[j].w * g[j].w;
+      ln += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+      reinterpret_cast<float4*>(out + (long long)m * d)[lane + 32 * j] = v[j];
+    }
+    for (int o = 16; o > 0; o >>= 1) { dot += __shfl_xor_sync(0xffffffffu, dot, o); ln += __shfl_xor_sync(0xffffffffu, ln, o); }
+    if (lane == 0) sm[m] = dot / (fmaxf(sqrtf(ln), 1e-6f) * gn);   // CosineSimilarity(eps=1e-6)
+  }
+  __syncthreads();
+  // softmax over the masks of the frame (dim=0)
+  float mx = -INFINITY;
+  for (int m = 0; m < M; m++) mx = fmaxf(mx, sm[m]);
+  float den = 0.f;
+  for (int m = 0; m < M; m++) den += expf(sm[m] - mx);
+  // pass 2: F_p = normalize(w_i*F_g + (1-w_i)*F_l)
+  for (int m = wid; m < M; m += nw) {
+    float wi = expf(sm[m] - mx) / den;
+    float om = 1.0f - wi;
+    float4 v[DV];
+    float nn = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV; j++) {
+      float4 l = reinterpret_cast<const float4*>(out + (long long)m * d)[lane + 32 * j];
+      v[j].x = __fadd_rn(__fmul_rn(wi, g[j].x), __fmul_rn(om, l.x));
+      v[j].y = __fadd_rn(__fmul_rn(wi, g[j].y), __fmul_rn(om, l.y));
+      v[j].z = __fadd_rn(__fmul_rn(wi, g[j].z), __fmul_rn(om, l.z));
+      v[j].w = __fadd_rn(__fmul_rn(wi, g[j].w), __fmul_rn(om, l.w));
+      nn += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+    }
+    for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+    float dn = fmaxf(sqrtf(nn), 1e-12f);
+#pragma unroll
+    for (int j = 0; j < DV; j++) {
+      v[j].x = __fdiv_rn(v[j].x, dn); v[j].y = __fdiv_rn(v[j].y, dn); v[j].z = __fdiv_rn(v[j].z, dn); v[j].w = __fdiv_rn(v[j].w, dn);
+      reinterpret_cast<float4*>(out + (long long)m * d)[lane + 32 * j] = v[j];
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------- A5/A6 scatter
+// One frame per launch (frames of a batch are launched in order => the fp32 accumulation
+// order per node equals the reference's frame order, and no atomics are needed: a node has
+// exactly one winning pixel per frame).  A warp scans 32 pixels, then cooperates on each
+// winner: lane owns DV float4 of the d-vector.
+__device__ __forceinline__ float round_half(float v) { return __half2float(__float2half_rn(v)); }
+
+template <int DV>
+__global__ void __launch_bounds__(TPB) k_scatter(const int32_t* __restrict__ pix_idx, const unsigned long long* __restrict__ win,
+                                                 const uint32_t* __restrict__ maskbits, const float* __restrict__ Fp, int HW, int M, int MW,
+                                                 uint32_t epoch, float* __restrict__ sum_feats, float* __restrict__ counter) {
+  const int d = 128 * DV;
+  int lane = threadIdx.x & 31;
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int nwarps = (gridDim.x * blockDim.x) >> 5;
+  for (int base = warp * 32; base < HW; base += nwarps * 32) {
+    int p = base + lane;
+    int n = (p < HW) ? pix_idx[p] : -1;
+    bool is_win = false;
+    if (n >= 0) is_win = (win[n] == (((unsigned long long)epoch << 32) | (unsigned)p));
+    unsigned ball = __ballot_sync(0xffffffffu, is_win);
+    while (ball) {
+      int s = __ffs(ball) - 1;
+      ball &= ball - 1;
+      int ns = __shfl_sync(0xffffffffu, n, s);
+      int ps = base + s;
+      float4 acc[DV];
+#pragma unroll
+      for (int j = 0; j < DV; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      for (int w = 0; w < MW; w++) {
+        uint32_t bits = __ldg(&maskbits[(long long)ps * MW + w]);
+        while (bits) {
+          int m = __ffs(bits) - 1 + 32 * w;
+          bits &= bits - 1;
+          any = true;
+          const float4* row = reinterpret_cast<const float4*>(Fp + (long long)m * d);
+#pragma unroll
+          for (int j = 0; j < DV; j++) {
+            float4 v = __ldg(&row[lane + 32 * j]);
+            acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;   // outfeat[idx] += F_p[i] in mask order
+          }
+        }
+      }
+      if (any) {
+        float nn = 0.f;
+#pragma unroll
+        for (int j = 0; j < DV; j++) nn += acc[j].x * acc[j].x + acc[j].y * acc[j].y + acc[j].z * acc[j].z + acc[j].w * acc[j].w;
+        for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        float den = fmaxf(sqrtf(nn), 1e-12f);       // extractor.py:188 F.normalize
+        float4* dst = reinterpret_cast<float4*>(sum_feats + (long long)ns * d);
+#pragma unroll
+        for (int j = 0; j < DV; j++) {
+          float4 cur = dst[lane + 32 * j];
+          cur.x += round_half(__fdiv_rn(acc[j].x, den));   // extractor.py:189 .half(); graph.py:410
+          cur.y += round_half(__fdiv_rn(acc[j].y, den));
+          cur.z += round_half(__fdiv_rn(acc[j].z, den));
+          cur.w += round_half(__fdiv_rn(acc[j].w, den));
+          dst[lane + 32 * j] = cur;
+        }
+      }
+      if (lane == 0) counter[ns] += 1.0f;          // graph.py:411 (once per frame per node)
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_finalize_feats(const float* __restrict__ sum_feats, const float* __restrict__ counter, long long n, int d,
+                                                        float* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = n * (d / 4);
+  if (i >= total) return;
+  long long node = i / (d / 4);
+  float c = counter[node];
+  if (c == 0.0f) c = 1e-5f;                        // graph.py:413
+  float4 v = reinterpret_cast<const float4*>(sum_feats)[i];
+  v.x = __fdiv_rn(v.x, c); v.y = __fdiv_rn(v.y, c); v.z = __fdiv_rn(v.z, c); v.w = __fdiv_rn(v.w, c);
+  reinterpret_cast<float4*>(out)[i] = v;
+}
+
+// ----------------------------------------------------------------------------- A7 mask nodes
+// generic.py:162-190.  Mask pixels' points are bit-identical to the frame's points, so the
+// NN index of a mask pixel is pix_idx of the frame.  Per mask: min bound over the hit node
+// positions, re-voxelisation key = floor((c - (min - vs/2)) / vs), accumulation weighted by
+// pixel multiplicity.  Implemented as: (1) per-mask min bound (atomicMin on ordered doubles),
+// (2) emit (mask, key) -> 64-bit composite per mask pixel into an open-addressing hash table in
+// HBM with f64 accumulators, (3) compaction on the host of the (small) table.
+struct MaskCell {
+  unsigned long long key;   // (mask+1) << 42 | i << 28 | j << 14 | k   (0 = empty)
+  double acc[6];
+  unsigned int cnt;
+  unsigned int pad;
+};
+
+__global__ void __launch_bounds__(TPB) k_mask_bounds(const int32_t* pix_idx, const uint32_t* maskbits, int HW, int MW, const double* nodes,
+                                                     long long* mb /*[M,3]*/) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int n = pix_idx[p];
+  if (n < 0) return;
+  double c[3] = {nodes[(long long)n * 3], nodes[(long long)n * 3 + 1], nodes[(long long)n * 3 + 2]};
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = maskbits[(long long)p * MW + w];
+    while (bits) {
+      int m = __ffs(bits) - 1 + 32 * w;
+      bits &= bits - 1;
+      for (int k = 0; k < 3; k++) atomicMin(&mb[m * 3 + k], d2ord(c[k]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_mask_accum(const int32_t* pix_idx, const uint32_t* maskbits, int HW, int MW, const double* nodes,
+                                                    const double* nrgb, const long long* mb, double vs, MaskCell* table,
+                                                    unsigned long long cap_mask, int* overflow) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int n = pix_idx[p];
+  if (n < 0) return;
+  double c[3] = {nodes[(long long)n * 3], nodes[(long long)n * 3 + 1], nodes[(long long)n * 3 + 2]};
+  double col[3] = {nrgb[(long long)n * 3], nrgb[(long long)n * 3 + 1], nrgb[(long long)n * 3 + 2]};
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = maskbits[(long long)p * MW + w];
+    while (bits) {
+      int m = __ffs(bits) - 1 + 32 * w;
+      bits &= bits - 1;
+      unsigned long long key = (unsigned long long)(m + 1) << 42;
+      bool bad = false;
+      for (int k = 0; k < 3; k++) {
+        long long o = mb[m * 3 + k];
+        long long bb = o >= 0 ? o : (o ^ 0x7FFFFFFFFFFFFFFFLL);
+        double mn = __longlong_as_double(bb);
+        double vmin = __dsub_rn(mn, __dmul_rn(vs, 0.5));
+        long long q = (long long)floor(cell_coord(c[k], vmin, vs));
+        if (q < 0 || q >= (1 << 14)) bad = true;
+        key |= (unsigned long long)q << (14 * (2 - k));
+      }
+      if (bad) { atomicExch(overflow, 2); continue; }
+      unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
+      unsigned long long slot = (h >> 20) & cap_mask;
+      for (unsigned long long probe = 0; probe <= cap_mask; probe++) {
+        unsigned long long prev = atomicCAS(&table[slot].key, 0ULL, key);
+        if (prev == 0ULL || prev == key) {
+          for (int k = 0; k < 3; k++) { atomicAdd(&table[slot].acc[k], c[k]); atomicAdd(&table[slot].acc[3 + k], col[k]); }
+          atomicAdd(&table[slot].cnt, 1u);
+          break;
+        }
+        slot = (slot + 1) & cap_mask;
+        if (probe == cap_mask) atomicExch(overflow, 1);
+      }
+    }
+  }
+}
+
+// ======================================================================================
+// host side
+// ======================================================================================
+static int32_t ensure_batch(hmsg_ctx* ctx, int n_frames, int M) {
+  if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "masks/features: call hmsg_radius_filter first");
+  if (M <= 0 || M > 1024) return ctx->fail(HMSG_ERR_ARG, "masks: M out of range");
+  size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
+  int MW = (M + 31) / 32;
+  int32_t rc;
+  if ((rc = ctx->reserve(&ctx->maskbits, &ctx->maskbits_bytes, (size_t)n_frames * hw * MW * 4))) return rc;
+  if ((rc = ctx->reserve(&ctx->pix_idx, &ctx->pix_idx_bytes, (size_t)n_frames * hw * 4))) return rc;
+  ctx->batch_M = M; ctx->batch_MW = MW; ctx->batch_n = n_frames;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (frame_begin < 0 || n <= 0 || frame_begin + n > ctx->nframes || !xywh) return ctx->fail(HMSG_ERR_ARG, "hmsg_masks_boxes: bad argument");
+  int32_t rc = ensure_batch(ctx, n, M);
+  if (rc) return rc;
+  const int32_t* dbox = xywh;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&ctx->boxes_stage, &ctx->boxes_stage_bytes, (size_t)n * M * 16))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(ctx->boxes_stage, xywh, (size_t)n * M * 16, cudaMemcpyHostToDevice, ctx->stream));
+    dbox = ctx->boxes_stage;
+  }
+  int HW = ctx->cam.H * ctx->cam.W;
+  dim3 grid((HW + TPB - 1) / TPB, n);
+  k_masks_boxes<<<grid, TPB, M * 16, ctx->stream>>>(ctx->depth, frame_begin, ctx->cam.H, ctx->cam.W, ctx->cam.scale, M, ctx->batch_MW, dbox,
+                                                    ctx->maskbits);
+  HMSG_LAUNCH_CHECK();
+  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->batch_begin = frame_begin;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const uint8_t* seg, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (frame_begin < 0 || n <= 0 || frame_begin + n > ctx->nframes || !seg) return ctx->fail(HMSG_ERR_ARG, "hmsg_masks_dense: bad argument");
+  int32_t rc = ensure_batch(ctx, n, M);
+  if (rc) return rc;
+  size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
+  const uint8_t* dseg = seg;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&ctx->seg_stage, &ctx->seg_stage_bytes, (size_t)n * M * hw))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(ctx->seg_stage, seg, (size_t)n * M * hw, cudaMemcpyHostToDevice, ctx->stream));
+    dseg = ctx->seg_stage;
+  }
+  dim3 grid((unsigned)((hw + TPB - 1) / TPB), n);
+  k_masks_dense<<<grid, TPB, 0, ctx->stream>>>(dseg, (int)hw, M, ctx->batch_MW, ctx->maskbits);
+  HMSG_LAUNCH_CHECK();
+  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->batch_begin = frame_begin;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_features_begin(hmsg_ctx* ctx, int32_t d) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_features_begin: call hmsg_radius_filter first");
+  if (d <= 0 || d % 128 != 0 || d > 1024) return ctx->fail(HMSG_ERR_ARG, "hmsg_features_begin: d must be a multiple of 128, <= 1024");
+  free_dev(ctx->sum_feats); free_dev(ctx->counter);
+  size_t nn = (size_t)std::max<int64_t>(ctx->n_nodes, 1);
+  HMSG_CUDA(cudaMalloc((void**)&ctx->sum_feats, nn * d * 4));
+  HMSG_CUDA(cudaMalloc((void**)&ctx->counter, nn * 4));
+  HMSG_CUDA(cudaMemsetAsync(ctx->sum_feats, 0, nn * d * 4, ctx->stream));
+  HMSG_CUDA(cudaMemsetAsync(ctx->counter, 0, nn * 4, ctx->stream));
+  ctx->d = d;
+  return HMSG_OK;
+}
+
+template <int DV>
+static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfeats, float w_masked, float w_plain) {
+  int HW = ctx->cam.H * ctx->cam.W;
+  k_fuse<DV><<<n, TPB, M * sizeof(float), ctx->stream>>>(dfeats, M, w_masked, w_plain, ctx->Fp);
+  HMSG_LAUNCH_CHECK();
+  int blocks = std::min((HW + TPB - 1) / TPB, ctx->sm_count * 8);
+  for (int fb = 0; fb < n; fb++) {
+    k_scatter<DV><<<blocks, TPB, 0, ctx->stream>>>(ctx->pix_idx + (size_t)fb * HW, ctx->win + (size_t)fb * ctx->n_nodes,
+                                                    ctx->maskbits + (size_t)fb * HW * ctx->batch_MW, ctx->Fp + (size_t)fb * M * 128 * DV, HW, M,
+                                                    ctx->batch_MW, ctx->epoch, ctx->sum_feats, ctx->counter);
+    HMSG_LAUNCH_CHECK();
+  }
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const float* feats, float maskedd_weight,
+                                     float* F_p_out, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: call hmsg_features_begin first");
+  if (ctx->batch_begin != frame_begin || ctx->batch_n != n || ctx->batch_M != M)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: masks of this batch were not set (hmsg_masks_*)");
+  if (!feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_fuse_scatter: null feats");
+  int d = ctx->d;
+  int32_t rc;
+  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
+  if (ctx->epoch == 0 || ctx->epoch == 0xFFFFFFFFu) {   // first use / wrap: clear tags
+    HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream));
+    ctx->epoch = 0;
+  }
+  ctx->epoch++;
+  if ((rc = ctx->reserve(&ctx->Fp, &ctx->Fp_bytes, (size_t)n * M * d * 4))) return rc;
+  const float* dfeats = feats;
+  size_t fbytes = (size_t)n * (2 * M + 1) * d * 4;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&ctx->feats_stage, &ctx->feats_stage_bytes, fbytes))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(ctx->feats_stage, feats, fbytes, cudaMemcpyHostToDevice, ctx->stream));
+    dfeats = ctx->feats_stage;
+  }
+  if ((rc = geometry_nn_winner(ctx, frame_begin, n))) return rc;
+  // numpy: maskedd_weight * a + (1 - maskedd_weight) * b with float32 arrays and a Python float:
+  // both scalars are rounded to float32 (extractor.py:159-160)
+  float w_masked = maskedd_weight;
+  float w_plain = (float)(1.0 - (double)maskedd_weight);
+  switch (d / 128) {
+    case 1: rc = launch_fuse_scatter<1>(ctx, n, M, dfeats, w_masked, w_plain); break;
+    case 2: rc = launch_fuse_scatter<2>(ctx, n, M, dfeats, w_masked, w_plain); break;
+    case 4: rc = launch_fuse_scatter<4>(ctx, n, M, dfeats, w_masked, w_plain); break;
+    case 6: rc = launch_fuse_scatter<6>(ctx, n, M, dfeats, w_masked, w_plain); break;
+    case 8: rc = launch_fuse_scatter<8>(ctx, n, M, dfeats, w_masked, w_plain); break;
+    default: return ctx->fail(HMSG_ERR_ARG, "hmsg_fuse_scatter: unsupported d (128,256,512,768,1024)");
+  }
+  if (rc) return rc;
+  if (F_p_out) {
+    HMSG_CUDA(cudaMemcpyAsync(F_p_out, ctx->Fp, (size_t)n * M * d * 4, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                              ctx->stream));
+  }
+  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_node_feats_finalize(hmsg_ctx* ctx, float* full_feats, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_finalize: call hmsg_features_begin first");
+  if (!full_feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_node_feats_finalize: null output");
+  long long n = ctx->n_nodes;
+  int d = ctx->d;
+  if (n == 0) return HMSG_OK;
+  float* dout = full_feats;
+  if (!on_device) {
+    int32_t rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, (size_t)n * d * 4);
+    if (rc) return rc;
+    dout = (float*)ctx->scratch;
+  }
+  long long total = n * (d / 4);
+  k_finalize_feats<<<(unsigned)((total + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->sum_feats, ctx->counter, n, d, dout);
+  HMSG_LAUNCH_CHECK();
+  if (!on_device) {
+    HMSG_CUDA(cudaMemcpyAsync(full_feats, dout, (size_t)n * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_node_feats_raw(hmsg_ctx* ctx, float* sum_features, float* counter) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_raw: call hmsg_features_begin first");
+  long long n = ctx->n_nodes;
+  if (n == 0) return HMSG_OK;
+  if (sum_features) HMSG_CUDA(cudaMemcpyAsync(sum_features, ctx->sum_feats, (size_t)n * ctx->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  if (counter) HMSG_CUDA(cudaMemcpyAsync(counter, ctx->counter, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, float** counter, int64_t* n_nodes, int32_t* d) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_device: call hmsg_features_begin first");
+  if (sum_features) *sum_features = ctx->sum_feats;
+  if (counter) *counter = ctx->counter;
+  if (n_nodes) *n_nodes = ctx->n_nodes;
+  if (d) *d = ctx->d;
+  return HMSG_OK;
+}
+
+// A7: one frame (must be inside the current mask batch).
+extern "C" int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t* offsets, double* xyz, double* rgb, int32_t* ijk) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (ctx->batch_begin < 0 || frame < ctx->batch_begin || frame >= ctx->batch_begin + ctx->batch_n)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_mask_nodes: frame is not in the current mask batch (hmsg_masks_*)");
+  if (!offsets || !(down_size > 0)) return ctx->fail(HMSG_ERR_ARG, "hmsg_mask_nodes: bad argument");
+  int M = ctx->batch_M, MW = ctx->batch_MW;
+  int HW = ctx->cam.H * ctx->cam.W;
+  int fb = (int)(frame - ctx->batch_begin);
+  // pixel -> node for this frame (no winner election needed): reuse k_nn_winner into pix_idx with a scratch win row
+  int32_t rc;
+  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)ctx->batch_n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
+  if (ctx->epoch == 0) { HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream)); }
+  ctx->epoch++;
+  if ((rc = geometry_nn_winner(ctx, ctx->batch_begin, ctx->batch_n))) return rc;
+  // count mask pixels to size the table
+  size_t cap = 1;
+  while (cap < (size_t)HW * 2) cap <<= 1;       // >= 2x the largest possible number of distinct (mask,cell) pairs per mask pixel
+  cap = std::min(cap * (size_t)std::max(1, std::min(M, 8)), (size_t)1 << 24);
+  size_t need = cap * sizeof(MaskCell) + (size_t)M * 3 * 8 + 64;
+  if ((rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, need))) return rc;
+  MaskCell* table = (MaskCell*)ctx->scratch;
+  long long* mb = (long long*)((char*)ctx->scratch + cap * sizeof(MaskCell));
+  int* overflow = (int*)(mb + M * 3);
+  HMSG_CUDA(cudaMemsetAsync(table, 0, cap * sizeof(MaskCell), ctx->stream));
+  std::vector<long long> init(M * 3);
+  {
+    double pinf = INFINITY; long long a; memcpy(&a, &pinf, 8);
+    for (auto& v : init) v = a;
+  }
+  HMSG_CUDA(cudaMemcpyAsync(mb, init.data(), M * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
+  HMSG_CUDA(cudaMemsetAsync(overflow, 0, 4, ctx->stream));
+  const int32_t* pidx = ctx->pix_idx + (size_t)fb * HW;
+  const uint32_t* mbits = ctx->maskbits + (size_t)fb * HW * MW;
+  k_mask_bounds<<<(HW + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(pidx, mbits, HW, MW, ctx->node_xyz, mb);
+  HMSG_LAUNCH_CHECK();
+  k_mask_accum<<<(HW + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(pidx, mbits, HW, MW, ctx->node_xyz, ctx->node_rgb, mb, down_size, table,
+                                                              (unsigned long long)cap - 1, overflow);
+  HMSG_LAUNCH_CHECK();
+  std::vector<MaskCell> host(cap);
+  int ov = 0;
+  HMSG_CUDA(cudaMemcpyAsync(host.data(), table, cap * sizeof(MaskCell), cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(&ov, overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ov == 1) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_mask_nodes: mask cell table overflow");
+  if (ov == 2) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_mask_nodes: a mask spans more than 2^14 cells per axis");
+  // ragged compaction + canonical (mask, i, j, k) order: the composite key sorts exactly that way
+  std::vector<const MaskCell*> used;
+  used.reserve(1024);
+  for (size_t i = 0; i < cap; i++) if (host[i].key) used.push_back(&host[i]);
+  std::sort(used.begin(), used.end(), [](const MaskCell* a, const MaskCell* b) { return a->key < b->key; });
+  for (int m = 0; m <= M; m++) offsets[m] = 0;
+  for (auto* c : used) offsets[(c->key >> 42)]++;        // key>>42 = mask+1
+  for (int m = 0; m < M; m++) offsets[m + 1] += offsets[m];
+  if (xyz || rgb || ijk) {
+    int64_t r = 0;
+    for (auto* c : used) {
+      double n = (double)c->cnt;
+      if (xyz) for (int k = 0; k < 3; k++) xyz[r * 3 + k] = c->acc[k] / n;
+      if (rgb) for (int k = 0; k < 3; k++) rgb[r * 3 + k] = c->acc[3 + k] / n;
+      if (ijk) { ijk[r * 3] = (int32_t)((c->key >> 28) & 0x3FFF); ijk[r * 3 + 1] = (int32_t)((c->key >> 14) & 0x3FFF); ijk[r * 3 + 2] = (int32_t)(c->key & 0x3FFF); }
+      r++;
+    }
+  }
+  return HMSG_OK;
+}

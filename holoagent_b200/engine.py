@@ -1,0 +1,308 @@
+"""HmsgEngine: thin host-side owner of one hmsg_ctx (one per GPU).  Every method maps
+one to one onto a C-ABI entry point of include/hmsg_b200.h; numpy arrays are host buffers,
+torch CUDA tensors are passed as device pointers (on_device=1)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import VitDesc, ptr
+
+VIT_BLOB_ORDER_HEAD = ["conv1.weight", "class_embedding", "positional_embedding", "ln_pre.weight", "ln_pre.bias"]
+VIT_BLOB_ORDER_LAYER = ["ln_1.weight", "ln_1.bias", "attn.in_proj_weight", "attn.in_proj_bias", "attn.out_proj.weight",
+                        "attn.out_proj.bias", "ln_2.weight", "ln_2.bias", "mlp.c_fc.weight", "mlp.c_fc.bias",
+                        "mlp.c_proj.weight", "mlp.c_proj.bias"]
+VIT_BLOB_ORDER_TAIL = ["ln_post.weight", "ln_post.bias", "proj"]
+
+
+def pack_vit_blob(state_dict, layers: int) -> np.ndarray:
+    """Flatten an open_clip ``VisionTransformer.state_dict()`` (or the synthetic one from
+    holoagent_b200.synth.make_vit_weights) into the float32 "encoder blob" hmsg_encoder_load
+    expects (order documented in DESIGN.md)."""
+    parts = []
+
+    def get(k):
+        v = state_dict[k]
+        if hasattr(v, "detach"):
+            v = v.detach().float().cpu().numpy()
+        return np.ascontiguousarray(v, dtype=np.float32).reshape(-1)
+
+    for k in VIT_BLOB_ORDER_HEAD:
+        parts.append(get(k))
+    for i in range(layers):
+        for k in VIT_BLOB_ORDER_LAYER:
+            parts.append(get(f"transformer.resblocks.{i}.{k}"))
+    for k in VIT_BLOB_ORDER_TAIL:
+        parts.append(get(k))
+    return np.concatenate(parts)
+
+
+def _is_dev(a) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+class HmsgError(RuntimeError):
+    pass
+
+
+class HmsgEngine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        rc = self.lib.hmsg_ctx_create(device, C.byref(h))
+        if rc != 0:
+            raise HmsgError(self.lib.hmsg_last_error(None).decode())
+        self.h = h
+        self.device = device
+        self.H = self.W = 0
+        self.d = 0
+        self.vit = None
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.hmsg_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise HmsgError(f"[{rc}] " + self.lib.hmsg_last_error(self.h).decode())
+
+    # ------------------------------------------------------------------ torch stream plumbing
+    def torch_stream(self):
+        """The ctx-owned CUDA stream as a torch ExternalStream (for events / ordering)."""
+        import torch
+        if getattr(self, "_ts", None) is None:
+            self._ts = torch.cuda.ExternalStream(self.stream, device=self.device)
+        return self._ts
+
+    def wait_torch(self):
+        """Order the ctx stream after everything queued on torch's current stream."""
+        import torch
+        self.torch_stream().wait_stream(torch.cuda.current_stream(self.device))
+
+    def torch_wait(self):
+        """Order torch's current stream after everything queued on the ctx stream."""
+        import torch
+        torch.cuda.current_stream(self.device).wait_stream(self.torch_stream())
+
+    # ------------------------------------------------------------------ misc
+    def sync(self):
+        self._ck(self.lib.hmsg_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.hmsg_stream(self.h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.hmsg_launch_count(self.h))
+
+    # ------------------------------------------------------------------ scene
+    def scene_begin(self, H, W, K, depth_scale, voxel_size, frame_capacity):
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
+        self._ck(self.lib.hmsg_scene_begin(self.h, H, W, ptr(K), float(depth_scale), float(voxel_size), int(frame_capacity)))
+        self.H, self.W = H, W
+
+    def add_frames(self, depth, rgb, poses):
+        dev = _is_dev(depth)
+        if not dev:
+            depth = np.ascontiguousarray(depth, dtype=np.uint16)
+            rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+            poses = np.ascontiguousarray(poses, dtype=np.float64)
+            n = depth.shape[0] if depth.ndim == 3 else 1
+        else:
+            n = depth.shape[0]
+            self.wait_torch()
+        self._ck(self.lib.hmsg_scene_add_frames(self.h, ptr(depth), ptr(rgb), ptr(poses), int(n), 1 if dev else 0))
+
+    @property
+    def num_frames(self):
+        return int(self.lib.hmsg_scene_num_frames(self.h))
+
+    def unproject_frame(self, frame):
+        hw = self.H * self.W
+        xyz = np.empty((hw, 3), np.float64); rgb = np.empty((hw, 3), np.float64); valid = np.empty(hw, np.uint8)
+        self._ck(self.lib.hmsg_unproject_frame(self.h, int(frame), ptr(xyz), ptr(rgb), ptr(valid)))
+        return xyz, rgb, valid.astype(bool)
+
+    def voxel_build(self):
+        n = C.c_int64(0)
+        mb = np.zeros(3, np.float64)
+        self._ck(self.lib.hmsg_voxel_build(self.h, C.byref(n), ptr(mb)))
+        self.n_voxels = n.value
+        return n.value, mb
+
+    def voxels_read(self):
+        n = self.n_voxels
+        xyz = np.empty((n, 3), np.float64); rgb = np.empty((n, 3), np.float64)
+        ijk = np.empty((n, 3), np.int32); cnt = np.empty(n, np.uint32)
+        self._ck(self.lib.hmsg_voxels_read(self.h, ptr(xyz), ptr(rgb), ptr(ijk), ptr(cnt)))
+        return xyz, rgb, ijk, cnt
+
+    def radius_filter(self, nb_points=1000, radius=1.0):
+        n = C.c_int64(0)
+        self._ck(self.lib.hmsg_radius_filter(self.h, int(nb_points), float(radius), C.byref(n)))
+        self.n_nodes = n.value
+        return n.value
+
+    def radius_counts(self):
+        c = np.empty(self.n_voxels, np.uint32)
+        self._ck(self.lib.hmsg_radius_counts_read(self.h, ptr(c)))
+        return c
+
+    def nodes_read(self):
+        n = self.n_nodes
+        xyz = np.empty((n, 3), np.float64); rgb = np.empty((n, 3), np.float64)
+        ijk = np.empty((n, 3), np.int32); vox = np.empty(n, np.int64)
+        self._ck(self.lib.hmsg_nodes_read(self.h, ptr(xyz), ptr(rgb), ptr(ijk), ptr(vox)))
+        return xyz, rgb, ijk, vox
+
+    def pixel_to_node(self, frame, want_dist=True):
+        hw = self.H * self.W
+        idx = np.empty(hw, np.int64)
+        dist = np.empty(hw, np.float64) if want_dist else None
+        self._ck(self.lib.hmsg_pixel_to_node(self.h, int(frame), ptr(idx), ptr(dist)))
+        return idx, dist
+
+    def points_to_node(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        idx = np.empty(len(xyz), np.int64); dist = np.empty(len(xyz), np.float64)
+        self._ck(self.lib.hmsg_points_to_node(self.h, ptr(xyz), len(xyz), ptr(idx), ptr(dist)))
+        return idx, dist
+
+    # ------------------------------------------------------------------ features
+    def features_begin(self, d):
+        self._ck(self.lib.hmsg_features_begin(self.h, int(d)))
+        self.d = d
+
+    def masks_dense(self, frame_begin, seg):
+        dev = _is_dev(seg)
+        if not dev:
+            seg = np.ascontiguousarray(seg, dtype=np.uint8)
+        n, M = seg.shape[0], seg.shape[1]
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_masks_dense(self.h, int(frame_begin), int(n), int(M), ptr(seg), 1 if dev else 0))
+
+    def masks_boxes(self, frame_begin, xywh):
+        dev = _is_dev(xywh)
+        if not dev:
+            xywh = np.ascontiguousarray(xywh, dtype=np.int32)
+        n, M = xywh.shape[0], xywh.shape[1]
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_masks_boxes(self.h, int(frame_begin), int(n), int(M), ptr(xywh), 1 if dev else 0))
+
+    def fuse_scatter(self, frame_begin, n, M, feats, maskedd_weight, Fp_out=None):
+        dev = _is_dev(feats)
+        if not dev:
+            feats = np.ascontiguousarray(feats, dtype=np.float32)
+            if Fp_out is None:
+                Fp_out = np.empty((n, M, self.d), np.float32)
+        else:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_fuse_scatter(self.h, int(frame_begin), int(n), int(M), ptr(feats), float(maskedd_weight), ptr(Fp_out),
+                                            1 if dev else 0))
+        return Fp_out
+
+    def node_feats_finalize(self, out=None):
+        dev = out is not None and _is_dev(out)
+        if out is None:
+            out = np.empty((self.n_nodes, self.d), np.float32)
+        self._ck(self.lib.hmsg_node_feats_finalize(self.h, ptr(out), 1 if dev else 0))
+        return out
+
+    def node_feats_raw(self):
+        s = np.empty((self.n_nodes, self.d), np.float32); c = np.empty(self.n_nodes, np.float32)
+        self._ck(self.lib.hmsg_node_feats_raw(self.h, ptr(s), ptr(c)))
+        return s, c
+
+    def node_feats_device(self):
+        ps, pc = C.c_void_p(), C.c_void_p()
+        n, d = C.c_int64(), C.c_int32()
+        self._ck(self.lib.hmsg_node_feats_device(self.h, C.byref(ps), C.byref(pc), C.byref(n), C.byref(d)))
+        return ps.value, pc.value, n.value, d.value
+
+    def mask_nodes(self, frame, down_size, M):
+        off = np.zeros(M + 1, np.int64)
+        self._ck(self.lib.hmsg_mask_nodes(self.h, int(frame), float(down_size), ptr(off), None, None, None))
+        tot = int(off[M])
+        xyz = np.empty((tot, 3), np.float64); rgb = np.empty((tot, 3), np.float64); ijk = np.empty((tot, 3), np.int32)
+        if tot:
+            self._ck(self.lib.hmsg_mask_nodes(self.h, int(frame), float(down_size), ptr(off), ptr(xyz), ptr(rgb), ptr(ijk)))
+        return off, xyz, rgb, ijk
+
+    # ------------------------------------------------------------------ encoder
+    def encoder_load(self, state_dict, image=224, patch=32, width=768, layers=12, heads=12, mlp=3072, out_dim=512, quick_gelu=False):
+        blob = pack_vit_blob(state_dict, layers)
+        desc = VitDesc(image, patch, width, layers, heads, mlp, out_dim, 1 if quick_gelu else 0)
+        self._ck(self.lib.hmsg_encoder_load(self.h, C.byref(desc), ptr(blob), blob.size))
+        self.vit = desc
+
+    def encode_images(self, x, normalize=True, out=None):
+        dev = _is_dev(x)
+        B = x.shape[0]
+        if not dev:
+            x = np.ascontiguousarray(x, dtype=np.float32)
+            out = np.empty((B, self.vit.out_dim), np.float32)
+        elif out is None:
+            import torch
+            out = torch.empty((B, self.vit.out_dim), dtype=torch.float32, device=x.device)
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_encode_images(self.h, ptr(x), int(B), ptr(out), 1 if normalize else 0, 1 if dev else 0))
+        if dev:
+            self.torch_wait()
+        return out
+
+    def gemm_debug(self, A_f16, W_f16, C_f32, M, N, K):
+        self.wait_torch()
+        self._ck(self.lib.hmsg_gemm_f16_debug(self.h, ptr(A_f16), ptr(W_f16), ptr(C_f32), M, N, K))
+
+    # ------------------------------------------------------------------ retrieval
+    def index_set(self, E, borrow=False):
+        dev = _is_dev(E)
+        if not dev:
+            E = np.ascontiguousarray(E, dtype=np.float32)
+        self._E_keepalive = E if borrow else None
+        self.index_N, self.index_d = E.shape
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_index_set(self.h, ptr(E), int(E.shape[0]), int(E.shape[1]), (2 if borrow else 1) if dev else 0))
+
+    def query_topk(self, Q, k, row_mask=None, ids=None, scores=None):
+        dev = _is_dev(Q)
+        nq = Q.shape[0]
+        if not dev:
+            Q = np.ascontiguousarray(Q, dtype=np.float32)
+            if row_mask is not None:
+                row_mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+            ids = np.empty((nq, k), np.int64); scores = np.empty((nq, k), np.float32)
+        elif ids is None:
+            import torch
+            ids = torch.empty((nq, k), dtype=torch.int64, device=Q.device)
+            scores = torch.empty((nq, k), dtype=torch.float32, device=Q.device)
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_query_topk(self.h, ptr(Q), int(nq), int(k), ptr(row_mask), ptr(ids), ptr(scores), 1 if dev else 0))
+        if dev:
+            self.torch_wait()
+        return ids, scores
+
+    def query_object(self, Q, query_id, k, row_mask=None):
+        """Q [n_req, Qp, d] host float32.  Returns ids [n_req,k], scores [n_req,k], n_found [n_req]."""
+        Q = np.ascontiguousarray(Q, dtype=np.float32)
+        n_req, Qp = Q.shape[0], Q.shape[1]
+        if row_mask is not None:
+            row_mask = np.ascontiguousarray(row_mask, dtype=np.uint8)
+        ids = np.empty((n_req, k), np.int64); scores = np.empty((n_req, k), np.float32); nf = np.empty(n_req, np.int32)
+        self._ck(self.lib.hmsg_query_object(self.h, ptr(Q), n_req, Qp, int(query_id), int(k), ptr(row_mask), ptr(ids), ptr(scores), ptr(nf), 0))
+        return ids, scores, nf

@@ -1,0 +1,187 @@
+/*
+ * hmsg_b200.h - C-ABI of libhmsg_b200.so: the B200-native (sm_100a) HMSG
+ * build-and-retrieve hot path of HorizonRobotics/HoloAgent (FSR-VLN).
+ *
+ * The reference has no FFI for this path: its boundary is a set of Python call
+ * signatures.  Each entry point below names the reference call it
+ * replaces (paths relative to /root/reference/fsr_vln/).  INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns int32_t status (HMSG_OK == 0); hmsg_last_error() gives text
+ *   - the caller owns every buffer it passes; the library owns all device memory in hmsg_ctx
+ *   - `on_device` != 0 means the pointer is a CUDA device pointer on the ctx's device
+ *     (inputs already resident in HBM); 0 means host memory (copied inside the call)
+ *   - a ctx is single-owner (one host thread at a time), one ctx per GPU, all work is
+ *     issued on the ctx-owned CUDA stream; calls that return data to host buffers
+ *     synchronise, calls with device outputs are asynchronous until hmsg_sync()
+ *   - there is NO CPU fallback: without a CUDA device hmsg_ctx_create fails
+ */
+#ifndef HMSG_B200_H_
+#define HMSG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HMSG_OK            0
+#define HMSG_ERR_ARG       1
+#define HMSG_ERR_CUDA      2
+#define HMSG_ERR_STATE     3
+#define HMSG_ERR_CAPACITY  4
+#define HMSG_ERR_NCCL      5
+
+typedef struct hmsg_ctx hmsg_ctx;
+
+/* ---- context ------------------------------------------------------------------------ */
+int32_t     hmsg_ctx_create(int32_t device, hmsg_ctx** out);
+int32_t     hmsg_ctx_destroy(hmsg_ctx* ctx);
+const char* hmsg_last_error(const hmsg_ctx* ctx);   /* ctx may be NULL: last create error */
+int32_t     hmsg_sync(hmsg_ctx* ctx);
+/* CUDA stream handle (cudaStream_t) all work is issued on - for event timing by the caller */
+void*       hmsg_stream(hmsg_ctx* ctx);
+/* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
+int64_t     hmsg_launch_count(const hmsg_ctx* ctx);
+int32_t     hmsg_version(void);
+
+/* ---- scene: resident frame store ---------------------------------------------------- */
+/* Graph.__init__ dataset + intrinsics (memory/hmsg/graph/graph.py:203-216;
+ * dataloader/generic.py:19-33): depth intrinsics K (row-major 3x3 float64), depth scale
+ * (horizon.py:38 -> 1000) and cfg.pipeline.voxel_size (graph.py:349). */
+int32_t hmsg_scene_begin(hmsg_ctx* ctx, int32_t H, int32_t W, const double K[9],
+                         float depth_scale, double voxel_size, int64_t frame_capacity);
+/* dataset[i] -> (rgb, depth, pose) (graph.py:343): uint16 depth [n,H,W], uint8 rgb [n,H,W,3],
+ * camera-to-world poses float64 [n,16] row-major.  Frames get ids in arrival order. */
+int32_t hmsg_scene_add_frames(hmsg_ctx* ctx, const uint16_t* depth, const uint8_t* rgb,
+                              const double* poses, int32_t n_frames, int32_t on_device);
+int64_t hmsg_scene_num_frames(const hmsg_ctx* ctx);
+
+/* A1  RGBDDataset.create_pcd (dataloader/generic.py:74-138).  Dense outputs in row-major
+ * pixel order: xyz [H*W,3] world float64, rgb [H*W,3] float64 (= u8/255.0), valid [H*W]
+ * (depth>0).  Rows of invalid pixels are zero.  The caller compacts (Python shim does). */
+int32_t hmsg_unproject_frame(hmsg_ctx* ctx, int64_t frame, double* xyz, double* rgb,
+                             uint8_t* valid);
+
+/* A2  `full_pcd += create_pcd(...)` over all frames + full_pcd.voxel_down_sample(voxel_size)
+ * (graph.py:339-348, Open3D 0.18.0 VoxelDownSample semantics).  Builds the voxel table in
+ * canonical ascending (i,j,k) order.  min_bound_out [3] = min over all points (nullable). */
+int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* min_bound_out);
+int32_t hmsg_voxels_read(hmsg_ctx* ctx, double* xyz, double* rgb, int32_t* ijk,
+                         uint32_t* count);           /* any pointer may be NULL */
+
+/* A3  pcd_denoise_dbscan(eps=.01,min_points=100) [identity, SURVEY H6] +
+ * remove_radius_outlier(nb_points, radius) + select_by_index (graph.py:352-358).
+ * After this call the node table (= Graph.full_pcd) is final. */
+int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double radius, int64_t* n_nodes);
+int32_t hmsg_radius_counts_read(hmsg_ctx* ctx, uint32_t* counts /* [n_voxels] */);
+int32_t hmsg_nodes_read(hmsg_ctx* ctx, double* xyz, double* rgb, int32_t* ijk,
+                        int64_t* voxel_index);        /* any pointer may be NULL */
+int64_t hmsg_num_nodes(const hmsg_ctx* ctx);
+
+/* A4  tree_pcd.query(np.asarray(pcd.points), k=1) (graph.py:362-364, :409; generic.py:181):
+ * exact nearest node for every valid pixel.  idx [H*W] (-1 for depth==0), dist [H*W] or NULL. */
+int32_t hmsg_pixel_to_node(hmsg_ctx* ctx, int64_t frame, int64_t* idx, double* dist);
+/* same query for arbitrary float64 points [n,3] (graph.py:458) */
+int32_t hmsg_points_to_node(hmsg_ctx* ctx, const double* xyz, int64_t n, int64_t* idx,
+                            double* dist);
+
+/* ---- feature ingest (A5, A6) -------------------------------------------------------- */
+/* counter/sum_features = zeros (graph.py:366-368).  d = clip_feat_dim, multiple of 128. */
+int32_t hmsg_features_begin(hmsg_ctx* ctx, int32_t d);
+
+/* SAM masks of a batch of consecutive frames ("segmentation" bool [M,H,W] per frame,
+ * perception/models/sam_clip_feats_extractor.py:117,184).  Either dense uint8 [n,M,H,W]
+ * (0/1) or XYWH rectangles int32 [n,M,4] meaning rect AND (depth>0) (synthetic). */
+int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                         const uint8_t* seg, int32_t on_device);
+int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                         const int32_t* xywh, int32_t on_device);
+
+/* A5+A6 for the batch whose masks were just set: given the encoder outputs of the batch,
+ * feats [n, 2M+1, d] float32 unit rows ordered (M masked crops, M plain crops, 1 full
+ * frame) = (cropped_masked_feats, cropped_feats, F_g) of extractor.py:147-158, computes
+ * F_p (extractor.py:159-175), the per-pixel map restricted to the pixels that win their
+ * node (extractor.py:177-190 incl. .half(); graph.py:404-411 with the last-writer-wins
+ * rule) and accumulates sum_features / counter.
+ * F_p_out [n,M,d] float32 (device if on_device else host; nullable). */
+int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                          const float* feats, float maskedd_weight, float* F_p_out,
+                          int32_t on_device);
+/* graph.py:413-415: counter[counter==0]=1e-5; full_feats = sum/counter -> [n_nodes,d] f32 */
+int32_t hmsg_node_feats_finalize(hmsg_ctx* ctx, float* full_feats, int32_t on_device);
+int32_t hmsg_node_feats_raw(hmsg_ctx* ctx, float* sum_features, float* counter);
+
+/* A7  RGBDDataset.create_3d_masks (dataloader/generic.py:140-190) for one frame whose masks
+ * were set: per mask the node positions hit by its pixels, re-voxelised (down_size) relative
+ * to the mask's own min bound with pixel multiplicity as weight.  Ragged output: offsets
+ * [M+1]; xyz/rgb [offsets[M],3] float64; ijk int32.  Call once with NULL data pointers to
+ * get offsets, then again with buffers. */
+int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t* offsets,
+                        double* xyz, double* rgb, int32_t* ijk);
+
+/* ---- A9 encoder: open_clip ViT visual tower ------------------------------------------ */
+typedef struct hmsg_vit_desc {
+  int32_t image;      /* 224 */
+  int32_t patch;      /* 32  */
+  int32_t width;      /* 768 */
+  int32_t layers;     /* 12  */
+  int32_t heads;      /* 12  */
+  int32_t mlp;        /* 3072 */
+  int32_t out_dim;    /* 512 */
+  int32_t quick_gelu; /* 0: erf GELU (open_clip ViT-B-32), 1: x*sigmoid(1.702x) (openai cfg) */
+} hmsg_vit_desc;
+
+/* weights: one float32 host blob in the order documented in DESIGN.md ("encoder blob"),
+ * i.e. open_clip VisionTransformer.state_dict() flattened by holoagent_b200.encoder.pack().
+ * Values are rounded to fp16 on upload (graph.py:117 precision='fp16'). */
+int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, const float* blob,
+                          int64_t blob_floats);
+/* clip_model.encode_image(x).float(); F.normalize(dim=-1) (utils/clip_utils.py:75-76, :91-92).
+ * x [B,3,image,image] float32 (already preprocessed); out [B,out_dim] float32 unit rows.
+ * normalize=0 returns the raw projection. */
+int32_t hmsg_encode_images(hmsg_ctx* ctx, const float* nchw, int32_t B, float* out,
+                           int32_t normalize, int32_t on_device);
+/* debug / unit test: C[M,N] (f32) = A[M,K] (f16 bits) * W[N,K]^T (f16 bits), device ptrs */
+int32_t hmsg_gemm_f16_debug(hmsg_ctx* ctx, const void* A, const void* W, float* C,
+                            int32_t M, int32_t N, int32_t K);
+
+/* ---- A8 (N3) crops + preprocess on device -------------------------------------------- */
+/* crop_all_bounding_boxs x2 + preprocess (utils/sam_utils.py:119-181; clip_utils.py:88-89)
+ * for the frames whose masks were set with hmsg_masks_*: writes [n, 2M+1, 3, 224, 224] f32
+ * into the ctx crop buffer (returned device pointer) in (masked, plain, full) order. */
+int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                        const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
+                        float** crops_dev_out);
+
+/* ---- A11 retrieval -------------------------------------------------------------------- */
+/* object_embs = np.array([obj.embedding ...]) (graph.py:3126): E [N,d] float32, copied into
+ * HBM (on_device 0/1) or borrowed without a copy (on_device 2). */
+int32_t hmsg_index_set(hmsg_ctx* ctx, const float* E, int64_t N, int32_t d, int32_t on_device);
+/* np.dot(q, E.T); np.argsort(...)[::-1][:k] per query row (graph.py:2196-2200, :3127-3133,
+ * :2888-2897).  Q [nq,d]; ids [nq,k] int64; scores [nq,k] float32 (descending; ties -> lower
+ * index).  row_mask: optional uint8 [N] device/host like Q (rows with 0 are skipped; the
+ * room filter of graph.py:3112-3122). */
+int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, int32_t k,
+                        const uint8_t* row_mask, int64_t* ids, float* scores,
+                        int32_t on_device);
+/* query_hmsg_object core with negative prompts (graph.py:3134-3151): for each request r the
+ * Qp rows Q[r] are (query + negatives); objects whose column-argmax is query_id, sorted by
+ * -max score, first k.  n_found[r] = number returned (< k possible; 0 => caller falls back to
+ * the plain top-k exactly as the reference keeps `top_index`, graph.py:3133). */
+int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_req, int32_t Qp,
+                          int32_t query_id, int32_t k, const uint8_t* row_mask,
+                          int64_t* ids, float* scores, int32_t* n_found, int32_t on_device);
+
+/* ---- multi-GPU ------------------------------------------------------------ */
+/* One ncclAllGather of this rank's F_p rows + partial sum_features/counter is issued by the
+ * caller's communicator; see holoagent_b200/dist.py.  The library exposes the device
+ * buffers so the host side can hand them to NCCL without a copy. */
+int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, float** counter,
+                               int64_t* n_nodes, int32_t* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HMSG_B200_H_ */

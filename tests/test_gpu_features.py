@@ -1,0 +1,72 @@
+"""GPU parity: A5/A6 (mask-feature fusion, last-writer-wins scatter) vs the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import hmsg_oracle as O
+from holoagent_b200 import synth
+from tests.scenes import scene, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+def _unit(rs, *shape):
+    x = rs.randn(*shape).astype(np.float32)
+    return x / np.linalg.norm(x, axis=-1, keepdims=True)
+
+
+@pytest.mark.parametrize("d,M,dense", [(512, 32, False), (256, 40, True)])
+def test_fuse_scatter(engine, d, M, dense):
+    sc = scene()
+    load_scene(engine, sc)
+    engine.voxel_build()
+    n_nodes = engine.radius_filter(150, 0.4)
+    nxyz, _, _, _ = engine.nodes_read()
+    tree = O.build_tree(nxyz)
+    engine.features_begin(d)
+    F = len(sc["ids"])
+    rs = np.random.RandomState(5)
+    w = 0.4418
+    sum_f = torch.zeros(n_nodes, d); cnt = torch.zeros(n_nodes, 1)
+    batches = [(0, 4), (4, 3), (7, F - 7)]
+    for (b0, nb) in batches:
+        feats = _unit(rs, nb, 2 * M + 1, d)
+        boxes = np.stack([synth.make_mask_boxes(int(sc["ids"][b0 + i]), sc["H"], sc["W"], M) for i in range(nb)])
+        segs = []
+        for i in range(nb):
+            valid = sc["depth"][b0 + i] > 0
+            s = np.zeros((M, sc["H"], sc["W"]), bool)
+            for m, (x, y, ww, hh) in enumerate(boxes[i]):
+                s[m, y:y + hh, x:x + ww] = valid[y:y + hh, x:x + ww]
+            segs.append(s)
+        if dense:
+            engine.masks_dense(b0, np.stack(segs).astype(np.uint8))
+        else:
+            engine.masks_boxes(b0, boxes)
+        Fp = engine.fuse_scatter(b0, nb, M, feats, w)
+        for i in range(nb):
+            oFp = O.fuse_mask_feats(feats[i, :M], feats[i, M:2 * M], feats[i, 2 * M:2 * M + 1], w)
+            assert np.allclose(Fp[i], oFp, rtol=0, atol=2e-6)
+            O.ingest_frame(sum_f, cnt, tree, n_nodes, sc["depth"][b0 + i], sc["rgb"][b0 + i], sc["poses"][b0 + i], sc["K"], sc["scale"], oFp, segs[i])
+    gs, gc = engine.node_feats_raw()
+    assert np.array_equal(gc, cnt.numpy().reshape(-1))               # counter: +1 per frame per touched node, exact
+    # fp16 rounding of a differently-rounded fp32 value may flip one half-ulp (4.9e-4 relative)
+    assert np.allclose(gs, sum_f.numpy(), rtol=0, atol=1e-3)
+    assert np.mean(np.abs(gs - sum_f.numpy()) > 1e-6) < 1e-3
+    full = engine.node_feats_finalize()
+    ofull = O.finalize_node_feats(sum_f, cnt)
+    hit = gc > 0
+    assert np.allclose(full[hit], ofull[hit], rtol=1e-3, atol=1e-3)
+    assert np.allclose(full[~hit], 0)
+
+
+def test_dense_map_equals_sparse_form():
+    """oracle self-check on CPU-sized input: dense extractor map == winners-only form"""
+    rs = np.random.RandomState(0)
+    H, W, M, d = 24, 32, 5, 128
+    segs = rs.rand(M, H, W) > 0.6
+    Fp = _unit(rs, M, d)
+    dense = O.pixel_feature_map(Fp, segs, H, W)
+    pix = np.arange(H * W)[::7]
+    sparse = O.pixel_features_at(Fp, segs.reshape(M, -1)[:, pix])
+    assert torch.equal(dense[pix], sparse)

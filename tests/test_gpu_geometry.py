@@ -1,0 +1,122 @@
+"""GPU parity: A1-A4 + A7 through the C-ABI vs the CPU oracle (bit-exact indices)."""
+import numpy as np
+import pytest
+
+from oracle import hmsg_oracle as O
+from tests.scenes import scene, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def built(engine):
+    sc = scene()
+    load_scene(engine, sc)
+    nv, mb = engine.voxel_build()
+    P, Cc = [], []
+    for f in range(len(sc["ids"])):
+        p, c, _ = O.create_pcd(sc["rgb"][f], sc["depth"][f], sc["K"], sc["scale"], sc["poses"][f])
+        P.append(p); Cc.append(c)
+    P = np.concatenate(P); Cc = np.concatenate(Cc)
+    ovx, ovc, oijk, inv = O.voxel_down_sample(P, Cc, sc["vs"])
+    return {"sc": sc, "nv": nv, "mb": mb, "P": P, "ovx": ovx, "ovc": ovc, "oijk": oijk, "inv": inv}
+
+
+def test_unproject_bit_exact(engine, built):
+    sc = built["sc"]
+    for f in (0, len(sc["ids"]) - 1):
+        xyz, rgb, valid = engine.unproject_frame(f)
+        p, c, m = O.create_pcd(sc["rgb"][f], sc["depth"][f], sc["K"], sc["scale"], sc["poses"][f])
+        assert np.array_equal(valid, m.reshape(-1))
+        assert np.array_equal(xyz[valid], p)          # float64, bit for bit
+        assert np.array_equal(rgb[valid], c)
+        assert not xyz[~valid].any()
+
+
+def test_voxel_table(engine, built):
+    xyz, rgb, ijk, cnt = engine.voxels_read()
+    assert built["nv"] == len(built["ovx"])
+    assert np.array_equal(built["mb"], built["P"].min(axis=0))           # global min bound, exact
+    assert np.array_equal(ijk, built["oijk"])                              # voxel keys, canonical order, exact
+    assert np.array_equal(cnt, np.bincount(built["inv"], minlength=len(cnt)))
+    # centroids: fp64 atomics change the summation order -> last-ulp differences only
+    assert np.allclose(xyz, built["ovx"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(rgb, built["ovc"], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("nb,radius", [(1000, 1.0), (150, 0.4)])
+def test_radius_filter_and_nn(engine, built, nb, radius):
+    sc = built["sc"]
+    n_nodes = engine.radius_filter(nb, radius)
+    vx, _, vijk, _ = engine.voxels_read()
+    counts = engine.radius_counts()
+    sub = np.random.RandomState(0).choice(len(vx), size=min(3000, len(vx)), replace=False)
+    from scipy.spatial import cKDTree
+    tree = cKDTree(vx)
+    r2 = radius * radius
+    for i in sub[:1500]:
+        js = np.asarray(tree.query_ball_point(vx[i], radius * (1 + 1e-9) + 1e-12))
+        dl = vx[js] - vx[i]
+        d2 = (dl[:, 0] * dl[:, 0] + dl[:, 1] * dl[:, 1]) + dl[:, 2] * dl[:, 2]
+        assert counts[i] == np.count_nonzero(d2 < r2)
+    keep = np.nonzero(counts > nb)[0]
+    nxyz, nrgb, nijk, nvox = engine.nodes_read()
+    assert n_nodes == len(keep) and np.array_equal(nvox, keep)
+    assert np.array_equal(nxyz, vx[keep]) and np.array_equal(nijk, vijk[keep])
+    if n_nodes == 0:
+        return
+    # A4: exact nearest node == scipy cKDTree on the same node table
+    nt = cKDTree(nxyz)
+    for f in (0, 3, len(sc["ids"]) - 1):
+        idx, dist = engine.pixel_to_node(f)
+        p, _, m = O.create_pcd(sc["rgb"][f], sc["depth"][f], sc["K"], sc["scale"], sc["poses"][f])
+        od, oi = nt.query(p, k=1)
+        valid = m.reshape(-1)
+        assert np.all(idx[~valid] == -1)
+        gi = idx[valid]
+        bad = np.nonzero(gi != oi)[0]
+        # only exact distance ties may differ
+        for b in bad:
+            assert np.sum((nxyz[gi[b]] - p[b]) ** 2) == np.sum((nxyz[oi[b]] - p[b]) ** 2)
+        assert len(bad) <= 2
+        assert np.allclose(dist[valid], od, rtol=1e-12, atol=1e-14)
+    # generic point query incl. points far outside the grid
+    rs = np.random.RandomState(1)
+    q = np.concatenate([rs.uniform(-3, 15, size=(500, 3)), nxyz[:50] + 1e-4])
+    gi, gd = engine.points_to_node(q)
+    od, oi = nt.query(q, k=1)
+    assert np.array_equal(gi, oi) and np.allclose(gd, od, rtol=1e-12, atol=1e-14)
+
+
+def test_end_to_end_geometry_vs_oracle(engine, built):
+    """independent pipelines: same node set, same indices"""
+    sc = built["sc"]
+    g = O.build_geometry(sc["depth"], sc["rgb"], sc["poses"], sc["K"], sc["scale"], sc["vs"], nb_points=150, radius=0.4)
+    n = engine.radius_filter(150, 0.4)
+    nxyz, nrgb, nijk, nvox = engine.nodes_read()
+    assert n == len(g["keep"]) and np.array_equal(nvox, g["keep"])
+    assert np.array_equal(nijk, g["node_ijk"])
+    assert np.allclose(nxyz, g["node_xyz"], rtol=1e-12, atol=1e-12)
+
+
+def test_mask_nodes(engine, built):
+    from holoagent_b200 import synth
+    sc = built["sc"]
+    engine.radius_filter(150, 0.4)
+    nxyz, nrgb, _, _ = engine.nodes_read()
+    from scipy.spatial import cKDTree
+    tree = cKDTree(nxyz)
+    f = 2
+    M = 12
+    masks = synth.make_masks(int(sc["ids"][f]), sc["depth"][f], M)
+    seg = np.stack([m["segmentation"] for m in masks]).astype(np.uint8)
+    engine.masks_dense(f, seg[None])
+    off, xyz, rgb, ijk = engine.mask_nodes(f, sc["vs"], M)
+    ref = O.create_3d_masks([m["segmentation"] for m in masks], sc["depth"][f], sc["K"], sc["scale"], sc["poses"][f], nxyz, nrgb, tree, sc["vs"])
+    for m in range(M):
+        p, c, k = ref[m]
+        a, b = off[m], off[m + 1]
+        assert b - a == len(p)
+        assert np.array_equal(ijk[a:b], k)
+        assert np.allclose(xyz[a:b], p, rtol=1e-12, atol=1e-12)
+        assert np.allclose(rgb[a:b], c, rtol=1e-12, atol=1e-12)
