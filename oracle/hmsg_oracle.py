@@ -439,12 +439,14 @@ def build_geometry(depths, rgbs, poses, K, scale, voxel_size, nb_points=1000, ra
             "min_bound": P.min(axis=0), "n_points": len(P)}
 
 
-def ingest_frame(sum_features, counter, tree, n_nodes, depth, rgb, pose, K, scale, F_p, segs):
+def ingest_frame(sum_features, counter, tree, n_nodes, depth, rgb, pose, K, scale, F_p, segs, idx=None):
     """graph.py:390, :404-411 for one frame given its mask embeddings F_p and masks.
     Uses the sparse-at-winners form of the dense feature map (equal by construction,
-    verified against the dense form in tests)."""
+    verified against the dense form in tests).  ``idx`` overrides the KD-tree result
+    (stage-wise parity: exact-distance ties are implementation-defined in cKDTree)."""
     pts, _, valid = create_pcd(rgb, depth, K, scale, pose)
-    _, idx = pixel_to_node(tree, pts)
+    if idx is None:
+        _, idx = pixel_to_node(tree, pts)
     nodes, pos = winners(idx, n_nodes)
     vpix = np.nonzero(valid.reshape(-1))[0]
     wpix = vpix[pos]

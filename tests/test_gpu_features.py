@@ -47,7 +47,12 @@ def test_fuse_scatter(engine, d, M, dense):
         for i in range(nb):
             oFp = O.fuse_mask_feats(feats[i, :M], feats[i, M:2 * M], feats[i, 2 * M:2 * M + 1], w)
             assert np.allclose(Fp[i], oFp, rtol=0, atol=2e-6)
-            O.ingest_frame(sum_f, cnt, tree, n_nodes, sc["depth"][b0 + i], sc["rgb"][b0 + i], sc["poses"][b0 + i], sc["K"], sc["scale"], oFp, segs[i])
+            # stage-wise: feed the oracle the GPU's pixel->node map (checked against cKDTree in
+            # test_gpu_geometry; exact-distance ties are implementation-defined there)
+            gidx, _ = engine.pixel_to_node(b0 + i, want_dist=False)
+            gidx = gidx[(sc["depth"][b0 + i] > 0).reshape(-1)]
+            O.ingest_frame(sum_f, cnt, tree, n_nodes, sc["depth"][b0 + i], sc["rgb"][b0 + i], sc["poses"][b0 + i], sc["K"], sc["scale"], oFp, segs[i],
+                           idx=gidx)
     gs, gc = engine.node_feats_raw()
     assert np.array_equal(gc, cnt.numpy().reshape(-1))               # counter: +1 per frame per touched node, exact
     # fp16 rounding of a differently-rounded fp32 value may flip one half-ulp (4.9e-4 relative)

@@ -8,6 +8,11 @@ from tests.scenes import scene, load_scene
 pytestmark = pytest.mark.gpu
 
 
+def O_sq(a, b):
+    d = a - b
+    return (d[0] * d[0] + d[1] * d[1]) + d[2] * d[2]
+
+
 @pytest.fixture(scope="module")
 def built(engine):
     sc = scene()
@@ -75,10 +80,13 @@ def test_radius_filter_and_nn(engine, built, nb, radius):
         assert np.all(idx[~valid] == -1)
         gi = idx[valid]
         bad = np.nonzero(gi != oi)[0]
-        # only exact distance ties may differ
+        # only exact float64 distance ties may differ (symmetric single-point voxels around a pixel
+        # whose own voxel was filtered out; cKDTree's choice there is traversal-order dependent,
+        # ours is the lower node index)
         for b in bad:
-            assert np.sum((nxyz[gi[b]] - p[b]) ** 2) == np.sum((nxyz[oi[b]] - p[b]) ** 2)
-        assert len(bad) <= 2
+            assert O_sq(nxyz[gi[b]], p[b]) == O_sq(nxyz[oi[b]], p[b])
+            assert gi[b] < oi[b]
+        assert len(bad) <= 1e-3 * len(gi)
         assert np.allclose(dist[valid], od, rtol=1e-12, atol=1e-14)
     # generic point query incl. points far outside the grid
     rs = np.random.RandomState(1)
