@@ -26,6 +26,8 @@ SIGNATURES = {
     "hmsg_sync": (_i32, [_vp]),
     "hmsg_stream": (_vp, [_vp]),
     "hmsg_launch_count": (_i64, [_vp]),
+    "hmsg_prof_enable": (_i32, [_vp, C.c_uint32]),
+    "hmsg_prof_read": (_i32, [_vp, _i32, C.POINTER(_f64), C.POINTER(_i64), C.POINTER(_f64)]),
     "hmsg_scene_begin": (_i32, [_vp, _i32, _i32, _vp, _f32, _f64, _i64]),
     "hmsg_scene_add_frames": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32]),
     "hmsg_scene_num_frames": (_i64, [_vp]),
@@ -49,6 +51,10 @@ SIGNATURES = {
     "hmsg_encode_images": (_i32, [_vp, _vp, _i32, _vp, _i32, _i32]),
     "hmsg_gemm_f16_debug": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32, _i32]),
     "hmsg_make_crops": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, C.POINTER(_vp)]),
+    "hmsg_crops_read": (_i32, [_vp, _i64, _vp]),
+    "hmsg_scene_reset_frames": (_i32, [_vp]),
+    "hmsg_node_feats_pack": (_i32, [_vp, _vp, _vp, _i64]),
+    "hmsg_node_feats_merge": (_i32, [_vp, _vp, _i32, _i64]),
     "hmsg_index_set": (_i32, [_vp, _vp, _i64, _i32, _i32]),
     "hmsg_query_topk": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32]),
     "hmsg_query_object": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),

@@ -43,6 +43,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   vit_destroy(ctx);
   knn_destroy(ctx);
+  crops_destroy(ctx);
   free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->d_bounds);
   free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt);
   free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt); free_dev(ctx->nbitmap); free_dev(ctx->nprefix); free_dev(ctx->node_xyz);
@@ -50,6 +51,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   free_dev(ctx->maskbits); free_dev(ctx->pix_idx); free_dev(ctx->win); free_dev(ctx->Fp); free_dev(ctx->feats_stage);
   free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage);
   if (ctx->scratch) cudaFree(ctx->scratch);
+  for (auto& pc : ctx->prof) for (auto e : pc.ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HMSG_OK;
@@ -65,3 +67,28 @@ extern "C" int32_t hmsg_sync(hmsg_ctx* ctx) {
 
 extern "C" void* hmsg_stream(hmsg_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" int64_t hmsg_launch_count(const hmsg_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+extern "C" int32_t hmsg_prof_enable(hmsg_ctx* ctx, uint32_t class_mask) {
+  if (!ctx) return HMSG_ERR_ARG;
+  ctx->prof_mask = class_mask;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_prof_read(hmsg_ctx* ctx, int32_t cls, double* ms, int64_t* launches, double* work) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (cls < 0 || cls >= PROF_NCLASS) return ctx->fail(HMSG_ERR_ARG, "hmsg_prof_read: bad class");
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ProfClass& p = ctx->prof[cls];
+  double tot = 0.0;
+  for (size_t i = 0; i + 1 < p.used; i += 2) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, p.ev[i], p.ev[i + 1]);
+    tot += t;
+  }
+  if (ms) *ms = tot;
+  if (launches) *launches = (int64_t)(p.used / 2);
+  if (work) *work = p.work;
+  p.used = 0;
+  p.work = 0.0;
+  return HMSG_OK;
+}

@@ -26,6 +26,14 @@
       return ctx->fail(HMSG_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e__)); \
   } while (0)
 
+// ---- optional per-kernel-class CUDA-event profiling (bench.py roofline numbers)
+enum { PROF_GEMM = 0, PROF_ATTN, PROF_ELTWISE, PROF_KNN, PROF_NN, PROF_SCATTER, PROF_GEOM, PROF_CROPS, PROF_NCLASS };
+struct ProfClass {
+  std::vector<cudaEvent_t> ev;   // pairs (begin, end)
+  size_t used = 0;
+  double work = 0.0;             // algorithmic flops or bytes accumulated
+};
+
 struct VitState;   // encoder.cu
 struct KnnState;   // knn.cu
 
@@ -112,6 +120,24 @@ struct hmsg_ctx {
   VitState* vit = nullptr;
   KnnState* knn = nullptr;
 
+  uint32_t prof_mask = 0;
+  ProfClass prof[PROF_NCLASS];
+  void prof_begin(int cls) {
+    if (!(prof_mask & (1u << cls))) return;
+    ProfClass& p = prof[cls];
+    if (p.used + 2 > p.ev.size()) {
+      for (int i = 0; i < 2; i++) { cudaEvent_t e; cudaEventCreate(&e); p.ev.push_back(e); }
+    }
+    cudaEventRecord(p.ev[p.used], stream);
+  }
+  void prof_end(int cls, double work) {
+    if (!(prof_mask & (1u << cls))) return;
+    ProfClass& p = prof[cls];
+    cudaEventRecord(p.ev[p.used + 1], stream);
+    p.used += 2;
+    p.work += work;
+  }
+
   int32_t fail(int32_t code, const std::string& msg) {
     err = msg;
     return code;
@@ -187,3 +213,5 @@ __device__ __forceinline__ double sqdist3(double ax, double ay, double az, doubl
 // sub-module entry points used by api.cu
 int32_t vit_destroy(hmsg_ctx* ctx);
 int32_t knn_destroy(hmsg_ctx* ctx);
+int32_t crops_destroy(hmsg_ctx* ctx);
+int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, int normalize);

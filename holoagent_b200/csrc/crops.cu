@@ -1,8 +1,309 @@
-// crops.cu - A8 / N3: crop + resize + open_clip preprocess on device (placeholder until the
-// bit-exact cv2/PIL resamplers land; the entry point reports that clearly).
+// crops.cu - A8 (N3): mask crops + open_clip preprocessing on device, bit-exact in uint8.
+// Reference: fsr_vln/memory/hmsg/utils/sam_utils.py:58-81 (increase_bbox_by_margin), :119-146
+// (crop_all_bounding_boxs: cv2.resize(crop,(512,512)) bilinear), :149-181 (crop_image/crop_bbox);
+// fsr_vln/memory/hmsg/utils/clip_utils.py:72-73,88-89 (open_clip preprocess: PIL bicubic
+// antialiased Resize(224) + CenterCrop + ToTensor + Normalize).
+//
+// Both resamplers are restated in their own fixed-point arithmetic (validated bit for bit
+// against cv2 4.13 / PIL 12.2 in tests/test_oracle.py):
+//   cv2 INTER_LINEAR 8U : 11-bit coefficients, horizontal pass in int32, vertical
+//                         (((b0*(S0>>4))>>16) + ((b1*(S1>>4))>>16) + 2) >> 2 ; x coefficients are zeroed
+//                         at the clamped borders, y coefficients are not (rows are clamped instead)
+//   PIL ImagingResample : precompute_coeffs in double (host), 22-bit fixed point, horizontal
+//                         pass then vertical pass with clip8 in between
+// Per frame the kernels emit [2M+1, 3, 224, 224] fp32: M background-blocked crops, M plain
+// crops (bbox + margin), the full frame (extractor.py:147-158 order).
 #include "common.cuh"
+#include <cmath>
+#include <map>
+#include <vector>
 
-extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t, int32_t, int32_t, const int32_t*, int32_t, int32_t, float**) {
+#define CROP_MID 512
+#define ROWS_PER_BLOCK 16
+
+struct ResampleTable {
+  int in_size = 0, out_size = 0, ksize = 0;
+  int* bounds = nullptr;   // [out][2] (xmin, count)
+  int* kk = nullptr;       // [out][ksize]
+};
+
+struct CropState {
+  std::map<std::pair<int, int>, ResampleTable> tables;
+  uint8_t* t1 = nullptr; size_t t1_bytes = 0;        // [crops, rows, 224, 3]
+  float* out = nullptr;  size_t out_bytes = 0;       // [crops, 3, 224, 224]
+  int32_t* boxes = nullptr; size_t boxes_bytes = 0;
+};
+static std::map<hmsg_ctx*, CropState*> g_crop_states;
+
+// PIL bicubic_filter (a = -0.5)
+static double bicubic_filter(double x) {
+  const double a = -0.5;
+  if (x < 0.0) x = -x;
+  if (x < 1.0) return ((a + 2.0) * x - (a + 3.0)) * x * x + 1;
+  if (x < 2.0) return (((x - 5) * x + 8) * x - 4) * a;
+  return 0.0;
+}
+
+// PIL precompute_coeffs + normalize_coeffs_8bpc (Resample.c), box = whole image
+static void pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int& ksize) {
+  double scale = (double)in_size / out_size, filterscale = scale;
+  if (filterscale < 1.0) filterscale = 1.0;
+  double support = 2.0 * filterscale;
+  ksize = (int)ceil(support) * 2 + 1;
+  bounds.assign((size_t)out_size * 2, 0);
+  kk.assign((size_t)out_size * ksize, 0);
+  std::vector<double> k(ksize);
+  for (int xx = 0; xx < out_size; xx++) {
+    double center = (xx + 0.5) * scale;
+    double ww = 0.0, ss = 1.0 / filterscale;
+    int xmin = (int)(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = (int)(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    for (int x = 0; x < xmax; x++) { double w = bicubic_filter((x + xmin - center + 0.5) * ss); k[x] = w; ww += w; }
+    for (int x = 0; x < xmax; x++) if (ww != 0.0) k[x] /= ww;
+    for (int x = 0; x < xmax; x++) {
+      double v = k[x];
+      kk[(size_t)xx * ksize + x] = (v < 0) ? (int)(-0.5 + v * (1 << 22)) : (int)(0.5 + v * (1 << 22));
+    }
+    bounds[xx * 2] = xmin; bounds[xx * 2 + 1] = xmax;
+  }
+}
+
+static int32_t get_table(hmsg_ctx* ctx, CropState* cs, int in_size, int out_size, ResampleTable** out) {
+  auto key = std::make_pair(in_size, out_size);
+  auto it = cs->tables.find(key);
+  if (it == cs->tables.end()) {
+    ResampleTable t; t.in_size = in_size; t.out_size = out_size;
+    std::vector<int> b, k;
+    pil_coeffs(in_size, out_size, b, k, t.ksize);
+    HMSG_CUDA(cudaMalloc((void**)&t.bounds, b.size() * 4));
+    HMSG_CUDA(cudaMalloc((void**)&t.kk, k.size() * 4));
+    HMSG_CUDA(cudaMemcpy(t.bounds, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+    HMSG_CUDA(cudaMemcpy(t.kk, k.data(), k.size() * 4, cudaMemcpyHostToDevice));
+    it = cs->tables.emplace(key, t).first;
+  }
+  *out = &it->second;
+  return HMSG_OK;
+}
+
+// cv2 resize coefficient for destination index d (INTER_LINEAR, 8U): source index + 11-bit pair
+__device__ __forceinline__ void cv_coef(int d, double scale, int src, bool clamp_coef, int& s, int& a0, int& a1) {
+  float f = (float)__dsub_rn(__dmul_rn((double)d + 0.5, scale), 0.5);
+  s = (int)floorf(f);
+  f = __fsub_rn(f, (float)s);
+  if (clamp_coef) {
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= src - 1) { f = 0.f; s = src - 1; }
+  }
+  a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+// ---- pass 1 (crops): cv2 bilinear to 512x512 fused with the PIL horizontal pass 512 -> 224.
+// grid = (512/ROWS_PER_BLOCK, 2M, n_frames); T1[crop][dy][ox][c]
+__global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ maskbits, long long frame0,
+                                                   int H, int W, int M, int MW, const int32_t* __restrict__ boxes, int margin,
+                                                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
+                                                   uint8_t* __restrict__ t1) {
+  __shared__ short s_xofs[CROP_MID];
+  __shared__ short s_a[CROP_MID][2];
+  __shared__ int s_h[2][CROP_MID * 3];
+  __shared__ uint8_t s_row[CROP_MID * 3];
+  const int fb = blockIdx.z, ci = blockIdx.y;
+  const bool masked = ci < M;
+  const int m = masked ? ci : ci - M;
+  const int32_t* b = boxes + ((long long)fb * M + m) * 4;
+  int x = b[0], y = b[1], w = b[2], h = b[3];
+  if (!masked) {   // increase_bbox_by_margin (sam_utils.py:58-81)
+    x -= margin; y -= margin; w += 2 * margin; h += 2 * margin;
+    if (x < 0) { w += x; x = 0; }
+    if (y < 0) { h += y; y = 0; }
+  }
+  // numpy slicing image[y:y+h, x:x+w] truncates at the image border
+  int x1 = min(x + w, W), y1 = min(y + h, H);
+  x = min(max(x, 0), W); y = min(max(y, 0), H);
+  const int cw = x1 - x, ch = y1 - y;
+  const long long crop_id = (long long)fb * (2 * M + 1) + ci;
+  uint8_t* dst = t1 + crop_id * (long long)CROP_MID * 224 * 3;
+  const int dy0 = blockIdx.x * ROWS_PER_BLOCK;
+  if (cw <= 0 || ch <= 0) {   // empty crop: cv2.resize would raise in the reference; emit zeros
+    for (int i = threadIdx.x; i < ROWS_PER_BLOCK * 224 * 3; i += blockDim.x) dst[(long long)dy0 * 224 * 3 + i] = 0;
+    return;
+  }
+  const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)cw));
+  const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)ch));
+  for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+    int s, a0, a1;
+    cv_coef(d, scale_x, cw, true, s, a0, a1);
+    s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
+  }
+  __syncthreads();
+  const uint8_t* img = rgb + (frame0 + fb) * (long long)H * W * 3;
+  const uint32_t* mb = maskbits + (long long)fb * H * W * MW;
+  int tag0 = -1, tag1 = -1;   // source rows currently held in s_h[0], s_h[1]
+  int sl0 = 0;                 // which slot holds "row0"
+  for (int r = 0; r < ROWS_PER_BLOCK; r++) {
+    const int dy = dy0 + r;
+    int sy, b0, b1;
+    cv_coef(dy, scale_y, ch, false, sy, b0, b1);
+    const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
+    // make slot sl0 hold r0 and slot 1-sl0 hold r1 (reuse across consecutive dy)
+    int need0 = 1, need1 = 1;
+    if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
+    else if (tag1 == r0) { sl0 ^= 1; tag0 = tag1; tag1 = -1; need0 = 0; }
+    for (int which = 0; which < 2; which++) {
+      if (which == 0 ? !need0 : !need1) continue;
+      const int sr = which == 0 ? r0 : r1;
+      int* hb = s_h[which == 0 ? sl0 : (sl0 ^ 1)];
+      const uint8_t* srow = img + ((long long)(y + sr) * W + x) * 3;
+      const uint32_t* mrow = mb + ((long long)(y + sr) * W + x) * MW;
+      for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+        int s0 = s_xofs[d], s1 = min(s0 + 1, cw - 1);
+        int a0 = s_a[d][0], a1 = s_a[d][1];
+        int k0 = 1, k1 = 1;
+        if (masked) {   // crop_image: image * segmentation (sam_utils.py:159)
+          k0 = (mrow[(long long)s0 * MW + (m >> 5)] >> (m & 31)) & 1;
+          k1 = (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) hb[d * 3 + c] = (int)srow[s0 * 3 + c] * k0 * a0 + (int)srow[s1 * 3 + c] * k1 * a1;
+      }
+    }
+    tag0 = r0; tag1 = r1;
+    __syncthreads();
+    const int* h0 = s_h[sl0];
+    const int* h1 = s_h[sl0 ^ 1];
+    for (int i = threadIdx.x; i < CROP_MID * 3; i += blockDim.x)
+      s_row[i] = (uint8_t)((((b0 * (h0[i] >> 4)) >> 16) + ((b1 * (h1[i] >> 4)) >> 16) + 2) >> 2);
+    __syncthreads();
+    // PIL horizontal pass 512 -> 224
+    for (int i = threadIdx.x; i < 224 * 3; i += blockDim.x) {
+      int ox = i / 3, c = i - ox * 3;
+      int xmin = __ldg(&bounds[ox * 2]), cnt = __ldg(&bounds[ox * 2 + 1]);
+      int acc = 1 << 21;
+      for (int k = 0; k < cnt; k++) acc += (int)s_row[(xmin + k) * 3 + c] * __ldg(&kk[ox * ksize + k]);
+      acc >>= 22;
+      dst[((long long)dy * 224 + ox) * 3 + c] = (uint8_t)min(max(acc, 0), 255);
+    }
+    __syncthreads();
+  }
+}
+
+// ---- pass 1 (full frame): PIL horizontal pass W -> nw, only columns [left, left+224)
+// grid = (H, n_frames); T1[crop][y][ox][c] with `rows_alloc` rows per crop
+__global__ void __launch_bounds__(256) k_frame_rows(const uint8_t* __restrict__ rgb, long long frame0, int H, int W, int M, int left,
+                                                    const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int rows_alloc,
+                                                    uint8_t* __restrict__ t1) {
+  const int fb = blockIdx.y, yy = blockIdx.x;
+  const uint8_t* srow = rgb + ((frame0 + fb) * (long long)H + yy) * W * 3;
+  const long long crop_id = (long long)fb * (2 * M + 1) + 2 * M;
+  uint8_t* dst = t1 + crop_id * (long long)rows_alloc * 224 * 3 + (long long)yy * 224 * 3;
+  for (int i = threadIdx.x; i < 224 * 3; i += blockDim.x) {
+    int ox = i / 3, c = i - ox * 3;
+    int sx = ox + left;
+    int xmin = __ldg(&bounds[sx * 2]), cnt = __ldg(&bounds[sx * 2 + 1]);
+    int acc = 1 << 21;
+    for (int k = 0; k < cnt; k++) acc += (int)srow[(xmin + k) * 3 + c] * __ldg(&kk[sx * ksize + k]);
+    acc >>= 22;
+    dst[i] = (uint8_t)min(max(acc, 0), 255);
+  }
+}
+
+// ---- pass 2: PIL vertical pass + ToTensor + Normalize -> fp32 planar
+// grid = (ceil(224*224/256), crops per frame in this launch, n_frames); crop = frame*(2M+1) + crop0 + blockIdx.y
+__global__ void __launch_bounds__(256) k_crop_cols(const uint8_t* __restrict__ t1, int rows_alloc, int top, const int* __restrict__ bounds,
+                                                   const int* __restrict__ kk, int ksize, int crop0, int crops_per_frame,
+                                                   float* __restrict__ out) {
+  const long long crop = (long long)blockIdx.z * crops_per_frame + crop0 + blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 224 * 224) return;
+  int oy = p / 224, ox = p - oy * 224;
+  int sy = oy + top;
+  int ymin = __ldg(&bounds[sy * 2]), cnt = __ldg(&bounds[sy * 2 + 1]);
+  const uint8_t* src = t1 + crop * (long long)rows_alloc * 224 * 3 + ((long long)ymin * 224 + ox) * 3;
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int k = 0; k < cnt; k++) {
+    int kv = __ldg(&kk[sy * ksize + k]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[c] += (int)src[(long long)k * 224 * 3 + c] * kv;
+  }
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    int v = min(max(acc[c] >> 22, 0), 255);
+    float f = __fdiv_rn((float)v, 255.0f);                       // ToTensor
+    f = __fdiv_rn(__fsub_rn(f, mean[c]), stdv[c]);               // Normalize
+    out[(crop * 3 + c) * (long long)(224 * 224) + p] = f;
+  }
+}
+
+int32_t crops_destroy(hmsg_ctx* ctx) {
+  auto it = g_crop_states.find(ctx);
+  if (it == g_crop_states.end()) return HMSG_OK;
+  CropState* cs = it->second;
+  for (auto& kv : cs->tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.kk); }
+  free_dev(cs->t1); free_dev(cs->out); free_dev(cs->boxes);
+  delete cs;
+  g_crop_states.erase(it);
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin,
+                                   int32_t on_device, float** crops_dev_out) {
   if (!ctx) return HMSG_ERR_ARG;
-  return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: device-side crop/resize is not built yet; pass preprocessed crops to hmsg_encode_images");
+  if (ctx->batch_begin != frame_begin || ctx->batch_n != n || ctx->batch_M != M)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: masks of this batch were not set (hmsg_masks_*)");
+  if (!xywh || !crops_dev_out) return ctx->fail(HMSG_ERR_ARG, "hmsg_make_crops: null argument");
+  const int H = ctx->cam.H, W = ctx->cam.W;
+  CropState*& cs = g_crop_states[ctx];
+  if (!cs) cs = new CropState();
+  int32_t rc;
+  // open_clip Resize(224): shorter side -> 224, the other int(224 * long / short); CenterCrop(224)
+  int nw, nh;
+  if (W <= H) { nw = 224; nh = (int)(224.0 * H / W); } else { nh = 224; nw = (int)(224.0 * W / H); }
+  if (W == H) { nw = nh = 224; }
+  const int left = (int)nearbyint((nw - 224) / 2.0), top = (int)nearbyint((nh - 224) / 2.0);
+  ResampleTable *tc, *tw, *th;
+  if ((rc = get_table(ctx, cs, CROP_MID, 224, &tc))) return rc;
+  if ((rc = get_table(ctx, cs, W, nw, &tw))) return rc;
+  if ((rc = get_table(ctx, cs, H, nh, &th))) return rc;
+  const int rows_alloc = std::max(CROP_MID, H);
+  const long long ncrops = (long long)n * (2 * M + 1);
+  if ((rc = ctx->reserve(&cs->t1, &cs->t1_bytes, (size_t)ncrops * rows_alloc * 224 * 3))) return rc;
+  if ((rc = ctx->reserve(&cs->out, &cs->out_bytes, (size_t)ncrops * 3 * 224 * 224 * 4))) return rc;
+  const int32_t* dbox = xywh;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&cs->boxes, &cs->boxes_bytes, (size_t)n * M * 16))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(cs->boxes, xywh, (size_t)n * M * 16, cudaMemcpyHostToDevice, ctx->stream));
+    dbox = cs->boxes;
+  }
+  ctx->prof_begin(PROF_CROPS);
+  k_crop_rows<<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
+                                                                                   bbox_margin, tc->bounds, tc->kk, tc->ksize, cs->t1);
+  HMSG_LAUNCH_CHECK();
+  k_frame_rows<<<dim3(H, n), 256, 0, ctx->stream>>>(ctx->rgb, frame_begin, H, W, M, left, tw->bounds, tw->kk, tw->ksize, rows_alloc, cs->t1);
+  HMSG_LAUNCH_CHECK();
+  const int pb = (224 * 224 + 255) / 256;
+  k_crop_cols<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, cs->out);
+  HMSG_LAUNCH_CHECK();
+  k_crop_cols<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, cs->out);
+  HMSG_LAUNCH_CHECK();
+  ctx->prof_end(PROF_CROPS, (double)ncrops * 3 * 224 * 224 * 4);
+  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  *crops_dev_out = cs->out;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_crops_read(hmsg_ctx* ctx, int64_t n_crops, float* host_out) {
+  if (!ctx) return HMSG_ERR_ARG;
+  auto it = g_crop_states.find(ctx);
+  if (it == g_crop_states.end() || !it->second->out) return ctx->fail(HMSG_ERR_STATE, "hmsg_crops_read: call hmsg_make_crops first");
+  size_t bytes = (size_t)n_crops * 3 * 224 * 224 * 4;
+  if (bytes > it->second->out_bytes) return ctx->fail(HMSG_ERR_ARG, "hmsg_crops_read: more crops requested than were made");
+  HMSG_CUDA(cudaMemcpyAsync(host_out, it->second->out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  return HMSG_OK;
 }

@@ -630,7 +630,9 @@ static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtenso
   }
   int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   int grid = std::min(tiles, ctx->sm_count);
+  ctx->prof_begin(PROF_GEMM);
   k_gemm_f16<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(ta, tb, g);
+  ctx->prof_end(PROF_GEMM, 2.0 * g.M * (double)g.N * g.K);
   HMSG_LAUNCH_CHECK();
   return HMSG_OK;
 }
@@ -771,7 +773,9 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     k_zero_pad_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a0, RP, vs->Kc, vs->Kpad);
     HMSG_LAUNCH_CHECK();
   }
+  ctx->prof_begin(PROF_ELTWISE);
   k_im2col<<<(unsigned)(B * 3 * d.image), 256, 0, ctx->stream>>>(dx, a0, d.image, d.patch, G, vs->Kpad);
+  ctx->prof_end(PROF_ELTWISE, (double)B * 3 * d.image * d.image * 6);
   HMSG_LAUNCH_CHECK();
   if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
   k_embed_lnpre<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->x, R, T);
@@ -779,9 +783,12 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
   const float scale = 1.0f / sqrtf(64.0f);
   for (int l = 0; l < d.layers; l++) {
     const LayerW& L = vs->layers[l];
+    ctx->prof_begin(PROF_ELTWISE);
     k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln1_g, L.ln1_b, vs->h, R, 1);
+    ctx->prof_end(PROF_ELTWISE, (double)R * W * 6);
     HMSG_LAUNCH_CHECK();
     if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
+    ctx->prof_begin(PROF_ATTN);
     if (vs->attn_simple) {
       k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     } else {
@@ -793,9 +800,12 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       long long pairs = (long long)B * d.heads;
       k_attention_mma<<<(unsigned)((pairs + 3) / 4), 128, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     }
+    ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();
     if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->h, L.wo, (int)R, W, W, L.bo, vs->x, W))) return rc;
+    ctx->prof_begin(PROF_ELTWISE);
     k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln2_g, L.ln2_b, vs->h, R, 1);
+    ctx->prof_end(PROF_ELTWISE, (double)R * W * 6);
     HMSG_LAUNCH_CHECK();
     if ((rc = gemm(ctx, vs, EPI_F16_BIAS_GELU, vs->h, L.wfc, (int)R, d.mlp, W, L.bfc, vs->gbuf, d.mlp))) return rc;
     if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->gbuf, L.wproj, (int)R, W, d.mlp, L.bproj, vs->x, W))) return rc;

@@ -360,12 +360,14 @@ static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfe
   k_fuse<DV><<<n, TPB, M * sizeof(float), ctx->stream>>>(dfeats, M, w_masked, w_plain, ctx->Fp);
   HMSG_LAUNCH_CHECK();
   int blocks = std::min((HW + TPB - 1) / TPB, ctx->sm_count * 8);
+  ctx->prof_begin(PROF_SCATTER);
   for (int fb = 0; fb < n; fb++) {
     k_scatter<DV><<<blocks, TPB, 0, ctx->stream>>>(ctx->pix_idx + (size_t)fb * HW, ctx->win + (size_t)fb * ctx->n_nodes,
                                                     ctx->maskbits + (size_t)fb * HW * ctx->batch_MW, ctx->Fp + (size_t)fb * M * 128 * DV, HW, M,
                                                     ctx->batch_MW, ctx->epoch, ctx->sum_feats, ctx->counter);
     HMSG_LAUNCH_CHECK();
   }
+  ctx->prof_end(PROF_SCATTER, 0.0);
   return HMSG_OK;
 }
 
@@ -522,5 +524,37 @@ extern "C" int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_siz
       r++;
     }
   }
+  return HMSG_OK;
+}
+
+// ---- multi-GPU merge: packed partial = [sum_features n*d | counter n | F_p rows]
+__global__ void __launch_bounds__(TPB) k_merge_partials(const float* __restrict__ gathered, int world, long long stride, long long count,
+                                                        float* __restrict__ sum_feats, float* __restrict__ counter, long long nd) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  float a = 0.f;
+  for (int r = 0; r < world; r++) a += gathered[(long long)r * stride + i];   // rank order: deterministic
+  if (i < nd) sum_feats[i] = a; else counter[i - nd] = a;
+}
+
+extern "C" int32_t hmsg_node_feats_pack(hmsg_ctx* ctx, float* dst, const float* Fp_rows, int64_t fp_floats) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats || !dst) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_pack: call hmsg_features_begin first");
+  size_t nd = (size_t)ctx->n_nodes * ctx->d;
+  HMSG_CUDA(cudaMemcpyAsync(dst, ctx->sum_feats, nd * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(dst + nd, ctx->counter, (size_t)ctx->n_nodes * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  if (Fp_rows && fp_floats > 0)
+    HMSG_CUDA(cudaMemcpyAsync(dst + nd + ctx->n_nodes, Fp_rows, (size_t)fp_floats * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_node_feats_merge(hmsg_ctx* ctx, const float* gathered, int32_t world, int64_t stride_floats) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->sum_feats || !gathered || world < 1) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_merge: bad state/argument");
+  long long nd = (long long)ctx->n_nodes * ctx->d, count = nd + ctx->n_nodes;
+  if (stride_floats < count) return ctx->fail(HMSG_ERR_ARG, "hmsg_node_feats_merge: stride smaller than the partial");
+  if (count == 0) return HMSG_OK;
+  k_merge_partials<<<(unsigned)((count + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(gathered, world, stride_floats, count, ctx->sum_feats, ctx->counter, nd);
+  HMSG_LAUNCH_CHECK();
   return HMSG_OK;
 }

@@ -548,6 +548,12 @@ extern "C" int32_t hmsg_scene_add_frames(hmsg_ctx* ctx, const uint16_t* depth, c
   return HMSG_OK;
 }
 
+extern "C" int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx) {
+  if (!ctx) return HMSG_ERR_ARG;
+  ctx->nframes = 0; ctx->voxels_built = false; ctx->nodes_built = false; ctx->batch_begin = -1;
+  return HMSG_OK;
+}
+
 extern "C" int64_t hmsg_scene_num_frames(const hmsg_ctx* ctx) { return ctx ? ctx->nframes : -1; }
 
 extern "C" int32_t hmsg_unproject_frame(hmsg_ctx* ctx, int64_t frame, double* xyz, double* rgb, uint8_t* valid) {
@@ -600,6 +606,7 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   if (!ctx) return HMSG_ERR_ARG;
   if (ctx->nframes <= 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_build: no frames");
   HMSG_CUDA(cudaSetDevice(ctx->device));
+  ctx->prof_begin(PROF_GEOM);
   // ---- pass 1: global bounds (graph.py:344-348: voxel keys are relative to the min bound of
   // the concatenated cloud)
   long long init[6];
@@ -664,6 +671,7 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   HMSG_LAUNCH_CHECK();
   k_write_ijk<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->bitmap, ctx->prefix, g, ctx->vox_ijk);
   HMSG_LAUNCH_CHECK();
+  ctx->prof_end(PROF_GEOM, (double)ctx->nframes * ctx->cam.H * ctx->cam.W * (2.0 + 2.0 + 5.0));
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->voxels_built = true; ctx->nodes_built = false;
   if (n_voxels) *n_voxels = ctx->n_voxels;
@@ -790,8 +798,10 @@ extern "C" int32_t hmsg_points_to_node(hmsg_ctx* ctx, const double* xyz, int64_t
 int32_t geometry_nn_winner(hmsg_ctx* ctx, int64_t frame_begin, int n_frames) {
   int HW = ctx->cam.H * ctx->cam.W;
   dim3 grid((HW + TPB - 1) / TPB, n_frames);
+  ctx->prof_begin(PROF_NN);
   k_nn_winner<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, frame_begin), ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->node_xyz, ctx->pix_idx,
                                              ctx->win, ctx->n_nodes, ctx->epoch);
+  ctx->prof_end(PROF_NN, (double)HW * n_frames * 14.0);
   HMSG_LAUNCH_CHECK();
   return HMSG_OK;
 }

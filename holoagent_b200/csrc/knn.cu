@@ -283,8 +283,10 @@ static int32_t launch_pass(hmsg_ctx* ctx, KnnState* st, const float* dq, int nq,
     cudaFuncSetAttribute(k_sim_topk<DV, BQ, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
+  ctx->prof_begin(PROF_KNN);
   k_sim_topk<DV, BQ, RW><<<st->grid, KNN_TPB, smem, ctx->stream>>>(st->E, st->N, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate,
                                                                     st->part_s, st->part_i);
+  ctx->prof_end(PROF_KNN, (double)st->N * st->d * 4.0);
   HMSG_LAUNCH_CHECK();
   return HMSG_OK;
 }

@@ -105,6 +105,19 @@ class HmsgEngine:
     def launches(self) -> int:
         return int(self.lib.hmsg_launch_count(self.h))
 
+    PROF = {"gemm": 0, "attn": 1, "eltwise": 2, "knn": 3, "nn": 4, "scatter": 5, "geom": 6, "crops": 7}
+
+    def prof_enable(self, *classes):
+        mask = 0
+        for c in classes:
+            mask |= 1 << self.PROF[c]
+        self._ck(self.lib.hmsg_prof_enable(self.h, mask))
+
+    def prof_read(self, cls):
+        ms, n, w = C.c_double(), C.c_int64(), C.c_double()
+        self._ck(self.lib.hmsg_prof_read(self.h, self.PROF[cls], C.byref(ms), C.byref(n), C.byref(w)))
+        return {"ms": ms.value, "launches": n.value, "work": w.value}
+
     # ------------------------------------------------------------------ scene
     def scene_begin(self, H, W, K, depth_scale, voxel_size, frame_capacity):
         K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
@@ -262,6 +275,50 @@ class HmsgEngine:
         if dev:
             self.torch_wait()
         return out
+
+    def encode_images_ptr(self, x_ptr: int, B: int, out, normalize=True):
+        """device pointer in (e.g. the ctx crop buffer), torch CUDA tensor out"""
+        self._ck(self.lib.hmsg_encode_images(self.h, C.c_void_p(x_ptr), int(B), ptr(out), 1 if normalize else 0, 1))
+        return out
+
+    # ------------------------------------------------------------------ crops (A8 / N3)
+    def has_device_crops(self) -> bool:
+        return True
+
+    def make_crops(self, frame_begin, n, M, xywh, bbox_margin) -> int:
+        """-> device pointer of [n, 2M+1, 3, 224, 224] float32 (masked, plain, full-frame order)"""
+        dev = _is_dev(xywh)
+        if not dev:
+            xywh = np.ascontiguousarray(xywh, dtype=np.int32)
+        else:
+            self.wait_torch()
+        out = C.c_void_p()
+        self._ck(self.lib.hmsg_make_crops(self.h, int(frame_begin), int(n), int(M), ptr(xywh), int(bbox_margin), 1 if dev else 0, C.byref(out)))
+        return out.value
+
+    def crops_read(self, n_crops):
+        a = np.empty((n_crops, 3, 224, 224), np.float32)
+        self._ck(self.lib.hmsg_crops_read(self.h, int(n_crops), ptr(a)))
+        return a
+
+    # ------------------------------------------------------------------ host-buffer variants used by bench e2e / multi-GPU
+    def scene_reset_frames(self):
+        self._ck(self.lib.hmsg_scene_reset_frames(self.h))
+
+    def add_frames_host(self, depth_t, rgb_t, poses_np):
+        """pinned torch CPU tensors (depth int16-viewed uint16, rgb uint8) + float64 poses"""
+        poses_np = np.ascontiguousarray(poses_np, dtype=np.float64)
+        self._ck(self.lib.hmsg_scene_add_frames(self.h, ptr(depth_t), ptr(rgb_t), ptr(poses_np), int(depth_t.shape[0]), 0))
+
+    def node_feats_finalize_host(self, out_t):
+        self._ck(self.lib.hmsg_node_feats_finalize(self.h, ptr(out_t), 0))
+
+    def pack_partials(self, dst, Fp_rows, fp_floats):
+        self.wait_torch()
+        self._ck(self.lib.hmsg_node_feats_pack(self.h, ptr(dst), ptr(Fp_rows), int(fp_floats)))
+
+    def merge_partials(self, gathered, world, stride):
+        self._ck(self.lib.hmsg_node_feats_merge(self.h, ptr(gathered), int(world), int(stride)))
 
     def gemm_debug(self, A_f16, W_f16, C_f32, M, N, K):
         self.wait_torch()

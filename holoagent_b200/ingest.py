@@ -1,0 +1,125 @@
+"""Frame-batched HMSG ingest driver: the loop body of Graph.create_feature_map
+(fsr_vln/memory/hmsg/graph/graph.py:339-415) expressed over C-ABI calls, for one rank.
+
+Multi-GPU (option B): every rank builds the (identical) node table from all
+frames - the geometry passes read 5 B/pixel and cost ~1 % of the step - and owns the frame
+batches b with b % world == rank for crops -> encoder -> fusion -> scatter.  One NCCL
+all-gather then carries each rank's packed [partial sum_features | counter | F_p rows]; the
+partials are summed in rank order by hmsg_node_feats_merge (deterministic)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+class IngestJob:
+    def __init__(self, eng, n_frames, frame_batch, M, d, boxes_dev, rank=0, world=1, crops="auto", maskedd_weight=0.4418, bbox_margin=50,
+                 nb_points=1000, radius=1.0):
+        import torch
+        self.torch = torch
+        self.eng, self.F, self.FB, self.M, self.d = eng, n_frames, frame_batch, M, d
+        self.rank, self.world = rank, world
+        self.boxes_dev = boxes_dev
+        self.w, self.margin, self.nb, self.radius = maskedd_weight, bbox_margin, nb_points, radius
+        self.batches = [(b0, min(frame_batch, n_frames - b0)) for b0 in range(0, n_frames, frame_batch)]
+        self.my_batches = [b for i, b in enumerate(self.batches) if i % world == rank]
+        self.n_local = sum(n for _, n in self.my_batches)
+        dev = boxes_dev.device
+        B = frame_batch * (2 * M + 1)
+        self.feats = torch.empty((B, d), dtype=torch.float32, device=dev)
+        self.Fp_local = torch.empty((max(self.n_local, 1), M, d), dtype=torch.float32, device=dev)
+        self.crops_mode = crops
+        if crops in ("auto", "device"):
+            if eng.has_device_crops():
+                self.crops_mode = "device"
+            elif crops == "device":
+                raise RuntimeError("device crops requested but hmsg_make_crops is not available")
+            else:
+                self.crops_mode = "synthetic"
+        self.syn_crops = None
+        if self.crops_mode == "synthetic":
+            g = torch.Generator(device=dev).manual_seed(1)
+            self.syn_crops = torch.randn((B, 3, 224, 224), generator=g, device=dev, dtype=torch.float32)
+        self.full_feats = None
+        self.gather_buf = None
+        self.host = None
+        self.h2d_bytes = self.d2h_bytes = 0
+
+    # ------------------------------------------------------------------
+    def _features_pass(self, boxes_host=None):
+        eng, M, d = self.eng, self.M, self.d
+        off = 0
+        for (b0, n) in self.my_batches:
+            B = n * (2 * M + 1)
+            if boxes_host is not None:
+                eng.masks_boxes(b0, boxes_host[b0:b0 + n])          # host XYWH -> staged H2D inside
+            else:
+                eng.masks_boxes(b0, self.boxes_dev[b0:b0 + n])
+            if self.crops_mode == "device":
+                crops_ptr = eng.make_crops(b0, n, M, self.boxes_dev[b0:b0 + n], self.margin)
+                eng.encode_images_ptr(crops_ptr, B, self.feats)
+            else:
+                eng.encode_images(self.syn_crops[:B], out=self.feats)
+            eng.fuse_scatter(b0, n, M, self.feats[:B].view(n, 2 * M + 1, d), self.w, Fp_out=self.Fp_local[off:off + n])
+            off += n
+
+    def _merge(self):
+        """all-gather of packed partials + deterministic rank-order sum (world > 1 only)."""
+        if self.world == 1:
+            return
+        import torch.distributed as dist
+        torch = self.torch
+        eng = self.eng
+        ps, pc, n, d = eng.node_feats_device()
+        nmax_local = -(-len(self.batches) // self.world) * self.FB
+        part = n * d + n
+        stride = part + nmax_local * self.M * d
+        if self.gather_buf is None or self.gather_buf.numel() != self.world * stride:
+            self.gather_buf = torch.empty(self.world * stride, dtype=torch.float32, device=self.boxes_dev.device)
+            self.send_buf = torch.zeros(stride, dtype=torch.float32, device=self.boxes_dev.device)
+        eng.pack_partials(self.send_buf, self.Fp_local, self.n_local * self.M * d)
+        eng.torch_wait()
+        dist.all_gather_into_tensor(self.gather_buf, self.send_buf)
+        eng.wait_torch()
+        eng.merge_partials(self.gather_buf, self.world, stride)
+
+    def step_device(self):
+        """One whole build with frames resident in HBM."""
+        eng = self.eng
+        eng.voxel_build()
+        eng.radius_filter(self.nb, self.radius)
+        eng.features_begin(self.d)
+        self._features_pass()
+        self._merge()
+        if self.full_feats is None or self.full_feats.shape[0] != eng.n_nodes:
+            self.full_feats = self.torch.empty((eng.n_nodes, self.d), dtype=self.torch.float32, device=self.boxes_dev.device)
+        eng.node_feats_finalize(self.full_feats)
+
+    # ------------------------------------------------------------------
+    def bind_host(self, host_depth, host_rgb, poses, boxes_np):
+        self.host = (host_depth, host_rgb, np.ascontiguousarray(poses, dtype=np.float64), np.ascontiguousarray(boxes_np, dtype=np.int32))
+        self.h2d_bytes = host_depth.numel() * 2 + host_rgb.numel() + poses.size * 8 + self.n_local * self.M * 16
+        self.host_out = None
+
+    def step_host(self):
+        """Same build through host buffers: pinned frames -> H2D, node features -> D2H."""
+        eng = self.eng
+        hd, hr, poses, boxes = self.host
+        eng.scene_reset_frames()
+        CH = 512
+        for f0 in range(0, self.F, CH):
+            f1 = min(self.F, f0 + CH)
+            eng.add_frames_host(hd[f0:f1], hr[f0:f1], poses[f0:f1])
+        eng.voxel_build()
+        eng.radius_filter(self.nb, self.radius)
+        eng.features_begin(self.d)
+        self._features_pass(boxes_host=boxes)
+        self._merge()
+        if self.host_out is None or self.host_out.shape[0] != eng.n_nodes:
+            self.host_out = self.torch.empty((eng.n_nodes, self.d), dtype=self.torch.float32).pin_memory()
+        eng.node_feats_finalize_host(self.host_out)
+        self.d2h_bytes = self.host_out.numel() * 4
+
+    def release(self):
+        self.syn_crops = None
+        self.gather_buf = None
+        self.feats = None

@@ -45,6 +45,13 @@ void*       hmsg_stream(hmsg_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t     hmsg_launch_count(const hmsg_ctx* ctx);
 int32_t     hmsg_version(void);
+/* Per-kernel-class device timing with CUDA events on the ctx stream (bench.py roofline).
+ * class: 0 gemm (work = flops), 1 attention, 2 elementwise/LN, 3 knn pass (work = bytes of E
+ * streamed), 4 pixel->node + winner, 5 feature scatter, 6 geometry passes, 7 crops.
+ * hmsg_prof_read synchronises, returns the summed event time / launch count / algorithmic
+ * work since the last read and resets the class. */
+int32_t     hmsg_prof_enable(hmsg_ctx* ctx, uint32_t class_mask);
+int32_t     hmsg_prof_read(hmsg_ctx* ctx, int32_t cls, double* ms, int64_t* launches, double* work);
 
 /* ---- scene: resident frame store ---------------------------------------------------- */
 /* Graph.__init__ dataset + intrinsics (memory/hmsg/graph/graph.py:203-216;
@@ -57,6 +64,8 @@ int32_t hmsg_scene_begin(hmsg_ctx* ctx, int32_t H, int32_t W, const double K[9],
 int32_t hmsg_scene_add_frames(hmsg_ctx* ctx, const uint16_t* depth, const uint8_t* rgb,
                               const double* poses, int32_t n_frames, int32_t on_device);
 int64_t hmsg_scene_num_frames(const hmsg_ctx* ctx);
+/* forget the stored frames (capacity and intrinsics stay): the next add starts at frame id 0 */
+int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx);
 
 /* A1  RGBDDataset.create_pcd (dataloader/generic.py:74-138).  Dense outputs in row-major
  * pixel order: xyz [H*W,3] world float64, rgb [H*W,3] float64 (= u8/255.0), valid [H*W]
@@ -147,13 +156,15 @@ int32_t hmsg_encode_images(hmsg_ctx* ctx, const float* nchw, int32_t B, float* o
 int32_t hmsg_gemm_f16_debug(hmsg_ctx* ctx, const void* A, const void* W, float* C,
                             int32_t M, int32_t N, int32_t K);
 
-/* ---- A8 (N3) crops + preprocess on device -------------------------------------------- */
+/* ---- A8 (N3) crops + preprocess on device (bit-exact cv2 bilinear + PIL antialiased bicubic) -------------------------------------------- */
 /* crop_all_bounding_boxs x2 + preprocess (utils/sam_utils.py:119-181; clip_utils.py:88-89)
  * for the frames whose masks were set with hmsg_masks_*: writes [n, 2M+1, 3, 224, 224] f32
  * into the ctx crop buffer (returned device pointer) in (masked, plain, full) order. */
 int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
                         const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
                         float** crops_dev_out);
+/* copy the first n_crops [3,224,224] float32 crops of the last hmsg_make_crops to host (tests) */
+int32_t hmsg_crops_read(hmsg_ctx* ctx, int64_t n_crops, float* host_out);
 
 /* ---- A11 retrieval -------------------------------------------------------------------- */
 /* object_embs = np.array([obj.embedding ...]) (graph.py:3126): E [N,d] float32, copied into
@@ -180,6 +191,12 @@ int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_req, int32_t 
  * buffers so the host side can hand them to NCCL without a copy. */
 int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, float** counter,
                                int64_t* n_nodes, int32_t* d);
+/* dst (device) <- [sum_features n*d | counter n | Fp_rows fp_floats]: the send buffer of the
+ * all-gather.  hmsg_node_feats_merge sums the `world` gathered partials (each `stride_floats`
+ * apart) in rank order into sum_features / counter. */
+int32_t hmsg_node_feats_pack(hmsg_ctx* ctx, float* dst, const float* Fp_rows, int64_t fp_floats);
+int32_t hmsg_node_feats_merge(hmsg_ctx* ctx, const float* gathered, int32_t world,
+                              int64_t stride_floats);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,38 @@
+"""GPU parity: A8 (N3) device-side crops + preprocessing vs real cv2 + PIL (bit-exact)."""
+import numpy as np
+import pytest
+
+from holoagent_b200 import synth
+from oracle import hmsg_oracle as O
+from tests.scenes import scene, load_scene
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("H,W", [(240, 320), (480, 640)])
+def test_crops_bit_exact(engine, H, W):
+    sc = scene(n_frames=3, H=H, W=W)
+    load_scene(engine, sc)
+    engine.voxel_build()
+    engine.radius_filter(50, 0.5)
+    M = 7
+    n = 2
+    boxes = np.stack([synth.make_mask_boxes(int(sc["ids"][f]) + 77, H, W, M) for f in range(n)])
+    boxes[0, 0] = (0, 0, 40, 30)                      # touches the top-left corner (margin clamp)
+    boxes[0, 1] = (W - 45, H - 37, 45, 37)            # touches the bottom-right corner (slicing truncation)
+    boxes[1, 2] = (5, H // 2, W - 10, 20)             # wide
+    engine.masks_boxes(0, boxes)
+    engine.make_crops(0, n, M, boxes, 50)
+    got = engine.crops_read(n * (2 * M + 1)).reshape(n, 2 * M + 1, 3, 224, 224)
+    for f in range(n):
+        valid = sc["depth"][f] > 0
+        masks = []
+        for (x, y, w, h) in boxes[f]:
+            seg = np.zeros((H, W), bool); seg[y:y + h, x:x + w] = valid[y:y + h, x:x + w]
+            masks.append({"bbox": [int(x), int(y), int(w), int(h)], "segmentation": seg})
+        img = sc["rgb"][f]
+        masked = O.crop_all_bounding_boxs(img, masks, True, 50)
+        plain = O.crop_all_bounding_boxs(img, masks, False, 50)
+        ref = [O.clip_preprocess(c).numpy() for c in masked] + [O.clip_preprocess(c).numpy() for c in plain] + [O.clip_preprocess(img).numpy()]
+        ref = np.stack(ref)
+        assert np.array_equal(got[f], ref), np.abs(got[f] - ref).max()

@@ -168,3 +168,19 @@ def test_vit_oracle_matches_transformers_clip():
         ref = m(pixel_values=x).image_embeds
     out = O.vit_forward(sd, x, heads=2)
     assert torch.allclose(out, ref, atol=2e-5), (out - ref).abs().max()
+
+
+def test_device_resampler_arithmetic_matches_cv2_and_pil():
+    """crops.cu restates cv2 INTER_LINEAR (8U) and PIL antialiased bicubic in fixed point; the
+    same arithmetic in numpy (tests/resample_ref.py) must equal the real libraries bit for bit."""
+    import cv2
+    from PIL import Image
+    from tests import resample_ref as R
+    rs = np.random.RandomState(0)
+    for (h, w) in [(3, 5), (57, 200), (150, 356), (356, 356), (480, 640), (700, 33), (1024, 1024)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        assert np.array_equal(cv2.resize(img, (512, 512)), R.cv_resize_linear(img, 512, 512)), (h, w)
+    for (h, w, nw, nh) in [(512, 512, 224, 224), (480, 640, 298, 224), (240, 320, 298, 224), (120, 160, 298, 224)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ref = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
+        assert np.array_equal(ref, R.pil_resize_bicubic(img, nw, nh)), (h, w)
