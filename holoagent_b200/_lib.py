@@ -55,6 +55,8 @@ SIGNATURES = {
     "hmsg_scene_reset_frames": (_i32, [_vp]),
     "hmsg_node_feats_pack": (_i32, [_vp, _vp, _vp, _i64]),
     "hmsg_node_feats_merge": (_i32, [_vp, _vp, _i32, _i64]),
+    "hmsg_query_scores": (_i32, [_vp, _vp, _i32, _vp, _i32]),
+    "hmsg_pixel_feature_map": (_i32, [_vp, _i64, _vp]),
     "hmsg_index_set": (_i32, [_vp, _vp, _i64, _i32, _i32]),
     "hmsg_query_topk": (_i32, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _i32]),
     "hmsg_query_object": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),

@@ -292,7 +292,6 @@ extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n
   k_crop_cols<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, cs->out);
   HMSG_LAUNCH_CHECK();
   ctx->prof_end(PROF_CROPS, (double)ncrops * 3 * 224 * 224 * 4);
-  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   *crops_dev_out = cs->out;
   return HMSG_OK;
 }

@@ -315,7 +315,6 @@ extern "C" int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t 
   k_masks_boxes<<<grid, TPB, M * 16, ctx->stream>>>(ctx->depth, frame_begin, ctx->cam.H, ctx->cam.W, ctx->cam.scale, M, ctx->batch_MW, dbox,
                                                     ctx->maskbits);
   HMSG_LAUNCH_CHECK();
-  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->batch_begin = frame_begin;
   return HMSG_OK;
 }
@@ -335,7 +334,6 @@ extern "C" int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t 
   dim3 grid((unsigned)((hw + TPB - 1) / TPB), n);
   k_masks_dense<<<grid, TPB, 0, ctx->stream>>>(dseg, (int)hw, M, ctx->batch_MW, ctx->maskbits);
   HMSG_LAUNCH_CHECK();
-  if (!on_device) HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->batch_begin = frame_begin;
   return HMSG_OK;
 }
@@ -556,5 +554,68 @@ extern "C" int32_t hmsg_node_feats_merge(hmsg_ctx* ctx, const float* gathered, i
   if (count == 0) return HMSG_OK;
   k_merge_partials<<<(unsigned)((count + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(gathered, world, stride_floats, count, ctx->sum_feats, ctx->counter, nd);
   HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+// ---- dense per-pixel feature map of ONE frame (extractor.py:177-190), only for API parity of
+// extract_feats_per_pixel's first return value: [H*W, d] fp16.  The ingest path never builds it.
+template <int DV>
+__global__ void __launch_bounds__(TPB) k_pixel_map(const uint32_t* __restrict__ maskbits, const float* __restrict__ Fp, int HW, int MW,
+                                                   __half* __restrict__ out) {
+  const int d = 128 * DV;
+  int lane = threadIdx.x & 31;
+  long long p = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (p >= HW) return;
+  float4 acc[DV];
+#pragma unroll
+  for (int j = 0; j < DV; j++) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = maskbits[p * MW + w];
+    while (bits) {
+      int m = __ffs(bits) - 1 + 32 * w;
+      bits &= bits - 1;
+      const float4* row = reinterpret_cast<const float4*>(Fp + (long long)m * d);
+#pragma unroll
+      for (int j = 0; j < DV; j++) { float4 v = __ldg(&row[lane + 32 * j]); acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w; }
+    }
+  }
+  float nn = 0.f;
+#pragma unroll
+  for (int j = 0; j < DV; j++) nn += acc[j].x * acc[j].x + acc[j].y * acc[j].y + acc[j].z * acc[j].z + acc[j].w * acc[j].w;
+  for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+  float den = fmaxf(sqrtf(nn), 1e-12f);
+#pragma unroll
+  for (int j = 0; j < DV; j++) {
+    __half2 a = __floats2half2_rn(__fdiv_rn(acc[j].x, den), __fdiv_rn(acc[j].y, den));
+    __half2 b = __floats2half2_rn(__fdiv_rn(acc[j].z, den), __fdiv_rn(acc[j].w, den));
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    reinterpret_cast<uint2*>(out + p * d)[lane + 32 * j] = pk;
+  }
+}
+
+extern "C" int32_t hmsg_pixel_feature_map(hmsg_ctx* ctx, int64_t frame, uint16_t* out_half) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (ctx->batch_begin < 0 || frame < ctx->batch_begin || frame >= ctx->batch_begin + ctx->batch_n || !ctx->Fp)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_pixel_feature_map: frame is not in the batch last passed to hmsg_fuse_scatter");
+  if (!out_half) return ctx->fail(HMSG_ERR_ARG, "hmsg_pixel_feature_map: null output");
+  int HW = ctx->cam.H * ctx->cam.W, d = ctx->d, M = ctx->batch_M, MW = ctx->batch_MW;
+  int fb = (int)(frame - ctx->batch_begin);
+  int32_t rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, (size_t)HW * d * 2);
+  if (rc) return rc;
+  __half* dout = (__half*)ctx->scratch;
+  const uint32_t* mb = ctx->maskbits + (size_t)fb * HW * MW;
+  const float* fp = ctx->Fp + (size_t)fb * M * d;
+  unsigned blocks = (unsigned)(((long long)HW * 32 + TPB - 1) / TPB);
+  switch (d / 128) {
+    case 1: k_pixel_map<1><<<blocks, TPB, 0, ctx->stream>>>(mb, fp, HW, MW, dout); break;
+    case 2: k_pixel_map<2><<<blocks, TPB, 0, ctx->stream>>>(mb, fp, HW, MW, dout); break;
+    case 4: k_pixel_map<4><<<blocks, TPB, 0, ctx->stream>>>(mb, fp, HW, MW, dout); break;
+    case 6: k_pixel_map<6><<<blocks, TPB, 0, ctx->stream>>>(mb, fp, HW, MW, dout); break;
+    case 8: k_pixel_map<8><<<blocks, TPB, 0, ctx->stream>>>(mb, fp, HW, MW, dout); break;
+    default: return ctx->fail(HMSG_ERR_ARG, "hmsg_pixel_feature_map: unsupported d");
+  }
+  HMSG_LAUNCH_CHECK();
+  HMSG_CUDA(cudaMemcpyAsync(out_half, dout, (size_t)HW * d * 2, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   return HMSG_OK;
 }

@@ -444,3 +444,46 @@ extern "C" int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_re
   }
   return HMSG_OK;
 }
+
+// dense similarity for small tables (room / label retrieval: graph.py:1452, :3204, :3250):
+// one warp per (query, row): scores[q][row] = dot(Q[q], E[row])
+__global__ void __launch_bounds__(256) k_sim_dense(const float* __restrict__ E, long long N, int d, const float* __restrict__ Q, int nq,
+                                                   float* __restrict__ out) {
+  long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (w >= N * nq) return;
+  int q = (int)(w / N);
+  long long row = w % N;
+  const float4* e = reinterpret_cast<const float4*>(E + row * d);
+  const float4* qq = reinterpret_cast<const float4*>(Q + (long long)q * d);
+  float a = 0.f;
+  for (int j = lane; j < d / 4; j += 32) {
+    float4 x = e[j], y = qq[j];
+    a = fmaf(x.x, y.x, a); a = fmaf(x.y, y.y, a); a = fmaf(x.z, y.z, a); a = fmaf(x.w, y.w, a);
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[(long long)q * N + row] = a;
+}
+
+extern "C" int32_t hmsg_query_scores(hmsg_ctx* ctx, const float* Q, int32_t nq, float* scores, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  KnnState* st = ctx->knn;
+  if (!st || !st->E) return ctx->fail(HMSG_ERR_STATE, "hmsg_query_scores: call hmsg_index_set first");
+  if (!Q || nq <= 0 || !scores) return ctx->fail(HMSG_ERR_ARG, "hmsg_query_scores: bad argument");
+  const float* dq; const uint8_t* dm;
+  int32_t rc = stage_inputs(ctx, st, Q, (size_t)nq * st->d, nullptr, on_device, &dq, &dm);
+  if (rc) return rc;
+  float* ds = scores;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&st->out_s, &st->out_s_bytes, (size_t)nq * st->N * 4))) return rc;
+    ds = st->out_s;
+  }
+  long long warps = (long long)st->N * nq;
+  k_sim_dense<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(st->E, st->N, st->d, dq, nq, ds);
+  HMSG_LAUNCH_CHECK();
+  if (!on_device) {
+    HMSG_CUDA(cudaMemcpyAsync(scores, ds, (size_t)nq * st->N * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return HMSG_OK;
+}

@@ -354,6 +354,17 @@ class HmsgEngine:
             self.torch_wait()
         return ids, scores
 
+    def query_scores(self, Q):
+        Q = np.ascontiguousarray(Q, dtype=np.float32).reshape(-1, self.index_d)
+        out = np.empty((Q.shape[0], self.index_N), np.float32)
+        self._ck(self.lib.hmsg_query_scores(self.h, ptr(Q), Q.shape[0], ptr(out), 0))
+        return out
+
+    def pixel_feature_map(self, frame):
+        out = np.empty((self.H * self.W, self.d), np.float16)
+        self._ck(self.lib.hmsg_pixel_feature_map(self.h, int(frame), ptr(out)))
+        return out
+
     def query_object(self, Q, query_id, k, row_mask=None):
         """Q [n_req, Qp, d] host float32.  Returns ids [n_req,k], scores [n_req,k], n_found [n_req]."""
         Q = np.ascontiguousarray(Q, dtype=np.float32)

@@ -11,6 +11,21 @@ from __future__ import annotations
 import numpy as np
 
 
+def shard_batches(n_frames: int, frame_batch: int, world: int, rank: int):
+    """Frame batches (begin, count) of the whole job and the ones rank `rank` owns (b % world == rank)."""
+    batches = [(b0, min(frame_batch, n_frames - b0)) for b0 in range(0, n_frames, frame_batch)]
+    return batches, [b for i, b in enumerate(batches) if i % world == rank]
+
+
+def packed_layout(n_nodes: int, d: int, n_frames: int, frame_batch: int, world: int, M: int):
+    """Per-rank send buffer of the single all-gather: [sum_features n*d | counter n | F_p rows].
+    Returns (partial_floats, stride_floats) - stride is padded to the largest per-rank F_p block."""
+    n_batches = -(-n_frames // frame_batch)
+    nmax_local = -(-n_batches // world) * frame_batch
+    part = n_nodes * d + n_nodes
+    return part, part + nmax_local * M * d
+
+
 class IngestJob:
     def __init__(self, eng, n_frames, frame_batch, M, d, boxes_dev, rank=0, world=1, crops="auto", maskedd_weight=0.4418, bbox_margin=50,
                  nb_points=1000, radius=1.0):
@@ -20,8 +35,7 @@ class IngestJob:
         self.rank, self.world = rank, world
         self.boxes_dev = boxes_dev
         self.w, self.margin, self.nb, self.radius = maskedd_weight, bbox_margin, nb_points, radius
-        self.batches = [(b0, min(frame_batch, n_frames - b0)) for b0 in range(0, n_frames, frame_batch)]
-        self.my_batches = [b for i, b in enumerate(self.batches) if i % world == rank]
+        self.batches, self.my_batches = shard_batches(n_frames, frame_batch, world, rank)
         self.n_local = sum(n for _, n in self.my_batches)
         dev = boxes_dev.device
         B = frame_batch * (2 * M + 1)
@@ -55,7 +69,7 @@ class IngestJob:
             else:
                 eng.masks_boxes(b0, self.boxes_dev[b0:b0 + n])
             if self.crops_mode == "device":
-                crops_ptr = eng.make_crops(b0, n, M, self.boxes_dev[b0:b0 + n], self.margin)
+                crops_ptr = eng.make_crops(b0, n, M, (boxes_host if boxes_host is not None else self.boxes_dev)[b0:b0 + n], self.margin)
                 eng.encode_images_ptr(crops_ptr, B, self.feats)
             else:
                 eng.encode_images(self.syn_crops[:B], out=self.feats)
@@ -70,9 +84,7 @@ class IngestJob:
         torch = self.torch
         eng = self.eng
         ps, pc, n, d = eng.node_feats_device()
-        nmax_local = -(-len(self.batches) // self.world) * self.FB
-        part = n * d + n
-        stride = part + nmax_local * self.M * d
+        part, stride = packed_layout(n, d, self.F, self.FB, self.world, self.M)
         if self.gather_buf is None or self.gather_buf.numel() != self.world * stride:
             self.gather_buf = torch.empty(self.world * stride, dtype=torch.float32, device=self.boxes_dev.device)
             self.send_buf = torch.zeros(stride, dtype=torch.float32, device=self.boxes_dev.device)

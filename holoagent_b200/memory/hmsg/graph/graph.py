@@ -1,0 +1,248 @@
+"""Drop-in for the hot half of fsr_vln/memory/hmsg/graph/graph.py: ``Graph.create_feature_map``
+(:262-415) and the retrieval cores ``query_hmsg_object`` (:3056-3162), ``query_object``
+(:3363-3481), ``query_graph`` (:2189-2214), ``identify_object`` (:1441-1454),
+``query_hmsg_room`` (:3164-3272) and ``query_room`` (:3277-3359), all on libhmsg_b200.so.
+
+Outside the hot path (and therefore injected by the caller instead of re-implemented):
+SAM (``mask_generator.generate``), the CLIP text tower (``clip_model.text_encoder`` or
+pre-computed ``query_feats``), floor/room segmentation, LLM/VLM reasoning, file I/O.  Method
+names, argument names/defaults and return shapes follow the reference so that
+application scripts and nav_agent's goal_pose_publisher call them unchanged.
+"""
+from __future__ import annotations
+
+from typing import List
+
+import numpy as np
+
+from holoagent_b200.memory.hmsg.utils.clip_utils import get_text_feats_multiple_templates
+from holoagent_b200.runtime import PointCloud, get_engine, to_o3d
+
+
+class _Cfg(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _ns(d):
+    if isinstance(d, dict):
+        return _Cfg({k: _ns(v) for k, v in d.items()})
+    return d
+
+
+class Graph:
+    def __init__(self, cfg, dataset=None, clip_model=None, preprocess=None, mask_generator=None, engine=None, clip_feat_dim=512):
+        """cfg: the reference's hydra config (dict / OmegaConf-like) - keys read here are the ones
+        the reference reads on the hot path: pipeline.voxel_size,
+        pipeline.skip_frames, pipeline.clip_bbox_margin, pipeline.clip_masked_weight,
+        pipeline.max_mask_distance.  dataset: an RGBDDataset-like object yielding
+        (rgb_image, depth_image, pose, rgb_intrinsics, depth_intrinsics) with .scale and
+        .depth_intrinsics (generic.py:19-33)."""
+        self.cfg = _ns(cfg) if isinstance(cfg, dict) else cfg
+        self.dataset = dataset
+        self.clip_model = clip_model
+        self.preprocess = preprocess
+        self.mask_generator = mask_generator
+        self.clip_feat_dim = clip_feat_dim
+        self.engine = engine or (clip_model.engine if clip_model is not None else get_engine(0))
+        self.full_pcd = PointCloud()
+        self.full_feats_array = None
+        self.mask_feats = []
+        self.mask_pcds = []
+        self.frames_feats = []
+        self.frames_pcd = []
+        self.objects = []
+        self.rooms = []
+        self.floors = []
+        self._index_key = None
+        self.frame_batch = 16
+
+    # ------------------------------------------------------------------ build (graph.py:262-415)
+    def create_feature_map(self, save_path=None):
+        if self.dataset is None:
+            print("No dataset loaded")          # graph.py:267-269
+            return
+        import torch
+        eng, p = self.engine, self.cfg.pipeline
+        skip = int(p.skip_frames)
+        ids = list(range(0, len(self.dataset), skip))
+        # ---- pass 1 (graph.py:339-345): frames -> resident HBM store
+        first = self.dataset[ids[0]]
+        depth0 = np.array(first[1])
+        H, W = depth0.shape
+        eng.scene_begin(H, W, np.asarray(self.dataset.depth_intrinsics, dtype=np.float64), float(self.dataset.scale), float(p.voxel_size), len(ids))
+        rgbs = []
+        for i in ids:
+            rgb_image, depth_image, pose, _, _ = self.dataset[i]
+            rgb = np.array(rgb_image).astype(np.uint8)
+            depth = np.array(depth_image).astype(np.uint16)
+            if rgb.shape[:2] != depth.shape[:2]:
+                import cv2
+                rgb = cv2.resize(rgb, (depth.shape[1], depth.shape[0]), interpolation=cv2.INTER_AREA)   # generic.py:98-104
+            eng.add_frames(depth[None], rgb[None], np.asarray(pose, dtype=np.float64).reshape(1, 16))
+            rgbs.append(rgb)
+        # ---- graph.py:348-358: voxel_down_sample, dbscan (identity), remove_radius_outlier
+        eng.voxel_build()
+        eng.radius_filter(1000, 1.0)
+        xyz, rgbc, _, _ = eng.nodes_read()
+        pc = PointCloud(xyz, rgbc)
+        self.full_pcd = to_o3d(pc)
+        frame_of = {i: k for k, i in enumerate(ids)}
+        try:
+            self.full_pcd._hmsg_engine = eng
+            self.full_pcd._hmsg_frame_of = frame_of.__getitem__
+        except AttributeError:          # open3d objects do not take attributes: keep the side table on self
+            pass
+        self._frame_of = frame_of
+        # ---- pass 2 (graph.py:373-411)
+        d = self.clip_feat_dim
+        eng.features_begin(d)
+        self.frames_pcd, self.frames_feats = [], []
+        dev = f"cuda:{eng.device}"
+        for b0 in range(0, len(ids), self.frame_batch):
+            chunk = ids[b0:b0 + self.frame_batch]
+            all_masks = [self.mask_generator.generate(rgbs[b0 + k]) for k in range(len(chunk))]   # SAM: outside the hot path
+            M = max(len(m) for m in all_masks)
+            if M == 0:
+                continue
+            n = len(chunk)
+            seg = np.zeros((n, M, H, W), np.uint8)
+            boxes = np.zeros((n, M, 4), np.int32)
+            for k, ms in enumerate(all_masks):
+                for j, m in enumerate(ms):
+                    seg[k, j] = np.asarray(m["segmentation"]).astype(np.uint8)
+                    boxes[k, j] = [int(v) for v in m["bbox"]]
+                for j in range(len(ms), M):       # pad with an empty mask on a 1-pixel box (never wins a pixel)
+                    boxes[k, j] = (0, 0, 1, 1)
+            eng.masks_dense(b0, seg)
+            crops_ptr = eng.make_crops(b0, n, M, boxes, int(p.clip_bbox_margin))
+            feats = torch.empty((n * (2 * M + 1), d), dtype=torch.float32, device=dev)
+            eng.encode_images_ptr(crops_ptr, n * (2 * M + 1), feats)
+            Fp = eng.fuse_scatter(b0, n, M, feats.view(n, 2 * M + 1, d), float(p.clip_masked_weight),
+                                  Fp_out=torch.empty((n, M, d), dtype=torch.float32, device=dev))
+            eng.torch_wait()
+            Fp = Fp.cpu()
+            for k, ms in enumerate(all_masks):
+                self.frames_feats.append(Fp[k, :len(ms)])
+                off, mx, mc, _ = eng.mask_nodes(b0 + k, float(p.voxel_size), M)
+                self.frames_pcd.append([to_o3d(PointCloud(mx[off[j]:off[j + 1]], mc[off[j]:off[j + 1]])) for j in range(len(ms))])
+        # ---- graph.py:413-415
+        self.full_feats_array = eng.node_feats_finalize()
+        return self.full_feats_array
+
+    # ------------------------------------------------------------------ retrieval plumbing
+    def _text(self, queries: List[str], query_feats=None):
+        if query_feats is not None:
+            return np.asarray(query_feats, dtype=np.float32).reshape(len(queries), -1)
+        return np.float32(get_text_feats_multiple_templates(queries, self.clip_model, self.clip_feat_dim))
+
+    def _set_index(self, key, rows):
+        """object_embs = np.array([obj.embedding ...]) (graph.py:3126) -> one HBM matrix, cached."""
+        if self._index_key != key:
+            E = np.ascontiguousarray(np.asarray(rows, dtype=np.float32))
+            d = E.shape[1]
+            if d % 128:
+                raise ValueError("embedding dimension must be a multiple of 128")
+            self.engine.index_set(E)
+            self._index_key = key
+        return self.engine
+
+    # graph.py:1441-1454
+    def identify_object(self, object_feat, text_feats, classes):
+        eng = self._set_index(("labels", id(text_feats)), text_feats)
+        sim = eng.query_scores(np.asarray(object_feat, dtype=np.float32).reshape(1, -1))
+        return classes[int(np.argmax(sim))]
+
+    # graph.py:2189-2214 (visualisation dropped)
+    def query_graph(self, query, query_feats=None):
+        q = self._text([query], query_feats)
+        eng = self._set_index(("objects", len(self.objects)), [o.embedding for o in self.objects])
+        ids, _ = eng.query_topk(q, min(5, len(self.objects)))
+        return self.objects[int(ids[0][0])]
+
+    # graph.py:3056-3162
+    def query_hmsg_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
+                          negative_prompt: List[str] = [], query_feats=None):
+        if query in negative_prompt:
+            query_id = negative_prompt.index(query)
+        else:
+            query_id = None
+        if query_id is None:
+            query = [query, *negative_prompt]
+            query_id = 0
+        else:
+            query = negative_prompt
+        q = self._text(query, query_feats)
+        room_ids_list = []
+        for obj in self.objects:
+            for i, room in enumerate(self.rooms):
+                if obj.room_id == room.room_id:
+                    room_ids_list.append(i)
+                    break
+        objects_list = None
+        if len(room_ids) != 0:
+            objects_list, room_ids_list = [], []
+            for i in room_ids:
+                src = self.floors[floor_id].rooms[i].objects if floor_id != -1 else self.rooms[i].objects
+                objects_list.extend(src)
+                room_ids_list.extend([i] * len(src))
+        if objects_list is None:
+            # the reference leaves `objects_list` undefined here; searching all objects is
+            # what its docstring promises ("Defaults to [], which means search from all rooms")
+            objects_list = list(self.objects)
+        if query_method != "clip":
+            return NotImplementedError
+        key = ("objsel", floor_id, tuple(room_ids), len(objects_list))
+        eng = self._set_index(key, [o.embedding for o in objects_list])
+        top_k_eff = min(top_k, len(objects_list))
+        top_index = None
+        if len(negative_prompt) > 0:
+            ids, sc, nf = eng.query_object(q[None], query_id, top_k_eff)
+            if nf[0] > 0:
+                top_index, scores = ids[0][:nf[0]], sc[0][:nf[0]]
+        if top_index is None:
+            ids, sc = eng.query_topk(q[query_id:query_id + 1], top_k_eff)
+            top_index, scores = ids[0], sc[0]
+        target_object_id = [objects_list[i].object_id for i in top_index]
+        target_object_score = [float(s) for s in scores]
+        target_room_id = [room_ids_list[i] for i in top_index]
+        target_id = [[i for i, x in enumerate(self.objects) if x.object_id == ti][0] for ti in target_object_id]
+        return target_id, target_room_id, target_object_score
+
+    # graph.py:3363-3481 (same core, returns (ids, room_ids))
+    def query_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
+                     negative_prompt: List[str] = [], query_feats=None):
+        tid, trid, _ = self.query_hmsg_object(query, floor_id, room_ids, query_method, top_k, negative_prompt, query_feats)
+        return tid, trid
+
+    # graph.py:3164-3272
+    def query_hmsg_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
+        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
+        q = self._text([query], query_feats)
+        rooms_list = self.rooms if floor_id == -1 else self.floors[floor_id].rooms
+        if query_method == "label" and is_room_text_valid:
+            embs = room_name_feats if room_name_feats is not None else get_text_feats_multiple_templates(
+                [r.name for r in rooms_list], self.clip_model, self.clip_feat_dim)
+            eng = self._set_index(("roomnames", floor_id, len(rooms_list)), embs)
+            sim = eng.query_scores(q)[0]
+            top_index = np.lexsort((np.arange(len(sim)), -sim))
+            tar = sim[top_index[0]]
+            same = [int(top_index[0])] + [int(i) for i in top_index[1:] if abs(sim[i] - tar) < 1e-3]      # :3216-3221
+            target_room_ids = [rooms_list[i].room_id for i in same]
+            return [i for i, x in enumerate(rooms_list) if x.room_id in target_room_ids]
+        rows, seg = [], []
+        for ri, room in enumerate(rooms_list):
+            e = np.stack(room.embeddings)
+            rows.append(e); seg.extend([ri] * len(e))
+        eng = self._set_index(("roomviews", floor_id, len(seg)), np.concatenate(rows))
+        sim = eng.query_scores(q)[0]
+        seg = np.asarray(seg)
+        room_max = np.array([sim[seg == ri].max() for ri in range(len(rooms_list))])                      # :3250-3253
+        order = sorted(range(len(rooms_list)), key=lambda r: room_max[r], reverse=True)
+        out = [int(str(rooms_list[r].room_id).split("_")[-1]) for r in order]                             # :3262-3267
+        return out[:min(len(out), 5 if is_room_text_valid else 10)]
+
+    # graph.py:3277-3359 (view-embedding branch: per-room max, top 3)
+    def query_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
+        if query_method == "label":
+            return self.query_hmsg_room(query, floor_id, "label", query_feats, room_name_feats)
+        return self.query_hmsg_room(query, floor_id, "view_embedding", query_feats)[:3]

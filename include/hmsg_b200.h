@@ -121,6 +121,9 @@ int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, 
 /* graph.py:413-415: counter[counter==0]=1e-5; full_feats = sum/counter -> [n_nodes,d] f32 */
 int32_t hmsg_node_feats_finalize(hmsg_ctx* ctx, float* full_feats, int32_t on_device);
 int32_t hmsg_node_feats_raw(hmsg_ctx* ctx, float* sum_features, float* counter);
+/* API parity only: the dense per-pixel map `outfeat` [H*W,d] fp16 of extract_feats_per_pixel
+ * (extractor.py:177-190) for one frame of the batch last passed to hmsg_fuse_scatter. */
+int32_t hmsg_pixel_feature_map(hmsg_ctx* ctx, int64_t frame, uint16_t* out_half);
 
 /* A7  RGBDDataset.create_3d_masks (dataloader/generic.py:140-190) for one frame whose masks
  * were set: per mask the node positions hit by its pixels, re-voxelised (down_size) relative
@@ -177,6 +180,9 @@ int32_t hmsg_index_set(hmsg_ctx* ctx, const float* E, int64_t N, int32_t d, int3
 int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, int32_t k,
                         const uint8_t* row_mask, int64_t* ids, float* scores,
                         int32_t on_device);
+/* dense sim = np.dot(Q, E.T) -> scores [nq,N] for small tables: room names / room view embeddings
+ * (graph.py:3204, :3250-3257, :3345-3350) and class labels (identify_object, graph.py:1452). */
+int32_t hmsg_query_scores(hmsg_ctx* ctx, const float* Q, int32_t nq, float* scores, int32_t on_device);
 /* query_hmsg_object core with negative prompts (graph.py:3134-3151): for each request r the
  * Qp rows Q[r] are (query + negatives); objects whose column-argmax is query_id, sorted by
  * -max score, first k.  n_found[r] = number returned (< k possible; 0 => caller falls back to
