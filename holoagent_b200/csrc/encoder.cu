@@ -114,30 +114,56 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int OUT_STAGE_BYTES = BM * 128;    // 16 KB: 128 rows x one 128-byte swizzle span
+constexpr int GEMM_THREADS = 384;            // 4 control warps + 8 epilogue warps
+constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU = 1, EPI_F32_RESIDUAL = 2, EPI_F32_STORE = 3 };
 
 struct GemmArgs {
   int M, N, K;
   const float* bias;     // [N] or null
-  void* out;             // fp16 [M,N] (EPI 0,1) or fp32 [M,N] (EPI 2: in-place +=, EPI 3: store)
-  int ldo;               // leading dimension of out in elements
   int quick_gelu;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far inside the 1e-3 embedding contract):
+// one MUFU.EX2 + one MUFU.RCP + 7 FMA instead of libdevice erff's ~40 instructions
+__device__ __forceinline__ float gelu_erf(float x) {
+  float z = fabsf(x) * 0.70710678118654752440f;
+  float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
+  float e = 1.0f - p * __expf(-z * z);          // erf(|x|/sqrt2)
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 __device__ __forceinline__ float gelu_quick(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(smem_src)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// Epilogue: 8 warps in two groups of 4 (one warp per TMEM lane quarter).  A group converts one
+// 128-row x 128-byte chunk of the accumulator tile (64 fp16 / 32 fp32 columns) into its own
+// 128B-swizzled staging buffer and one elected thread hands it to TMA (store, or reduce-add for
+// the in-place fp32 residual: x += acc + bias happens in L2, the SM never reads x).
 template <int EPI>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmArgs g) {
+k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES));
+  uint8_t* sO = smem + STAGES * (A_STAGE_BYTES + B_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * OUT_STAGE_BYTES);
   uint64_t* full = bars;                  // [STAGES]
   uint64_t* empty = bars + STAGES;        // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;    // [2]
@@ -151,10 +177,11 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 4); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -207,60 +234,72 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (4 warps = 128 TMEM lanes) =====================
-    const int ew = warp - 4;   // == warp % 4: the TMEM lane quarter this warp may access
+    // ===================== epilogue (8 warps) =====================
+    constexpr bool F16OUT = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU);
+    constexpr int CH_COLS = F16OUT ? 64 : 32;       // columns per 128-byte staging row
+    constexpr int NCH = BN / CH_COLS;
+    const int ew = warp - 4;
+    const int q = ew & 3;                            // == warp % 4: TMEM lane quarter of this warp
+    const int grp = ew >> 2;
+    uint8_t* stg = sO + grp * OUT_STAGE_BYTES;
+    const int trow = q * 32 + lane;                  // row inside the tile == TMEM lane
+    const bool issuer = (q == 0 && lane == 0);
+    uint8_t* srow = stg + trow * 128;
+    const int sw = trow & 7;
     int as = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb = tile / n_tiles, nb = tile % n_tiles;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const int row = mb * BM + ew * 32 + lane;
-      const bool row_ok = row < g.M;
-      const uint32_t t_addr = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * BN);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; c++) {
-        uint32_t r[32];
-        tmem_ld_32x32(t_addr + (uint32_t)(c * 32), r);
-        tmem_ld_wait();
-        const int col = nb * BN + c * 32;
-        if (row_ok) {
-          if (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU) {
-            __half* o = reinterpret_cast<__half*>(g.out) + (size_t)row * g.ldo + col;
+      for (int ch = grp; ch < NCH; ch += 2) {
+        if (issuer) tma_wait_read0();                // previous store out of this buffer has drained it
+        named_bar_sync(1 + grp, 128);
+        const int col0 = nb * BN + ch * CH_COLS;
 #pragma unroll
-            for (int q = 0; q < 4; q++) {
+        for (int h = 0; h < CH_COLS / 32; h++) {
+          uint32_t r[32];
+          tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + h * 32), r);
+          tmem_ld_wait();
+          const float* bp = g.bias ? g.bias + col0 + h * 32 : nullptr;
+          if (F16OUT) {
+#pragma unroll
+            for (int q4 = 0; q4 < 4; q4++) {
+              float v[8];
+#pragma unroll
+              for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
+              if (bp) {
+                float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              }
+              if (EPI == EPI_F16_BIAS_GELU) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = g.quick_gelu ? gelu_quick(v[e]) : gelu_erf(v[e]);
+              }
               uint32_t pk[4];
 #pragma unroll
-              for (int e = 0; e < 4; e++) {
-                int i = q * 8 + e * 2;
-                float v0 = __uint_as_float(r[i]) + (g.bias ? __ldg(g.bias + col + i) : 0.f);
-                float v1 = __uint_as_float(r[i + 1]) + (g.bias ? __ldg(g.bias + col + i + 1) : 0.f);
-                if (EPI == EPI_F16_BIAS_GELU) {
-                  if (g.quick_gelu) { v0 = gelu_quick(v0); v1 = gelu_quick(v1); }
-                  else { v0 = gelu_erf(v0); v1 = gelu_erf(v1); }
-                }
-                __half2 h = __floats2half2_rn(v0, v1);
-                pk[e] = *reinterpret_cast<uint32_t*>(&h);
-              }
-              *reinterpret_cast<uint4*>(o + q * 8) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
+              const int c16 = h * 4 + q4;              // 16-byte chunk index inside the 128-byte row
+              *reinterpret_cast<uint4*>(srow + ((c16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
           } else {
-            float* o = reinterpret_cast<float*>(g.out) + (size_t)row * g.ldo + col;
 #pragma unroll
-            for (int q = 0; q < 8; q++) {
+            for (int q8 = 0; q8 < 8; q8++) {
               float4 v;
-              v.x = __uint_as_float(r[q * 4 + 0]); v.y = __uint_as_float(r[q * 4 + 1]);
-              v.z = __uint_as_float(r[q * 4 + 2]); v.w = __uint_as_float(r[q * 4 + 3]);
-              if (g.bias) {
-                float4 b = __ldg(reinterpret_cast<const float4*>(g.bias + col) + q);
-                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-              }
-              if (EPI == EPI_F32_RESIDUAL) {
-                float4 x = reinterpret_cast<float4*>(o)[q];
-                v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
-              }
-              reinterpret_cast<float4*>(o)[q] = v;
+              v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
+              v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
+              if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+              *reinterpret_cast<float4*>(srow + ((q8 ^ sw) << 4)) = v;
             }
           }
+        }
+        fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA (async proxy)
+        named_bar_sync(1 + grp, 128);
+        if (issuer) {
+          if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, mb * BM);
+          else tma_store_2d(&tmO, stg, col0, mb * BM);
+          tma_commit_group();
         }
       }
       tc_fence_before();
@@ -268,6 +307,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
     }
+    if (issuer) tma_wait_all0();
   }
   tc_fence_before();
   __syncthreads();
@@ -600,12 +640,15 @@ struct VitState {
   bool smem_attr_set = false;
 };
 
-static int32_t make_tmap(hmsg_ctx* ctx, VitState* vs, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+static int32_t make_tmap(hmsg_ctx* ctx, VitState* vs, CUtensorMap* map, const void* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows,
+                         int elem_bytes = 2, uint64_t ld_elems = 0) {
+  // 2-D row-major tensor [rows, cols] (leading dimension ld_elems), box = (128 bytes of columns) x box_rows, 128B swizzle
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {cols * 2};
-  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint64_t strides[1] = {(ld_elems ? ld_elems : cols) * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = vs->encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = vs->encode(map, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return ctx->fail(HMSG_ERR_CUDA, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
   return HMSG_OK;
@@ -621,7 +664,7 @@ static int32_t get_encoder(hmsg_ctx* ctx, PFN_encodeTiled* out) {
 }
 
 template <int EPI>
-static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g) {
+static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g) {
   static bool attr = false;
   if (!attr) {
     cudaError_t e = cudaFuncSetAttribute(k_gemm_f16<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM);
@@ -631,7 +674,7 @@ static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtenso
   int tiles = ((g.M + BM - 1) / BM) * (g.N / BN);
   int grid = std::min(tiles, ctx->sm_count);
   ctx->prof_begin(PROF_GEMM);
-  k_gemm_f16<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(ta, tb, g);
+  k_gemm_f16<EPI><<<grid, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(ta, tb, to, g);
   ctx->prof_end(PROF_GEMM, 2.0 * g.M * (double)g.N * g.K);
   HMSG_LAUNCH_CHECK();
   return HMSG_OK;
@@ -641,16 +684,18 @@ static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtenso
 static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const __half* Wt, int M, int N, int K, const float* bias, void* out,
                     int ldo) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
   int32_t rc;
   if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
   if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, BN))) return rc;
-  GemmArgs g{M, N, K, bias, out, ldo, vs->desc.quick_gelu};
+  const bool f16out = (epi == EPI_F16_BIAS || epi == EPI_F16_BIAS_GELU);
+  if ((rc = make_tmap(ctx, vs, &to, out, (uint64_t)M, (uint64_t)N, BM, f16out ? 2 : 4, (uint64_t)ldo))) return rc;
+  GemmArgs g{M, N, K, bias, vs->desc.quick_gelu};
   switch (epi) {
-    case EPI_F16_BIAS: return launch_gemm_t<EPI_F16_BIAS>(ctx, ta, tb, g);
-    case EPI_F16_BIAS_GELU: return launch_gemm_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, g);
-    case EPI_F32_RESIDUAL: return launch_gemm_t<EPI_F32_RESIDUAL>(ctx, ta, tb, g);
-    default: return launch_gemm_t<EPI_F32_STORE>(ctx, ta, tb, g);
+    case EPI_F16_BIAS: return launch_gemm_t<EPI_F16_BIAS>(ctx, ta, tb, to, g);
+    case EPI_F16_BIAS_GELU: return launch_gemm_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, to, g);
+    case EPI_F32_RESIDUAL: return launch_gemm_t<EPI_F32_RESIDUAL>(ctx, ta, tb, to, g);
+    default: return launch_gemm_t<EPI_F32_STORE>(ctx, ta, tb, to, g);
   }
 }
 
