@@ -29,7 +29,7 @@ struct ResampleTable {
 
 struct CropState {
   std::map<std::pair<int, int>, ResampleTable> tables;
-  uint8_t* t1 = nullptr; size_t t1_bytes = 0;        // [crops, rows, 224, 3]
+  uint32_t* t1 = nullptr; size_t t1_bytes = 0;       // [crops, rows, 224] packed rgb
   float* out = nullptr;  size_t out_bytes = 0;       // [crops, 3, 224, 224]
   int32_t* boxes = nullptr; size_t boxes_bytes = 0;
 };
@@ -102,15 +102,16 @@ __device__ __forceinline__ void cv_coef(int d, double scale, int src, bool clamp
 }
 
 // ---- pass 1 (crops): cv2 bilinear to 512x512 fused with the PIL horizontal pass 512 -> 224.
-// grid = (512/ROWS_PER_BLOCK, 2M, n_frames); T1[crop][dy][ox][c]
+// grid = (512/ROWS_PER_BLOCK, 2M, n_frames); T1[crop][dy][ox] = packed r | g<<8 | b<<16.
+// A thread owns one output column of the PIL pass and keeps its (<= KS) coefficients in registers.
+template <int KS>
 __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ maskbits, long long frame0,
                                                    int H, int W, int M, int MW, const int32_t* __restrict__ boxes, int margin,
-                                                   const int* __restrict__ bounds, const int* __restrict__ kk, int ksize,
-                                                   uint8_t* __restrict__ t1) {
+                                                   const int* __restrict__ bounds, const int* __restrict__ kk, uint32_t* __restrict__ t1) {
   __shared__ short s_xofs[CROP_MID];
   __shared__ short s_a[CROP_MID][2];
   __shared__ int s_h[2][CROP_MID * 3];
-  __shared__ uint8_t s_row[CROP_MID * 3];
+  __shared__ uint32_t s_row[CROP_MID];
   const int fb = blockIdx.z, ci = blockIdx.y;
   const bool masked = ci < M;
   const int m = masked ? ci : ci - M;
@@ -126,10 +127,10 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   x = min(max(x, 0), W); y = min(max(y, 0), H);
   const int cw = x1 - x, ch = y1 - y;
   const long long crop_id = (long long)fb * (2 * M + 1) + ci;
-  uint8_t* dst = t1 + crop_id * (long long)CROP_MID * 224 * 3;
+  uint32_t* dst = t1 + crop_id * (long long)CROP_MID * 224;
   const int dy0 = blockIdx.x * ROWS_PER_BLOCK;
   if (cw <= 0 || ch <= 0) {   // empty crop: cv2.resize would raise in the reference; emit zeros
-    for (int i = threadIdx.x; i < ROWS_PER_BLOCK * 224 * 3; i += blockDim.x) dst[(long long)dy0 * 224 * 3 + i] = 0;
+    for (int i = threadIdx.x; i < ROWS_PER_BLOCK * 224; i += blockDim.x) dst[(long long)dy0 * 224 + i] = 0;
     return;
   }
   const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)cw));
@@ -139,17 +140,24 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
     cv_coef(d, scale_x, cw, true, s, a0, a1);
     s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
   }
+  // PIL coefficients of this thread's output column
+  const int ox = threadIdx.x;
+  int kreg[KS]; int pxmin = 0, pcnt = 0;
+  if (ox < 224) {
+    pxmin = __ldg(&bounds[ox * 2]); pcnt = __ldg(&bounds[ox * 2 + 1]);
+#pragma unroll
+    for (int k = 0; k < KS; k++) kreg[k] = __ldg(&kk[ox * KS + k]);   // entries beyond pcnt are zero
+  }
   __syncthreads();
   const uint8_t* img = rgb + (frame0 + fb) * (long long)H * W * 3;
   const uint32_t* mb = maskbits + (long long)fb * H * W * MW;
-  int tag0 = -1, tag1 = -1;   // source rows currently held in s_h[0], s_h[1]
-  int sl0 = 0;                 // which slot holds "row0"
+  int tag0 = -1, tag1 = -1;   // source rows currently held in s_h[sl0], s_h[sl0^1]
+  int sl0 = 0;
   for (int r = 0; r < ROWS_PER_BLOCK; r++) {
     const int dy = dy0 + r;
     int sy, b0, b1;
     cv_coef(dy, scale_y, ch, false, sy, b0, b1);
     const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
-    // make slot sl0 hold r0 and slot 1-sl0 hold r1 (reuse across consecutive dy)
     int need0 = 1, need1 = 1;
     if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
     else if (tag1 == r0) { sl0 ^= 1; tag0 = tag1; tag1 = -1; need0 = 0; }
@@ -162,58 +170,71 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
       for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
         int s0 = s_xofs[d], s1 = min(s0 + 1, cw - 1);
         int a0 = s_a[d][0], a1 = s_a[d][1];
-        int k0 = 1, k1 = 1;
         if (masked) {   // crop_image: image * segmentation (sam_utils.py:159)
-          k0 = (mrow[(long long)s0 * MW + (m >> 5)] >> (m & 31)) & 1;
-          k1 = (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
+          a0 *= (mrow[(long long)s0 * MW + (m >> 5)] >> (m & 31)) & 1;
+          a1 *= (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
         }
 #pragma unroll
-        for (int c = 0; c < 3; c++) hb[d * 3 + c] = (int)srow[s0 * 3 + c] * k0 * a0 + (int)srow[s1 * 3 + c] * k1 * a1;
+        for (int c = 0; c < 3; c++) hb[d * 3 + c] = (int)srow[s0 * 3 + c] * a0 + (int)srow[s1 * 3 + c] * a1;
       }
     }
     tag0 = r0; tag1 = r1;
     __syncthreads();
     const int* h0 = s_h[sl0];
     const int* h1 = s_h[sl0 ^ 1];
-    for (int i = threadIdx.x; i < CROP_MID * 3; i += blockDim.x)
-      s_row[i] = (uint8_t)((((b0 * (h0[i] >> 4)) >> 16) + ((b1 * (h1[i] >> 4)) >> 16) + 2) >> 2);
-    __syncthreads();
-    // PIL horizontal pass 512 -> 224
-    for (int i = threadIdx.x; i < 224 * 3; i += blockDim.x) {
-      int ox = i / 3, c = i - ox * 3;
-      int xmin = __ldg(&bounds[ox * 2]), cnt = __ldg(&bounds[ox * 2 + 1]);
-      int acc = 1 << 21;
-      for (int k = 0; k < cnt; k++) acc += (int)s_row[(xmin + k) * 3 + c] * __ldg(&kk[ox * ksize + k]);
-      acc >>= 22;
-      dst[((long long)dy * 224 + ox) * 3 + c] = (uint8_t)min(max(acc, 0), 255);
+    for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+      uint32_t pk = 0;
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        int v = (((b0 * (h0[d * 3 + c] >> 4)) >> 16) + ((b1 * (h1[d * 3 + c] >> 4)) >> 16) + 2) >> 2;
+        pk |= (uint32_t)(v & 255) << (8 * c);
+      }
+      s_row[d] = pk;
     }
     __syncthreads();
+    if (ox < 224) {   // PIL horizontal pass 512 -> 224
+      int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+#pragma unroll
+      for (int k = 0; k < KS; k++) {
+        if (k < pcnt) {
+          uint32_t px = s_row[pxmin + k];
+          a0 += (int)(px & 255) * kreg[k]; a1 += (int)((px >> 8) & 255) * kreg[k]; a2 += (int)((px >> 16) & 255) * kreg[k];
+        }
+      }
+      a0 = min(max(a0 >> 22, 0), 255); a1 = min(max(a1 >> 22, 0), 255); a2 = min(max(a2 >> 22, 0), 255);
+      dst[(long long)dy * 224 + ox] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16);
+    }
   }
 }
 
 // ---- pass 1 (full frame): PIL horizontal pass W -> nw, only columns [left, left+224)
-// grid = (H, n_frames); T1[crop][y][ox][c] with `rows_alloc` rows per crop
+// grid = (H, n_frames); T1[crop][y][ox] packed, `rows_alloc` rows per crop
 __global__ void __launch_bounds__(256) k_frame_rows(const uint8_t* __restrict__ rgb, long long frame0, int H, int W, int M, int left,
                                                     const int* __restrict__ bounds, const int* __restrict__ kk, int ksize, int rows_alloc,
-                                                    uint8_t* __restrict__ t1) {
+                                                    uint32_t* __restrict__ t1) {
   const int fb = blockIdx.y, yy = blockIdx.x;
   const uint8_t* srow = rgb + ((frame0 + fb) * (long long)H + yy) * W * 3;
   const long long crop_id = (long long)fb * (2 * M + 1) + 2 * M;
-  uint8_t* dst = t1 + crop_id * (long long)rows_alloc * 224 * 3 + (long long)yy * 224 * 3;
-  for (int i = threadIdx.x; i < 224 * 3; i += blockDim.x) {
-    int ox = i / 3, c = i - ox * 3;
-    int sx = ox + left;
-    int xmin = __ldg(&bounds[sx * 2]), cnt = __ldg(&bounds[sx * 2 + 1]);
-    int acc = 1 << 21;
-    for (int k = 0; k < cnt; k++) acc += (int)srow[(xmin + k) * 3 + c] * __ldg(&kk[sx * ksize + k]);
-    acc >>= 22;
-    dst[i] = (uint8_t)min(max(acc, 0), 255);
+  uint32_t* dst = t1 + crop_id * (long long)rows_alloc * 224 + (long long)yy * 224;
+  int ox = threadIdx.x;
+  if (ox >= 224) return;
+  int sx = ox + left;
+  int xmin = __ldg(&bounds[sx * 2]), cnt = __ldg(&bounds[sx * 2 + 1]);
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int k = 0; k < cnt; k++) {
+    int kv = __ldg(&kk[sx * ksize + k]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) acc[c] += (int)srow[(xmin + k) * 3 + c] * kv;
   }
+  uint32_t pk = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) pk |= (uint32_t)min(max(acc[c] >> 22, 0), 255) << (8 * c);
+  dst[ox] = pk;
 }
 
 // ---- pass 2: PIL vertical pass + ToTensor + Normalize -> fp32 planar
 // grid = (ceil(224*224/256), crops per frame in this launch, n_frames); crop = frame*(2M+1) + crop0 + blockIdx.y
-__global__ void __launch_bounds__(256) k_crop_cols(const uint8_t* __restrict__ t1, int rows_alloc, int top, const int* __restrict__ bounds,
+__global__ void __launch_bounds__(256) k_crop_cols(const uint32_t* __restrict__ t1, int rows_alloc, int top, const int* __restrict__ bounds,
                                                    const int* __restrict__ kk, int ksize, int crop0, int crops_per_frame,
                                                    float* __restrict__ out) {
   const long long crop = (long long)blockIdx.z * crops_per_frame + crop0 + blockIdx.y;
@@ -222,12 +243,12 @@ __global__ void __launch_bounds__(256) k_crop_cols(const uint8_t* __restrict__ t
   int oy = p / 224, ox = p - oy * 224;
   int sy = oy + top;
   int ymin = __ldg(&bounds[sy * 2]), cnt = __ldg(&bounds[sy * 2 + 1]);
-  const uint8_t* src = t1 + crop * (long long)rows_alloc * 224 * 3 + ((long long)ymin * 224 + ox) * 3;
+  const uint32_t* src = t1 + crop * (long long)rows_alloc * 224 + (long long)ymin * 224 + ox;
   int acc[3] = {1 << 21, 1 << 21, 1 << 21};
   for (int k = 0; k < cnt; k++) {
     int kv = __ldg(&kk[sy * ksize + k]);
-#pragma unroll
-    for (int c = 0; c < 3; c++) acc[c] += (int)src[(long long)k * 224 * 3 + c] * kv;
+    uint32_t px = __ldg(src + (long long)k * 224);
+    acc[0] += (int)(px & 255) * kv; acc[1] += (int)((px >> 8) & 255) * kv; acc[2] += (int)((px >> 16) & 255) * kv;
   }
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
@@ -272,7 +293,7 @@ extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n
   if ((rc = get_table(ctx, cs, H, nh, &th))) return rc;
   const int rows_alloc = std::max(CROP_MID, H);
   const long long ncrops = (long long)n * (2 * M + 1);
-  if ((rc = ctx->reserve(&cs->t1, &cs->t1_bytes, (size_t)ncrops * rows_alloc * 224 * 3))) return rc;
+  if ((rc = ctx->reserve(&cs->t1, &cs->t1_bytes, (size_t)ncrops * rows_alloc * 224 * 4))) return rc;
   if ((rc = ctx->reserve(&cs->out, &cs->out_bytes, (size_t)ncrops * 3 * 224 * 224 * 4))) return rc;
   const int32_t* dbox = xywh;
   if (!on_device) {
@@ -281,8 +302,9 @@ extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n
     dbox = cs->boxes;
   }
   ctx->prof_begin(PROF_CROPS);
-  k_crop_rows<<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
-                                                                                   bbox_margin, tc->bounds, tc->kk, tc->ksize, cs->t1);
+  if (tc->ksize != 11) return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: unexpected PIL kernel size for 512->224");
+  k_crop_rows<11><<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
+                                                                                       bbox_margin, tc->bounds, tc->kk, cs->t1);
   HMSG_LAUNCH_CHECK();
   k_frame_rows<<<dim3(H, n), 256, 0, ctx->stream>>>(ctx->rgb, frame_begin, H, W, M, left, tw->bounds, tw->kk, tw->ksize, rows_alloc, cs->t1);
   HMSG_LAUNCH_CHECK();

@@ -93,6 +93,14 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* r) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, 128-byte-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
@@ -115,7 +123,7 @@ constexpr int BM = 128, BN = 256, BK = 64, STAGES = 4, UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int OUT_STAGE_BYTES = BM * 128;    // 16 KB: 128 rows x one 128-byte swizzle span
-constexpr int GEMM_THREADS = 384;            // 4 control warps + 8 epilogue warps
+constexpr int GEMM_THREADS = 640;            // 4 control warps + 16 epilogue warps
 constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 enum { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU = 1, EPI_F32_RESIDUAL = 2, EPI_F32_STORE = 3 };
@@ -130,10 +138,10 @@ struct GemmArgs {
 // one MUFU.EX2 + one MUFU.RCP + 7 FMA instead of libdevice erff's ~40 instructions
 __device__ __forceinline__ float gelu_erf(float x) {
   float z = fabsf(x) * 0.70710678118654752440f;
-  float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
   float p = fmaf(fmaf(fmaf(fmaf(1.061405429f, t, -1.453152027f), t, 1.421413741f), t, -0.284496736f), t, 0.254829592f) * t;
-  float e = 1.0f - p * __expf(-z * z);          // erf(|x|/sqrt2)
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  float hh = 0.5f * x * (p * __expf(-z * z));   // 0.5 x erfc(|x|/sqrt2)
+  return x > 0.f ? x - hh : hh;                 // 0.5 x (1 + erf(x/sqrt2))
 }
 __device__ __forceinline__ float gelu_quick(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
@@ -151,7 +159,7 @@ __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-// Epilogue: 8 warps in two groups of 4 (one warp per TMEM lane quarter).  A group converts one
+// Epilogue: 16 warps in two groups of 8 (two warps per TMEM lane quarter).  A group converts one
 // 128-row x 128-byte chunk of the accumulator tile (64 fp16 / 32 fp32 columns) into its own
 // 128B-swizzled staging buffer and one elected thread hands it to TMA (store, or reduce-add for
 // the in-place fp32 residual: x += acc + bias happens in L2, the SM never reads x).
@@ -181,7 +189,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < STAGES; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 16); }
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, 512);
@@ -234,16 +242,20 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       }
     }
   } else if (warp >= 4) {
-    // ===================== epilogue (8 warps) =====================
+    // ===================== epilogue (16 warps) =====================
+    // two groups of 8 warps; in a group two warps share each TMEM lane quarter and split the
+    // chunk's columns (a warp loads 32 fp32 columns for fp16 output, 16 for fp32 output)
     constexpr bool F16OUT = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU);
     constexpr int CH_COLS = F16OUT ? 64 : 32;       // columns per 128-byte staging row
+    constexpr int WCOLS = CH_COLS / 2;              // columns per warp
     constexpr int NCH = BN / CH_COLS;
     const int ew = warp - 4;
     const int q = ew & 3;                            // == warp % 4: TMEM lane quarter of this warp
-    const int grp = ew >> 2;
+    const int half = (ew >> 2) & 1;
+    const int grp = ew >> 3;
     uint8_t* stg = sO + grp * OUT_STAGE_BYTES;
     const int trow = q * 32 + lane;                  // row inside the tile == TMEM lane
-    const bool issuer = (q == 0 && lane == 0);
+    const bool issuer = (q == 0 && half == 0 && lane == 0);
     uint8_t* srow = stg + trow * 128;
     const int sw = trow & 7;
     int as = 0; uint32_t aph = 0;
@@ -255,47 +267,50 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 #pragma unroll 1
       for (int ch = grp; ch < NCH; ch += 2) {
         if (issuer) tma_wait_read0();                // previous store out of this buffer has drained it
-        named_bar_sync(1 + grp, 128);
+        named_bar_sync(1 + grp, 256);
         const int col0 = nb * BN + ch * CH_COLS;
+        uint32_t r[WCOLS];
+        if (F16OUT) tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
+        else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
+        tmem_ld_wait();
+        const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
+        if (F16OUT) {
 #pragma unroll
-        for (int h = 0; h < CH_COLS / 32; h++) {
-          uint32_t r[32];
-          tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + h * 32), r);
-          tmem_ld_wait();
-          const float* bp = g.bias ? g.bias + col0 + h * 32 : nullptr;
-          if (F16OUT) {
+          for (int q4 = 0; q4 < 4; q4++) {
+            float v[8];
 #pragma unroll
-            for (int q4 = 0; q4 < 4; q4++) {
-              float v[8];
-#pragma unroll
-              for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
-              if (bp) {
-                float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
-                v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-              }
-              if (EPI == EPI_F16_BIAS_GELU) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = g.quick_gelu ? gelu_quick(v[e]) : gelu_erf(v[e]);
-              }
-              uint32_t pk[4];
-#pragma unroll
-              for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
-              const int c16 = h * 4 + q4;              // 16-byte chunk index inside the 128-byte row
-              *reinterpret_cast<uint4*>(srow + ((c16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
+            if (bp) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
             }
-          } else {
+            if (EPI == EPI_F16_BIAS_GELU) {
+              if (g.quick_gelu) {
 #pragma unroll
-            for (int q8 = 0; q8 < 8; q8++) {
-              float4 v;
-              v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
-              v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
-              if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
-              *reinterpret_cast<float4*>(srow + ((q8 ^ sw) << 4)) = v;
+                for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = gelu_erf(v[e]);
+              }
             }
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
+            const int c16 = half * 4 + q4;             // 16-byte chunk index inside the 128-byte row
+            *reinterpret_cast<uint4*>(srow + ((c16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; q8++) {
+            float4 v;
+            v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
+            v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
+            if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            *reinterpret_cast<float4*>(srow + (((half * 4 + q8) ^ sw) << 4)) = v;
           }
         }
         fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA (async proxy)
-        named_bar_sync(1 + grp, 128);
+        named_bar_sync(1 + grp, 256);
         if (issuer) {
           if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, mb * BM);
           else tma_store_2d(&tmO, stg, col0, mb * BM);
@@ -338,15 +353,22 @@ __global__ void k_pad_weight(const float* __restrict__ in, __half* __restrict__ 
 
 // im2col for the stride==patch convolution: x [B,3,S,S] fp32 -> A0 [B*G*G, Kpad] fp16,
 // column = c*P*P + iy*P + ix (conv1.weight flattening).  One block per (b, c, image row).
-__global__ void k_im2col(const float* __restrict__ x, __half* __restrict__ a0, int S, int P, int G, int Kpad) {
-  int rowid = blockIdx.x;            // b*3*S + c*S + y
-  int y = rowid % S; int c = (rowid / S) % 3; int b = rowid / (3 * S);
+__global__ void __launch_bounds__(256) k_im2col(const float* __restrict__ x, __half* __restrict__ a0, long long nrows, int S, int P, int G, int Kpad) {
+  // one warp per image row (b, c, y); requires S % 4 == 0 and P % 4 == 0 (float4 in, 4 halfs out)
+  long long rowid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // b*3*S + c*S + y
+  int lane = threadIdx.x & 31;
+  if (rowid >= nrows) return;
+  int y = (int)(rowid % S); int c = (int)((rowid / S) % 3); long long b = rowid / (3 * S);
   int py = y / P, iy = y % P;
   if (py >= G) return;
-  const float* src = x + (long long)rowid * S;
-  for (int t = threadIdx.x; t < G * P; t += blockDim.x) {
+  const float4* src = reinterpret_cast<const float4*>(x + rowid * S);
+  for (int t4 = lane; t4 < (G * P) / 4; t4 += 32) {
+    float4 v = __ldg(src + t4);
+    int t = t4 * 4;
     int px = t / P, ix = t % P;
-    a0[((long long)(b * G * G + py * G + px)) * Kpad + c * P * P + iy * P + ix] = __float2half_rn(src[t]);
+    __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(a0 + ((b * G * G + py * G + px)) * Kpad + c * P * P + iy * P + ix) = pk;
   }
 }
 __global__ void k_zero_pad_cols(__half* a0, long long rows, int Kc, int Kpad) {
@@ -569,6 +591,140 @@ __global__ void __launch_bounds__(128) k_attention_mma(const __half* __restrict_
   }
 }
 
+// ---- attention v2: persistent warps, cp.async double-buffered (image, head) tiles, ldmatrix
+// fragment loads (V through ldmatrix.trans, so no transposition pass), P kept in registers.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldsm_x4(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t* r, const void* p) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+
+constexpr int ATT2_WARPS = 4;
+constexpr int ATT2_TILE = 64 * ATT_LD;            // halfs per matrix
+constexpr int ATT2_SMEM = ATT2_WARPS * 2 * 3 * ATT2_TILE * 2;
+
+__global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
+                                                                       int W, float scale) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* wbase = reinterpret_cast<__half*>(att_smem) + (size_t)warp * 2 * 3 * ATT2_TILE;
+  // zero both buffers once: rows >= T are never written by cp.async and V padding rows must be finite (P = 0 there)
+  for (int i = lane; i < 2 * 3 * ATT2_TILE / 8; i += 32) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  const long long npairs = (long long)B * heads;
+  const long long gw = (long long)blockIdx.x * ATT2_WARPS + warp, tw = (long long)gridDim.x * ATT2_WARPS;
+  const int ld = 3 * W;
+  auto issue = [&](long long pair, int bi) {
+    int b = (int)(pair / heads), h = (int)(pair % heads);
+    __half* sQ = wbase + bi * 3 * ATT2_TILE;
+    const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
+    for (int i = lane; i < T * 8; i += 32) {
+      int r = i >> 3, ch = i & 7;
+      const __half* src = src0 + (long long)r * ld + ch * 8;
+      __half* dst = sQ + r * ATT_LD + ch * 8;
+      cp_async16(dst, src);
+      cp_async16(dst + ATT2_TILE, src + W);
+      cp_async16(dst + 2 * ATT2_TILE, src + 2 * W);
+    }
+  };
+  if (gw < npairs) issue(gw, 0);
+  cp_async_commit();
+  int cur = 0;
+  const int g = lane >> 2, t = lane & 3;
+  const int m_tiles = (T + 15) / 16;
+  for (long long pair = gw; pair < npairs; pair += tw) {
+    if (pair + tw < npairs) issue(pair + tw, cur ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+    const __half* sQ = wbase + cur * 3 * ATT2_TILE;
+    const __half* sK = sQ + ATT2_TILE;
+    const __half* sV = sK + ATT2_TILE;
+    const int b = (int)(pair / heads), h = (int)(pair % heads);
+    for (int mi = 0; mi < m_tiles; mi++) {
+      float s[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        uint32_t a[4];
+        ldsm_x4(a, sQ + (mi * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int np = 0; np < 4; np++) {     // two key tiles per ldmatrix.x4
+          uint32_t bb[4];
+          ldsm_x4(bb, sK + ((np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma_16816(s[np * 2], a, bb);
+          mma_16816(s[np * 2 + 1], a, bb + 2);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          int col = ni * 8 + 2 * t + e;
+          float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
+          float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
+          s[ni][e] = v0; s[ni][2 + e] = v1;
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          float p0 = __expf(s[ni][e] - mx0), p1 = __expf(s[ni][2 + e] - mx1);
+          s[ni][e] = p0; s[ni][2 + e] = p1;
+          sum0 += p0; sum1 += p1;
+        }
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      float oacc[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        uint32_t a[4];
+        __half2 h0 = __floats2half2_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+        __half2 h1 = __floats2half2_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+        __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+        __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+        a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
+        a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+#pragma unroll
+        for (int np = 0; np < 4; np++) {     // two d-column tiles per ldmatrix.x4.trans
+          uint32_t bb[4];
+          ldsm_x4_t(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + (np * 2 + (lane >> 4)) * 8);
+          mma_16816(oacc[np * 2], a, bb);
+          mma_16816(oacc[np * 2 + 1], a, bb + 2);
+        }
+      }
+      const int r0 = mi * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+        int col = h * 64 + ni * 8 + 2 * t;
+        if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0], oacc[ni][1]);
+        if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2], oacc[ni][3]);
+      }
+    }
+    __syncwarp();
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
 // straightforward fp32 reference attention (debug: HMSG_ATTN_SIMPLE=1), one block per (image, head)
 __global__ void __launch_bounds__(128) k_attention_simple(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads, int W,
                                                           float scale) {
@@ -637,6 +793,7 @@ struct VitState {
   float* in_stage = nullptr; size_t in_stage_bytes = 0;
   float* out_stage = nullptr; size_t out_stage_bytes = 0;
   bool attn_simple = false;
+  bool attn_v1 = false;
   bool smem_attr_set = false;
 };
 
@@ -721,7 +878,7 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
   if (!ctx) return HMSG_ERR_ARG;
   if (!desc || !blob) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: null argument");
   const hmsg_vit_desc& d = *desc;
-  if (d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
+  if (d.image % 4 != 0 || d.patch % 4 != 0 || d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
       (3 * d.width) % 256 != 0 || d.width % 256 != 0)
     return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: unsupported ViT shape (need head_dim 64, width/mlp/out_dim multiples of 256)");
   int G = d.image / d.patch, T = G * G + 1;
@@ -784,6 +941,7 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
   }
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   if (const char* e = getenv("HMSG_ATTN_SIMPLE")) vs->attn_simple = atoi(e) != 0;
+  if (const char* e = getenv("HMSG_ATTN_V1")) vs->attn_v1 = atoi(e) != 0;
   return HMSG_OK;
 }
 
@@ -819,7 +977,10 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     HMSG_LAUNCH_CHECK();
   }
   ctx->prof_begin(PROF_ELTWISE);
-  k_im2col<<<(unsigned)(B * 3 * d.image), 256, 0, ctx->stream>>>(dx, a0, d.image, d.patch, G, vs->Kpad);
+  {
+    long long nrows = (long long)B * 3 * d.image;
+    k_im2col<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(dx, a0, nrows, d.image, d.patch, G, vs->Kpad);
+  }
   ctx->prof_end(PROF_ELTWISE, (double)B * 3 * d.image * d.image * 6);
   HMSG_LAUNCH_CHECK();
   if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
@@ -836,7 +997,7 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     ctx->prof_begin(PROF_ATTN);
     if (vs->attn_simple) {
       k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
-    } else {
+    } else if (vs->attn_v1) {
       size_t sm = (size_t)4 * 3 * 64 * ATT_LD * 2;
       if (!vs->smem_attr_set) {
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
@@ -844,6 +1005,14 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       }
       long long pairs = (long long)B * d.heads;
       k_attention_mma<<<(unsigned)((pairs + 3) / 4), 128, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+    } else {
+      if (!vs->smem_attr_set) {
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
+        vs->smem_attr_set = true;
+      }
+      long long pairs = (long long)B * d.heads;
+      int grid = (int)std::min<long long>((pairs + ATT2_WARPS - 1) / ATT2_WARPS, ctx->sm_count);
+      k_attention_mma2<<<grid, ATT2_WARPS * 32, ATT2_SMEM, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();

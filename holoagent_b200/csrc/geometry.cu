@@ -405,12 +405,16 @@ __device__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, con
   int bj = min(max((int)floor(fy), 0), g.ny - 1);
   int bk = min(max((int)floor(fz), 0), g.nz - 1);
   double best = INFINITY; int besti = -1;
-  double vs2 = g.vs * g.vs;
+  const double vs2 = g.vs * g.vs;
+  // distance (in cells) from the query to the nearest face of its own cell: every centroid of another cell is
+  // at least that far away (only meaningful when the query lies inside the grid cell it was binned to)
+  double mface = fmin(fmin(fmin(fx - bi, bi + 1 - fx), fmin(fy - bj, bj + 1 - fy)), fmin(fz - bk, bk + 1 - fz));
+  long long cw = -1; uint32_t cword = 0, cpref = 0;   // one-entry cache of (bitmap word, prefix)
   int maxr = max(g.nx, max(g.ny, g.nz));
   for (int r = 0; r <= maxr; r++) {
-    if (r >= 1) {
-      double lbr = (double)(r - 1) * g.vs;     // every cell of ring >= r is at least this far
-      if (besti >= 0 && best < lbr * lbr) break;
+    if (besti >= 0) {
+      if (r == 1 && mface > 0.0 && best < mface * mface * vs2) break;
+      if (r >= 2) { double lbr = (double)(r - 1) * g.vs; if (best < lbr * lbr) break; }   // every cell of ring >= r is at least this far
     }
     int i0 = max(bi - r, 0), i1 = min(bi + r, g.nx - 1);
     int j0 = max(bj - r, 0), j1 = min(bj + r, g.ny - 1);
@@ -429,14 +433,15 @@ __device__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, con
         for (int t = 0; t < nk; t++) {
           int ck = shell ? (bk - r + t) : (t == 0 ? bk - r : bk + r);
           if (ck < 0 || ck >= g.nz) continue;
-          if (!shell && r == 0 && t == 1) continue;
+          long long lin = colbase + ck;
+          long long w = lin >> 5;
+          if (w != cw) { cw = w; cword = __ldg(&bm[w]); cpref = 0xffffffffu; }
+          int b = lin & 31;
+          if (!((cword >> b) & 1u)) continue;                     // occupancy first: most neighbour cells are empty
           double az = fmax(0.0, fmax((double)ck - fz, fz - (double)(ck + 1)));
           if ((axy + az * az) * vs2 * 0.999999999 > best) continue;
-          long long lin = colbase + ck;
-          uint32_t word = __ldg(&bm[lin >> 5]);
-          int b = lin & 31;
-          if (!((word >> b) & 1u)) continue;
-          int idx = (int)(__ldg(&pf[lin >> 5]) + __popc(word & ((1u << b) - 1u)));
+          if (cpref == 0xffffffffu) cpref = __ldg(&pf[w]);
+          int idx = (int)(cpref + __popc(cword & ((1u << b) - 1u)));
           const double* q = nodes + (long long)idx * 3;
           double d2 = sqdist3(q[0], q[1], q[2], px, py, pz);
           if (d2 < best || (d2 == best && idx < besti)) { best = d2; besti = idx; }
