@@ -26,6 +26,7 @@ SIGNATURES = {
     "hmsg_sync": (_i32, [_vp]),
     "hmsg_stream": (_vp, [_vp]),
     "hmsg_launch_count": (_i64, [_vp]),
+    "hmsg_set_option": (_i32, [_vp, C.c_char_p, _i32]),
     "hmsg_prof_enable": (_i32, [_vp, C.c_uint32]),
     "hmsg_prof_read": (_i32, [_vp, _i32, C.POINTER(_f64), C.POINTER(_i64), C.POINTER(_f64)]),
     "hmsg_scene_begin": (_i32, [_vp, _i32, _i32, _vp, _f32, _f64, _i64]),

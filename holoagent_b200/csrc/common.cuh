@@ -40,6 +40,7 @@ struct KnnState;   // knn.cu
 struct GridDesc {
   double vmin[3];     // min_bound - vs/2  (Open3D voxel_min_bound)
   double vs;
+  double inv_vs;      // rn(1/vs): used only for the fast floor below and for pruning bounds
   int nx, ny, nz, nzp;   // nzp = nz rounded up to a multiple of 32: a bitmap word never spans columns
   long long nwords;
 };
@@ -195,14 +196,30 @@ __device__ __forceinline__ void unproject_px(unsigned short dep, int x, int y, c
   double ax = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[0], X), __dmul_rn(T[1], Y)), __dmul_rn(T[2], Z)), T[3]);
   double ay = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[4], X), __dmul_rn(T[5], Y)), __dmul_rn(T[6], Z)), T[7]);
   double az = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(T[8], X), __dmul_rn(T[9], Y)), __dmul_rn(T[10], Z)), T[11]);
-  wx = __ddiv_rn(ax, w);
-  wy = __ddiv_rn(ay, w);
-  wz = __ddiv_rn(az, w);
+  if (w == 1.0) {   // rigid pose (bottom row 0 0 0 1): x / 1.0 == x exactly, skip three fp64 divisions
+    wx = ax; wy = ay; wz = az;
+  } else {
+    wx = __ddiv_rn(ax, w);
+    wy = __ddiv_rn(ay, w);
+    wz = __ddiv_rn(az, w);
+  }
 }
 
 // Open3D VoxelDownSample: ref = (p - voxel_min_bound) / voxel_size; floor
 __device__ __forceinline__ double cell_coord(double p, double vmin, double vs) {
   return __ddiv_rn(__dsub_rn(p, vmin), vs);
+}
+
+// floor((p - vmin) / vs) exactly as the reference computes it, without paying an fp64 division per
+// coordinate: q = (p - vmin) * rn(1/vs) differs from rn((p - vmin)/vs) by < 7e-10 for |q| < 2^21, so
+// the floors agree unless q is within 1e-8 of an integer - only then is the exact division evaluated.
+__device__ __forceinline__ int cell_index(double p, double vmin, double vs, double inv_vs) {
+  double t = __dsub_rn(p, vmin);
+  double q = __dmul_rn(t, inv_vs);
+  double f = floor(q);
+  double frac = q - f;
+  if (frac < 1e-8 || frac > 1.0 - 1e-8) f = floor(__ddiv_rn(t, vs));
+  return (int)f;
 }
 
 __device__ __forceinline__ double sqdist3(double ax, double ay, double az, double bx, double by, double bz) {

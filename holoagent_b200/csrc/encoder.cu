@@ -330,6 +330,225 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 }
 
 // ------------------------------------------------------------------------------------------
+// 2-CTA variant (cta_group::2): a CTA pair (cluster of 2, same TPC) computes a 256x256 tile.
+// Each CTA stages its own 128 rows of A and 128 of the 256 B rows, so per k-block a CTA writes
+// 32 KB and the tensor core reads 8 KB per MMA from each CTA's shared memory: shared-memory
+// traffic per SM drops from ~190 B/clk (1-CTA, over the 128 B/clk port) to ~128 B/clk, which is
+// what caps the 1-CTA kernel at ~68 % tensor-pipe activity.  One thread of the leader CTA issues
+// tcgen05.mma.cta_group::2 (M=256); commits are multicast to both CTAs' barriers; both CTAs run
+// their own 16-warp epilogue on their own 128 TMEM lanes.
+// ------------------------------------------------------------------------------------------
+constexpr int STAGES2 = 6;
+constexpr int A2_STAGE_BYTES = 128 * BK * 2;   // 16 KB
+constexpr int B2_STAGE_BYTES = 128 * BK * 2;   // 16 KB (this CTA's half of the 256 B rows)
+constexpr int GEMM2_SMEM = STAGES2 * (A2_STAGE_BYTES + B2_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 + 256;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  // executed by both CTAs; the peer bit of the barrier address is cleared so the bytes land on the leader's barrier
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(map), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on `bar` in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {   // arrive on the same barrier in CTA `cta` of the cluster
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO, GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES2 * A2_STAGE_BYTES;
+  uint8_t* sO = smem + STAGES2 * (A2_STAGE_BYTES + B2_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sO + 2 * OUT_STAGE_BYTES);
+  uint64_t* full = bars;                   // [STAGES2]  (used in the leader)
+  uint64_t* empty = bars + STAGES2;        // [STAGES2]
+  uint64_t* tfull = bars + 2 * STAGES2;    // [2]
+  uint64_t* tempty = bars + 2 * STAGES2 + 2;   // [2]  (used in the leader: 32 arrivals = 16 warps x 2 CTAs)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int m_tiles = (g.M + 255) / 256, n_tiles = g.N / BN, k_blocks = g.K / BK;
+  const int num_tiles = m_tiles * n_tiles;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < STAGES2; i++) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 32); }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        int mb = tile / n_tiles, nb = tile % n_tiles;
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (leader) mbar_arrive_expect_tx(&full[s], 2 * (A2_STAGE_BYTES + B2_STAGE_BYTES));
+          tma_load_2d_2sm(sA + s * A2_STAGE_BYTES, &tmA, kb * BK, mb * 256 + (int)rank * 128, &full[s]);
+          tma_load_2d_2sm(sB + s * B2_STAGE_BYTES, &tmB, kb * BK, nb * BN + (int)rank * 128, &full[s]);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      // D=f32, A=B=f16, K-major both, N=256, M=256 (two CTAs x 128 rows)
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int s = 0; uint32_t ph = 0;
+      int as = 0; uint32_t aph = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+        mbar_wait(&tempty[as], aph ^ 1);
+        tc_fence_after();
+        uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+        for (int kb = 0; kb < k_blocks; kb++) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + s * A2_STAGE_BYTES));
+          uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * B2_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) umma_f16_2sm(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_commit_2sm(&empty[s]);
+          if (kb == k_blocks - 1) umma_commit_2sm(&tfull[as]);
+          if (++s == STAGES2) { s = 0; ph ^= 1; }
+        }
+        if (++as == 2) { as = 0; aph ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================== epilogue (16 warps per CTA, own 128 TMEM lanes) =====================
+    constexpr bool F16OUT = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU);
+    constexpr int CH_COLS = F16OUT ? 64 : 32;
+    constexpr int WCOLS = CH_COLS / 2;
+    constexpr int NCH = BN / CH_COLS;
+    const int ew = warp - 4;
+    const int q = ew & 3;
+    const int half = (ew >> 2) & 1;
+    const int grp = ew >> 3;
+    uint8_t* stg = sO + grp * OUT_STAGE_BYTES;
+    const int trow = q * 32 + lane;
+    const bool issuer = (q == 0 && half == 0 && lane == 0);
+    uint8_t* srow = stg + trow * 128;
+    const int sw = trow & 7;
+    int as = 0; uint32_t aph = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
+      int mb = tile / n_tiles, nb = tile % n_tiles;
+      mbar_wait(&tfull[as], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
+      const int row0 = mb * 256 + (int)rank * 128;
+#pragma unroll 1
+      for (int ch = grp; ch < NCH; ch += 2) {
+        if (issuer) tma_wait_read0();
+        named_bar_sync(1 + grp, 256);
+        const int col0 = nb * BN + ch * CH_COLS;
+        uint32_t r[WCOLS];
+        if (F16OUT) tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
+        else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
+        tmem_ld_wait();
+        const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
+        if (F16OUT) {
+#pragma unroll
+          for (int q4 = 0; q4 < 4; q4++) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
+            if (bp) {
+              float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (EPI == EPI_F16_BIAS_GELU) {
+              if (g.quick_gelu) {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; e++) v[e] = gelu_erf(v[e]);
+              }
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
+            *reinterpret_cast<uint4*>(srow + (((half * 4 + q4) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        } else {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; q8++) {
+            float4 v;
+            v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
+            v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
+            if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            *reinterpret_cast<float4*>(srow + (((half * 4 + q8) ^ sw) << 4)) = v;
+          }
+        }
+        fence_proxy_async();
+        named_bar_sync(1 + grp, 256);
+        if (issuer) {
+          if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, row0);
+          else tma_store_2d(&tmO, stg, col0, row0);
+          tma_commit_group();
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
+      if (++as == 2) { as = 0; aph ^= 1; }
+    }
+    if (issuer) tma_wait_all0();
+  }
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_2sm(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
 // element-wise / small kernels
 // ------------------------------------------------------------------------------------------
 // fp32 -> fp16 (weights upload), optional transpose [R,C] -> [C,R]
@@ -837,17 +1056,55 @@ static int32_t launch_gemm_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtenso
   return HMSG_OK;
 }
 
+template <int EPI>
+static int32_t launch_gemm2_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const GemmArgs& g) {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(k_gemm_f16_2sm<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM2_SMEM);
+    if (e != cudaSuccess) return ctx->fail(HMSG_ERR_CUDA, std::string("gemm2 smem attr: ") + cudaGetErrorString(e));
+    attr = true;
+  }
+  int tiles = ((g.M + 255) / 256) * (g.N / BN);
+  int grid = 2 * std::min(tiles, ctx->sm_count / 2);
+  ctx->prof_begin(PROF_GEMM);
+  k_gemm_f16_2sm<EPI><<<grid, GEMM_THREADS, GEMM2_SMEM, ctx->stream>>>(ta, tb, to, g);
+  ctx->prof_end(PROF_GEMM, 2.0 * g.M * (double)g.N * g.K);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+static int g_gemm_2sm = -1;
+int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
+  if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
+  if (!strcmp(key, "attn_variant")) {   // 0: v2 (cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel
+    if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
+    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->smem_attr_set = false;
+    return HMSG_OK;
+  }
+  return -1;
+}
+
 // C = A[M,K] * Wt[N,K]^T with epilogue
 static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const __half* Wt, int M, int N, int K, const float* bias, void* out,
                     int ldo) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
   CUtensorMap ta, tb, to;
   int32_t rc;
+  if (g_gemm_2sm < 0) { const char* e = getenv("HMSG_GEMM_2SM"); g_gemm_2sm = e ? atoi(e) : 0; }
+  const bool two_sm = g_gemm_2sm != 0 && M > 128;
   if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
-  if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, BN))) return rc;
+  if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, two_sm ? 128 : BN))) return rc;
   const bool f16out = (epi == EPI_F16_BIAS || epi == EPI_F16_BIAS_GELU);
   if ((rc = make_tmap(ctx, vs, &to, out, (uint64_t)M, (uint64_t)N, BM, f16out ? 2 : 4, (uint64_t)ldo))) return rc;
   GemmArgs g{M, N, K, bias, vs->desc.quick_gelu};
+  if (two_sm) {
+    switch (epi) {
+      case EPI_F16_BIAS: return launch_gemm2_t<EPI_F16_BIAS>(ctx, ta, tb, to, g);
+      case EPI_F16_BIAS_GELU: return launch_gemm2_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, to, g);
+      case EPI_F32_RESIDUAL: return launch_gemm2_t<EPI_F32_RESIDUAL>(ctx, ta, tb, to, g);
+      default: return launch_gemm2_t<EPI_F32_STORE>(ctx, ta, tb, to, g);
+    }
+  }
   switch (epi) {
     case EPI_F16_BIAS: return launch_gemm_t<EPI_F16_BIAS>(ctx, ta, tb, to, g);
     case EPI_F16_BIAS_GELU: return launch_gemm_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, to, g);

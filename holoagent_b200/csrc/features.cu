@@ -198,6 +198,79 @@ __global__ void __launch_bounds__(TPB) k_scatter(const int32_t* __restrict__ pix
   }
 }
 
+// Node-major batch scatter: one warp per node walks the batch's frames IN ORDER, so the fp32 sum
+// per node is formed in exactly the reference's frame order (load once, add each winning frame's
+// fp16-rounded feature, store once).  HBM traffic: one 2 KB RMW per node touched per BATCH (a node
+// is typically hit by many consecutive frames) instead of one per frame.
+template <int DV>
+__global__ void __launch_bounds__(TPB) k_scatter_batch(const unsigned long long* __restrict__ win, int n_frames, long long n_nodes,
+                                                       const uint32_t* __restrict__ maskbits, const float* __restrict__ Fp, int HW, int M, int MW,
+                                                       uint32_t epoch, float* __restrict__ sum_feats, float* __restrict__ counter) {
+  const int d = 128 * DV;
+  int lane = threadIdx.x & 31;
+  long long node = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (node >= n_nodes) return;
+  float4 acc[DV];
+  bool loaded = false;
+  int cnt = 0;
+  float4* dst = reinterpret_cast<float4*>(sum_feats + node * d);
+  for (int f0 = 0; f0 < n_frames; f0 += 32) {
+    int f = f0 + lane;
+    unsigned long long tag = (f < n_frames) ? win[(long long)f * n_nodes + node] : 0ULL;
+    unsigned hits = __ballot_sync(0xffffffffu, (uint32_t)(tag >> 32) == epoch);
+    while (hits) {
+      int s = __ffs(hits) - 1;
+      hits &= hits - 1;
+      unsigned p = __shfl_sync(0xffffffffu, (unsigned)(tag & 0xffffffffu), s);
+      int fr = f0 + s;
+      if (!loaded) {
+#pragma unroll
+        for (int j = 0; j < DV; j++) acc[j] = dst[lane + 32 * j];
+        loaded = true;
+      }
+      cnt++;
+      float4 v[DV];
+#pragma unroll
+      for (int j = 0; j < DV; j++) v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      bool any = false;
+      const uint32_t* mb = maskbits + ((long long)fr * HW + p) * MW;
+      const float* fpf = Fp + (long long)fr * M * d;
+      for (int w = 0; w < MW; w++) {
+        uint32_t bits = __ldg(&mb[w]);
+        while (bits) {
+          int m = __ffs(bits) - 1 + 32 * w;
+          bits &= bits - 1;
+          any = true;
+          const float4* row = reinterpret_cast<const float4*>(fpf + (long long)m * d);
+#pragma unroll
+          for (int j = 0; j < DV; j++) { float4 x = __ldg(&row[lane + 32 * j]); v[j].x += x.x; v[j].y += x.y; v[j].z += x.z; v[j].w += x.w; }
+        }
+      }
+      if (any) {
+        float nn = 0.f;
+#pragma unroll
+        for (int j = 0; j < DV; j++) nn += v[j].x * v[j].x + v[j].y * v[j].y + v[j].z * v[j].z + v[j].w * v[j].w;
+        for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        float den = fmaxf(sqrtf(nn), 1e-12f);
+#pragma unroll
+        for (int j = 0; j < DV; j++) {
+          acc[j].x += round_half(__fdiv_rn(v[j].x, den)); acc[j].y += round_half(__fdiv_rn(v[j].y, den));
+          acc[j].z += round_half(__fdiv_rn(v[j].z, den)); acc[j].w += round_half(__fdiv_rn(v[j].w, den));
+        }
+      }
+    }
+  }
+  if (cnt) {
+#pragma unroll
+    for (int j = 0; j < DV; j++) dst[lane + 32 * j] = acc[j];
+    if (lane == 0) {
+      float c = counter[node];
+      for (int i = 0; i < cnt; i++) c += 1.0f;     // counter[idx] += 1 once per frame (graph.py:411)
+      counter[node] = c;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(TPB) k_finalize_feats(const float* __restrict__ sum_feats, const float* __restrict__ counter, long long n, int d,
                                                         float* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -357,12 +430,21 @@ static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfe
   int HW = ctx->cam.H * ctx->cam.W;
   k_fuse<DV><<<n, TPB, M * sizeof(float), ctx->stream>>>(dfeats, M, w_masked, w_plain, ctx->Fp);
   HMSG_LAUNCH_CHECK();
-  int blocks = std::min((HW + TPB - 1) / TPB, ctx->sm_count * 8);
   ctx->prof_begin(PROF_SCATTER);
-  for (int fb = 0; fb < n; fb++) {
-    k_scatter<DV><<<blocks, TPB, 0, ctx->stream>>>(ctx->pix_idx + (size_t)fb * HW, ctx->win + (size_t)fb * ctx->n_nodes,
-                                                    ctx->maskbits + (size_t)fb * HW * ctx->batch_MW, ctx->Fp + (size_t)fb * M * 128 * DV, HW, M,
-                                                    ctx->batch_MW, ctx->epoch, ctx->sum_feats, ctx->counter);
+  static int per_frame = -1;
+  if (per_frame < 0) { const char* e = getenv("HMSG_SCATTER_PER_FRAME"); per_frame = e ? atoi(e) : 0; }
+  if (per_frame) {   // one launch per frame (pixel-major); kept for A/B comparison
+    int blocks = std::min((HW + TPB - 1) / TPB, ctx->sm_count * 8);
+    for (int fb = 0; fb < n; fb++) {
+      k_scatter<DV><<<blocks, TPB, 0, ctx->stream>>>(ctx->pix_idx + (size_t)fb * HW, ctx->win + (size_t)fb * ctx->n_nodes,
+                                                      ctx->maskbits + (size_t)fb * HW * ctx->batch_MW, ctx->Fp + (size_t)fb * M * 128 * DV, HW, M,
+                                                      ctx->batch_MW, ctx->epoch, ctx->sum_feats, ctx->counter);
+      HMSG_LAUNCH_CHECK();
+    }
+  } else if (ctx->n_nodes > 0) {
+    long long threads = ctx->n_nodes * 32;
+    k_scatter_batch<DV><<<(unsigned)((threads + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->win, n, ctx->n_nodes, ctx->maskbits, ctx->Fp, HW, M,
+                                                                                        ctx->batch_MW, ctx->epoch, ctx->sum_feats, ctx->counter);
     HMSG_LAUNCH_CHECK();
   }
   ctx->prof_end(PROF_SCATTER, 0.0);

@@ -118,9 +118,9 @@ __global__ void __launch_bounds__(TPB) k_bounds(FrameArgs a, long long* bounds) 
 
 // ----------------------------------------------------------------------------- cell ids
 __device__ __forceinline__ bool cell_of(const GridDesc& g, double wx, double wy, double wz, int& ci, int& cj, int& ck) {
-  ci = (int)floor(cell_coord(wx, g.vmin[0], g.vs));
-  cj = (int)floor(cell_coord(wy, g.vmin[1], g.vs));
-  ck = (int)floor(cell_coord(wz, g.vmin[2], g.vs));
+  ci = cell_index(wx, g.vmin[0], g.vs, g.inv_vs);
+  cj = cell_index(wy, g.vmin[1], g.vs, g.inv_vs);
+  ck = cell_index(wz, g.vmin[2], g.vs, g.inv_vs);
   return ci >= 0 && cj >= 0 && ck >= 0 && ci < g.nx && cj < g.ny && ck < g.nz;
 }
 __device__ __forceinline__ long long cell_lin(const GridDesc& g, int ci, int cj, int ck) {
@@ -400,7 +400,9 @@ __global__ void __launch_bounds__(TPB) k_compact_nodes(const uint32_t* bitmap, c
 // is below r*vs (every unvisited cell is at least that far).  Ties -> lower node index.
 __device__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
                          const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
-  double fx = cell_coord(px, g.vmin[0], g.vs), fy = cell_coord(py, g.vmin[1], g.vs), fz = cell_coord(pz, g.vmin[2], g.vs);
+  // fractional cell coordinates only steer the search order and the (slack-protected) pruning bounds,
+  // so the reciprocal multiply is enough here; every accepted candidate is compared with exact distances
+  double fx = (px - g.vmin[0]) * g.inv_vs, fy = (py - g.vmin[1]) * g.inv_vs, fz = (pz - g.vmin[2]) * g.inv_vs;
   int bi = min(max((int)floor(fx), 0), g.nx - 1);
   int bj = min(max((int)floor(fy), 0), g.ny - 1);
   int bk = min(max((int)floor(fz), 0), g.nz - 1);
@@ -633,6 +635,7 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   if (!(ctx->min_bound[0] <= ctx->max_bound[0])) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_build: no valid depth pixel in any frame");
   GridDesc& g = ctx->grid;
   g.vs = ctx->vs;
+  g.inv_vs = 1.0 / ctx->vs;
   int dims[3];
   for (int k = 0; k < 3; k++) {
     g.vmin[k] = ctx->min_bound[k] - ctx->vs * 0.5;                      // Open3D: min_bound - voxel_size*0.5

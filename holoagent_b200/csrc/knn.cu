@@ -318,6 +318,11 @@ static int32_t launch_pass_any(hmsg_ctx* ctx, KnnState* st, int BQ, const float*
 static int pick_bq(int nq) { return nq <= 1 ? 1 : nq <= 2 ? 2 : nq <= 4 ? 4 : nq <= 8 ? 8 : 16; }
 static int g_knn_bq_override = 0;   // bench/tuning hook: HMSG_KNN_BQ env
 
+int32_t knn_set_option(hmsg_ctx*, const char* key, int value) {
+  if (!strcmp(key, "knn_bq")) { g_knn_bq_override = value; return HMSG_OK; }
+  return -1;
+}
+
 int32_t knn_destroy(hmsg_ctx* ctx) {
   KnnState* st = ctx->knn;
   if (!st) return HMSG_OK;

@@ -105,6 +105,9 @@ class HmsgEngine:
     def launches(self) -> int:
         return int(self.lib.hmsg_launch_count(self.h))
 
+    def set_option(self, key: str, value: int):
+        self._ck(self.lib.hmsg_set_option(self.h, key.encode(), int(value)))
+
     PROF = {"gemm": 0, "attn": 1, "eltwise": 2, "knn": 3, "nn": 4, "scatter": 5, "geom": 6, "crops": 7}
 
     def prof_enable(self, *classes):

@@ -45,6 +45,9 @@ void*       hmsg_stream(hmsg_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t     hmsg_launch_count(const hmsg_ctx* ctx);
 int32_t     hmsg_version(void);
+/* tuning / A-B switches: "gemm_2sm" (0|1: cta_group::2 GEMM), "attn_variant" (0 v2, 1 v1, 2 fp32
+ * reference kernel), "knn_bq" (queries per pass, 0 = auto) */
+int32_t     hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value);
 /* Per-kernel-class device timing with CUDA events on the ctx stream (bench.py roofline).
  * class: 0 gemm (work = flops), 1 attention, 2 elementwise/LN, 3 knn pass (work = bytes of E
  * streamed), 4 pixel->node + winner, 5 feature scatter, 6 geometry passes, 7 crops.

@@ -20,15 +20,18 @@ def timed(fn, reps=5, warm=2):
 
 what = sys.argv[1:] or ["gemm", "knn", "enc", "geom"]
 if "gemm" in what:
+  for two in (0, 1):
+    eng.set_option("gemm_2sm", two)
     for (M, N, K) in [(52000, 2304, 768), (52000, 768, 768), (52000, 3072, 768), (52000, 768, 3072), (8192, 8192, 8192 // 8 * 8)]:
         A = (torch.randn(M, K, device="cuda") * 0.5).half(); W = (torch.randn(N, K, device="cuda") * 0.05).half()
         C = torch.zeros(M, N, device="cuda"); torch.cuda.synchronize()
         ms = timed(lambda: eng.gemm_debug(A, W, C, M, N, K))
         ref = (A[:256].float() @ W.float().T)
         err = (C[:256] - ref).abs().max().item() / ref.abs().max().item()
-        res[f"gemm_{M}x{N}x{K}"] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "relerr": err}
-        print(res[f"gemm_{M}x{N}x{K}"], flush=True)
+        res[f"gemm{two}_{M}x{N}x{K}"] = {"ms": ms, "tflops": 2.0 * M * N * K / ms / 1e9, "relerr": err}
+        print(two, res[f"gemm{two}_{M}x{N}x{K}"], flush=True)
         del A, W, C
+  eng.set_option("gemm_2sm", 0)
 if "knn" in what:
     N, d = 1_000_000, 512
     E, Q = synth.make_knn_tables(N, 64, d, device="cuda")
@@ -45,11 +48,14 @@ if "knn" in what:
 if "enc" in what:
     sd = synth.make_vit_weights()
     eng.encoder_load(sd)
-    for B in (65, 1040, 2080):
+    for two in (0, 1):
+      eng.set_option("gemm_2sm", two)
+      for B in (65, 1040, 2080):
         x = torch.randn(B, 3, 224, 224, device="cuda"); torch.cuda.synchronize()
         ms = timed(lambda: eng.encode_images(x), reps=3, warm=1)
-        res[f"enc_B{B}"] = {"ms": ms, "img_per_s": B / ms * 1e3, "tflops": B * 8.82e9 / ms / 1e9}
-        print(B, res[f"enc_B{B}"], flush=True)
+        res[f"enc{two}_B{B}"] = {"ms": ms, "img_per_s": B / ms * 1e3, "tflops": B * 8.82e9 / ms / 1e9}
+        print(two, B, res[f"enc{two}_B{B}"], flush=True)
+    eng.set_option("gemm_2sm", 0)
 if "geom" in what:
     F, H, W = 200, 480, 640
     d, c, T, K = synth.make_frames(np.arange(F), H, W, device="cuda")

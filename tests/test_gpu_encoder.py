@@ -9,8 +9,10 @@ from holoagent_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 768), (1000, 768, 3072), (65, 512, 768)])
-def test_gemm_tcgen05(engine, M, N, K):
+@pytest.mark.parametrize("two_sm", [0, 1])
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 512, 768), (1000, 768, 3072), (65, 512, 768), (5000, 2304, 768)])
+def test_gemm_tcgen05(engine, M, N, K, two_sm):
+    engine.set_option("gemm_2sm", two_sm)
     g = torch.Generator().manual_seed(M + N + K)
     A = (torch.randn(M, K, generator=g) * 0.5).half()
     W = (torch.randn(N, K, generator=g) * 0.05).half()
@@ -20,6 +22,7 @@ def test_gemm_tcgen05(engine, M, N, K):
     torch.cuda.synchronize()
     engine.gemm_debug(Ad, Wd, Cd, M, N, K)
     out = Cd.cpu()
+    engine.set_option("gemm_2sm", 0)
     err = (out - ref).abs().max().item()
     assert err <= 1e-3 * ref.abs().max().item() + 1e-5, err
 
@@ -45,6 +48,18 @@ def test_vit_forward(engine, vit, B):
     assert err <= 1e-3
     assert np.all(cos > 1 - 1e-5)
     assert np.allclose(np.linalg.norm(out, axis=-1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("opt,val", [("gemm_2sm", 1), ("attn_variant", 1), ("attn_variant", 2)])
+def test_vit_variants_agree(engine, vit, opt, val):
+    x = torch.randn(70, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    base = engine.encode_images(x.numpy())
+    engine.set_option(opt, val)
+    try:
+        alt = engine.encode_images(x.numpy())
+    finally:
+        engine.set_option(opt, 0)
+    assert np.abs(alt - base).max() < 2e-4
 
 
 def test_vit_device_path_matches_host_path(engine, vit):
