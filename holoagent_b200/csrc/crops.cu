@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
                                                    const int* __restrict__ bounds, const int* __restrict__ kk, uint32_t* __restrict__ t1) {
   __shared__ short s_xofs[CROP_MID];
   __shared__ short s_a[CROP_MID][2];
-  __shared__ int s_h[2][CROP_MID * 3];
+  __shared__ int s_h[2][CROP_MID * 3];      // horizontally interpolated source rows, already >> 4
   __shared__ uint32_t s_row[CROP_MID];
+  __shared__ int s_ry[ROWS_PER_BLOCK][3];   // per destination row: source row index (unclamped), beta0, beta1
   const int fb = blockIdx.z, ci = blockIdx.y;
   const bool masked = ci < M;
   const int m = masked ? ci : ci - M;
@@ -140,6 +141,11 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
     cv_coef(d, scale_x, cw, true, s, a0, a1);
     s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
   }
+  if (threadIdx.x < ROWS_PER_BLOCK) {
+    int sy, b0, b1;
+    cv_coef(dy0 + threadIdx.x, scale_y, ch, false, sy, b0, b1);
+    s_ry[threadIdx.x][0] = sy; s_ry[threadIdx.x][1] = b0; s_ry[threadIdx.x][2] = b1;
+  }
   // PIL coefficients of this thread's output column
   const int ox = threadIdx.x;
   int kreg[KS]; int pxmin = 0, pcnt = 0;
@@ -155,8 +161,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   int sl0 = 0;
   for (int r = 0; r < ROWS_PER_BLOCK; r++) {
     const int dy = dy0 + r;
-    int sy, b0, b1;
-    cv_coef(dy, scale_y, ch, false, sy, b0, b1);
+    const int sy = s_ry[r][0], b0 = s_ry[r][1], b1 = s_ry[r][2];
     const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
     int need0 = 1, need1 = 1;
     if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
@@ -175,7 +180,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
           a1 *= (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
         }
 #pragma unroll
-        for (int c = 0; c < 3; c++) hb[d * 3 + c] = (int)srow[s0 * 3 + c] * a0 + (int)srow[s1 * 3 + c] * a1;
+        for (int c = 0; c < 3; c++) hb[d * 3 + c] = ((int)srow[s0 * 3 + c] * a0 + (int)srow[s1 * 3 + c] * a1) >> 4;
       }
     }
     tag0 = r0; tag1 = r1;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
       uint32_t pk = 0;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        int v = (((b0 * (h0[d * 3 + c] >> 4)) >> 16) + ((b1 * (h1[d * 3 + c] >> 4)) >> 16) + 2) >> 2;
+        int v = (((b0 * h0[d * 3 + c]) >> 16) + ((b1 * h1[d * 3 + c]) >> 16) + 2) >> 2;
         pk |= (uint32_t)(v & 255) << (8 * c);
       }
       s_row[d] = pk;
@@ -261,6 +266,37 @@ __global__ void __launch_bounds__(256) k_crop_cols(const uint32_t* __restrict__ 
   }
 }
 
+// same pass, but emits the encoder's patch matrix directly: A0[crop*G*G + py*G + px][c*P*P + iy*P + ix] = fp16(value)
+// (what k_im2col would produce from the fp32 crop) - saves one 1.2 GB write + read per 32-frame batch.
+__global__ void __launch_bounds__(256) k_crop_cols_patches(const uint32_t* __restrict__ t1, int rows_alloc, int top, const int* __restrict__ bounds,
+                                                           const int* __restrict__ kk, int ksize, int crop0, int crops_per_frame, int P, int G, int Kpad,
+                                                           __half* __restrict__ a0) {
+  const long long crop = (long long)blockIdx.z * crops_per_frame + crop0 + blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= 224 * 224) return;
+  int oy = p / 224, ox = p - oy * 224;
+  int sy = oy + top;
+  int ymin = __ldg(&bounds[sy * 2]), cnt = __ldg(&bounds[sy * 2 + 1]);
+  const uint32_t* src = t1 + crop * (long long)rows_alloc * 224 + (long long)ymin * 224 + ox;
+  int acc[3] = {1 << 21, 1 << 21, 1 << 21};
+  for (int k = 0; k < cnt; k++) {
+    int kv = __ldg(&kk[sy * ksize + k]);
+    uint32_t px = __ldg(src + (long long)k * 224);
+    acc[0] += (int)(px & 255) * kv; acc[1] += (int)((px >> 8) & 255) * kv; acc[2] += (int)((px >> 16) & 255) * kv;
+  }
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  const int py = oy / P, iy = oy - py * P, pxx = ox / P, ix = ox - pxx * P;
+  __half* dst = a0 + (crop * G * G + py * G + pxx) * (long long)Kpad + iy * P + ix;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    int v = min(max(acc[c] >> 22, 0), 255);
+    float f = __fdiv_rn((float)v, 255.0f);
+    f = __fdiv_rn(__fsub_rn(f, mean[c]), stdv[c]);
+    dst[c * P * P] = __float2half_rn(f);
+  }
+}
+
 int32_t crops_destroy(hmsg_ctx* ctx) {
   auto it = g_crop_states.find(ctx);
   if (it == g_crop_states.end()) return HMSG_OK;
@@ -272,12 +308,12 @@ int32_t crops_destroy(hmsg_ctx* ctx) {
   return HMSG_OK;
 }
 
-extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin,
-                                   int32_t on_device, float** crops_dev_out) {
-  if (!ctx) return HMSG_ERR_ARG;
+// a0 != nullptr: emit the fp16 patch matrix (P, G, Kpad describe it) instead of fp32 NCHW crops
+int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
+                  float** crops_dev_out, __half* a0, int P, int G, int Kpad) {
   if (ctx->batch_begin != frame_begin || ctx->batch_n != n || ctx->batch_M != M)
     return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: masks of this batch were not set (hmsg_masks_*)");
-  if (!xywh || !crops_dev_out) return ctx->fail(HMSG_ERR_ARG, "hmsg_make_crops: null argument");
+  if (!xywh) return ctx->fail(HMSG_ERR_ARG, "hmsg_make_crops: null argument");
   const int H = ctx->cam.H, W = ctx->cam.W;
   CropState*& cs = g_crop_states[ctx];
   if (!cs) cs = new CropState();
@@ -294,7 +330,7 @@ extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n
   const int rows_alloc = std::max(CROP_MID, H);
   const long long ncrops = (long long)n * (2 * M + 1);
   if ((rc = ctx->reserve(&cs->t1, &cs->t1_bytes, (size_t)ncrops * rows_alloc * 224 * 4))) return rc;
-  if ((rc = ctx->reserve(&cs->out, &cs->out_bytes, (size_t)ncrops * 3 * 224 * 224 * 4))) return rc;
+  if (!a0 && (rc = ctx->reserve(&cs->out, &cs->out_bytes, (size_t)ncrops * 3 * 224 * 224 * 4))) return rc;
   const int32_t* dbox = xywh;
   if (!on_device) {
     if ((rc = ctx->reserve(&cs->boxes, &cs->boxes_bytes, (size_t)n * M * 16))) return rc;
@@ -309,13 +345,27 @@ extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n
   k_frame_rows<<<dim3(H, n), 256, 0, ctx->stream>>>(ctx->rgb, frame_begin, H, W, M, left, tw->bounds, tw->kk, tw->ksize, rows_alloc, cs->t1);
   HMSG_LAUNCH_CHECK();
   const int pb = (224 * 224 + 255) / 256;
-  k_crop_cols<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, cs->out);
-  HMSG_LAUNCH_CHECK();
-  k_crop_cols<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, cs->out);
-  HMSG_LAUNCH_CHECK();
-  ctx->prof_end(PROF_CROPS, (double)ncrops * 3 * 224 * 224 * 4);
-  *crops_dev_out = cs->out;
+  if (a0) {
+    k_crop_cols_patches<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, P, G, Kpad, a0);
+    HMSG_LAUNCH_CHECK();
+    k_crop_cols_patches<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, P, G, Kpad, a0);
+    HMSG_LAUNCH_CHECK();
+  } else {
+    k_crop_cols<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, cs->out);
+    HMSG_LAUNCH_CHECK();
+    k_crop_cols<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, cs->out);
+    HMSG_LAUNCH_CHECK();
+  }
+  ctx->prof_end(PROF_CROPS, (double)ncrops * 3 * 224 * 224 * (a0 ? 2 : 4));
+  if (crops_dev_out) *crops_dev_out = cs->out;
   return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin,
+                                   int32_t on_device, float** crops_dev_out) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!crops_dev_out) return ctx->fail(HMSG_ERR_ARG, "hmsg_make_crops: null argument");
+  return crops_run(ctx, frame_begin, n, M, xywh, bbox_margin, on_device, crops_dev_out, nullptr, 0, 0, 0);
 }
 
 extern "C" int32_t hmsg_crops_read(hmsg_ctx* ctx, int64_t n_crops, float* host_out) {

@@ -944,6 +944,127 @@ __global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __h
   cp_async_wait<0>();
 }
 
+constexpr int ATT3_GROUPS = 4;                   // (image, head) tiles in flight per block, 2 warps each
+constexpr int ATT3_SMEM = ATT3_GROUPS * 2 * 3 * ATT2_TILE * 2;
+
+__global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
+                                                                       int W, float scale) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  // two warps share one (image, head) tile: 8 warps per SM (2 per scheduler) hide ldmatrix / HMMA latency,
+  // and each warp handles every other 16-row query tile
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = warp >> 1, wsub = warp & 1, l64 = wsub * 32 + lane;
+  __half* wbase = reinterpret_cast<__half*>(att_smem) + (size_t)grp * 2 * 3 * ATT2_TILE;
+  // zero both buffers once: rows >= T are never written by cp.async and V padding rows must be finite (P = 0 there)
+  for (int i = l64; i < 2 * 3 * ATT2_TILE / 8; i += 64) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  named_bar_sync(1 + grp, 64);
+  const long long npairs = (long long)B * heads;
+  const long long gw = (long long)blockIdx.x * ATT3_GROUPS + grp, tw = (long long)gridDim.x * ATT3_GROUPS;
+  const int ld = 3 * W;
+  auto issue = [&](long long pair, int bi) {
+    int b = (int)(pair / heads), h = (int)(pair % heads);
+    __half* sQ = wbase + bi * 3 * ATT2_TILE;
+    const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
+    for (int i = l64; i < T * 8; i += 64) {
+      int r = i >> 3, ch = i & 7;
+      const __half* src = src0 + (long long)r * ld + ch * 8;
+      __half* dst = sQ + r * ATT_LD + ch * 8;
+      cp_async16(dst, src);
+      cp_async16(dst + ATT2_TILE, src + W);
+      cp_async16(dst + 2 * ATT2_TILE, src + 2 * W);
+    }
+  };
+  if (gw < npairs) issue(gw, 0);
+  cp_async_commit();
+  int cur = 0;
+  const int g = lane >> 2, t = lane & 3;
+  const int m_tiles = (T + 15) / 16;
+  for (long long pair = gw; pair < npairs; pair += tw) {
+    if (pair + tw < npairs) issue(pair + tw, cur ^ 1);
+    cp_async_commit();
+    cp_async_wait<1>();
+    named_bar_sync(1 + grp, 64);       // both warps' cp.async data is visible to both
+    const __half* sQ = wbase + cur * 3 * ATT2_TILE;
+    const __half* sK = sQ + ATT2_TILE;
+    const __half* sV = sK + ATT2_TILE;
+    const int b = (int)(pair / heads), h = (int)(pair % heads);
+    for (int mi = wsub; mi < m_tiles; mi += 2) {
+      float s[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+        uint32_t a[4];
+        ldsm_x4(a, sQ + (mi * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+#pragma unroll
+        for (int np = 0; np < 4; np++) {     // two key tiles per ldmatrix.x4
+          uint32_t bb[4];
+          ldsm_x4(bb, sK + ((np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma_16816(s[np * 2], a, bb);
+          mma_16816(s[np * 2 + 1], a, bb + 2);
+        }
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          int col = ni * 8 + 2 * t + e;
+          float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
+          float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
+          s[ni][e] = v0; s[ni][2 + e] = v1;
+          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+        }
+      }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          float p0 = __expf(s[ni][e] - mx0), p1 = __expf(s[ni][2 + e] - mx1);
+          s[ni][e] = p0; s[ni][2 + e] = p1;
+          sum0 += p0; sum1 += p1;
+        }
+      }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+      float oacc[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        uint32_t a[4];
+        __half2 h0 = __floats2half2_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
+        __half2 h1 = __floats2half2_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
+        __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+        __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+        a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
+        a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+#pragma unroll
+        for (int np = 0; np < 4; np++) {     // two d-column tiles per ldmatrix.x4.trans
+          uint32_t bb[4];
+          ldsm_x4_t(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + (np * 2 + (lane >> 4)) * 8);
+          mma_16816(oacc[np * 2], a, bb);
+          mma_16816(oacc[np * 2 + 1], a, bb + 2);
+        }
+      }
+      const int r0 = mi * 16 + g, r1 = r0 + 8;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+        int col = h * 64 + ni * 8 + 2 * t;
+        if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0], oacc[ni][1]);
+        if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2], oacc[ni][3]);
+      }
+    }
+    named_bar_sync(1 + grp, 64);       // both warps are done with buf[cur] before it is refilled
+    cur ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
 // straightforward fp32 reference attention (debug: HMSG_ATTN_SIMPLE=1), one block per (image, head)
 __global__ void __launch_bounds__(128) k_attention_simple(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads, int W,
                                                           float scale) {
@@ -1013,6 +1134,7 @@ struct VitState {
   float* out_stage = nullptr; size_t out_stage_bytes = 0;
   bool attn_simple = false;
   bool attn_v1 = false;
+  bool attn_v2 = false;
   bool smem_attr_set = false;
 };
 
@@ -1076,9 +1198,9 @@ static int32_t launch_gemm2_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtens
 static int g_gemm_2sm = -1;
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
-  if (!strcmp(key, "attn_variant")) {   // 0: v2 (cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel
+  if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
-    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->smem_attr_set = false;
+    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->smem_attr_set = false;
     return HMSG_OK;
   }
   return -1;
@@ -1221,25 +1343,25 @@ static int32_t ensure_ws(hmsg_ctx* ctx, VitState* vs, int B) {
 }
 
 template <int NV>
-static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize) {
+static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize, bool patches_ready = false) {
   const hmsg_vit_desc& d = vs->desc;
   const int W = d.width, T = vs->T, G = vs->G;
   const long long R = (long long)B * T, RP = (long long)B * (T - 1);
   int32_t rc;
   __half* a0 = vs->gbuf;
   float* patch = reinterpret_cast<float*>(vs->qkv);
-  if (vs->Kpad != vs->Kc) {
+  if (!patches_ready && vs->Kpad != vs->Kc) {
     long long n = RP * (vs->Kpad - vs->Kc);
     k_zero_pad_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a0, RP, vs->Kc, vs->Kpad);
     HMSG_LAUNCH_CHECK();
   }
-  ctx->prof_begin(PROF_ELTWISE);
-  {
+  if (!patches_ready) {
+    ctx->prof_begin(PROF_ELTWISE);
     long long nrows = (long long)B * 3 * d.image;
     k_im2col<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(dx, a0, nrows, d.image, d.patch, G, vs->Kpad);
+    ctx->prof_end(PROF_ELTWISE, (double)B * 3 * d.image * d.image * 6);
+    HMSG_LAUNCH_CHECK();
   }
-  ctx->prof_end(PROF_ELTWISE, (double)B * 3 * d.image * d.image * 6);
-  HMSG_LAUNCH_CHECK();
   if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
   k_embed_lnpre<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->x, R, T);
   HMSG_LAUNCH_CHECK();
@@ -1262,7 +1384,7 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       }
       long long pairs = (long long)B * d.heads;
       k_attention_mma<<<(unsigned)((pairs + 3) / 4), 128, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
-    } else {
+    } else if (vs->attn_v2) {
       if (!vs->smem_attr_set) {
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma2, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT2_SMEM));
         vs->smem_attr_set = true;
@@ -1270,6 +1392,14 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       long long pairs = (long long)B * d.heads;
       int grid = (int)std::min<long long>((pairs + ATT2_WARPS - 1) / ATT2_WARPS, ctx->sm_count);
       k_attention_mma2<<<grid, ATT2_WARPS * 32, ATT2_SMEM, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+    } else {
+      if (!vs->smem_attr_set) {
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM));
+        vs->smem_attr_set = true;
+      }
+      long long pairs = (long long)B * d.heads;
+      int grid = (int)std::min<long long>((pairs + ATT3_GROUPS - 1) / ATT3_GROUPS, ctx->sm_count);
+      k_attention_mma3<<<grid, ATT3_GROUPS * 64, ATT3_SMEM, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();
@@ -1290,13 +1420,13 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
   return HMSG_OK;
 }
 
-static int32_t forward_chunk(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize) {
+static int32_t forward_chunk(hmsg_ctx* ctx, VitState* vs, const float* dx, int B, float* dout, int normalize, bool patches_ready = false) {
   switch (vs->desc.width / 128) {
-    case 6: return forward_chunk_t<6>(ctx, vs, dx, B, dout, normalize);
-    case 8: return forward_chunk_t<8>(ctx, vs, dx, B, dout, normalize);
-    case 10: return forward_chunk_t<10>(ctx, vs, dx, B, dout, normalize);
-    case 2: return forward_chunk_t<2>(ctx, vs, dx, B, dout, normalize);
-    case 4: return forward_chunk_t<4>(ctx, vs, dx, B, dout, normalize);
+    case 6: return forward_chunk_t<6>(ctx, vs, dx, B, dout, normalize, patches_ready);
+    case 8: return forward_chunk_t<8>(ctx, vs, dx, B, dout, normalize, patches_ready);
+    case 10: return forward_chunk_t<10>(ctx, vs, dx, B, dout, normalize, patches_ready);
+    case 2: return forward_chunk_t<2>(ctx, vs, dx, B, dout, normalize, patches_ready);
+    case 4: return forward_chunk_t<4>(ctx, vs, dx, B, dout, normalize, patches_ready);
   }
   return ctx->fail(HMSG_ERR_ARG, "encoder: unsupported width");
 }
@@ -1315,6 +1445,30 @@ int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, in
     if ((rc = forward_chunk(ctx, vs, dx + (size_t)b0 * img, nb, dout + (size_t)b0 * vs->desc.out_dim, normalize))) return rc;
   }
   return HMSG_OK;
+}
+
+int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
+                  float** crops_dev_out, __half* a0, int P, int G, int Kpad);
+
+// fused ingest entry: crops of a frame batch are resampled straight into the encoder's fp16 patch
+// matrix (no fp32 crop tensor, no im2col pass) and encoded.  feats_out [n*(2M+1), out_dim] device.
+extern "C" int32_t hmsg_encode_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int32_t* xywh, int32_t bbox_margin,
+                                     int32_t on_device, float* feats_out) {
+  if (!ctx) return HMSG_ERR_ARG;
+  VitState* vs = ctx->vit;
+  if (!vs) return ctx->fail(HMSG_ERR_STATE, "hmsg_encode_crops: call hmsg_encoder_load first");
+  if (!feats_out || !xywh) return ctx->fail(HMSG_ERR_ARG, "hmsg_encode_crops: null argument");
+  if (vs->desc.image != 224) return ctx->fail(HMSG_ERR_ARG, "hmsg_encode_crops: the crop kernels emit 224x224 inputs");
+  const int B = n * (2 * M + 1);
+  int32_t rc;
+  if (B > 4160 || vs->Kpad != vs->Kc) {   // large batches / padded K: unfused path
+    float* crops = nullptr;
+    if ((rc = crops_run(ctx, frame_begin, n, M, xywh, bbox_margin, on_device, &crops, nullptr, 0, 0, 0))) return rc;
+    return vit_encode_device(ctx, crops, B, feats_out, 1);
+  }
+  if ((rc = ensure_ws(ctx, vs, B))) return rc;
+  if ((rc = crops_run(ctx, frame_begin, n, M, xywh, bbox_margin, on_device, nullptr, vs->gbuf, vs->desc.patch, vs->G, vs->Kpad))) return rc;
+  return forward_chunk(ctx, vs, nullptr, B, feats_out, 1, true);
 }
 
 extern "C" int32_t hmsg_encode_images(hmsg_ctx* ctx, const float* nchw, int32_t B, float* out, int32_t normalize, int32_t on_device) {

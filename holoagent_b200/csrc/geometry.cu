@@ -398,8 +398,8 @@ __global__ void __launch_bounds__(TPB) k_compact_nodes(const uint32_t* bitmap, c
 // around the query's cell are visited; a cell is skipped when the distance from the query to
 // the cell's box already exceeds the best distance; the search stops once the best distance
 // is below r*vs (every unvisited cell is at least that far).  Ties -> lower node index.
-__device__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
-                         const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
+__device__ __noinline__ int nn_search_rings(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
+                                           const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
   // fractional cell coordinates only steer the search order and the (slack-protected) pruning bounds,
   // so the reciprocal multiply is enough here; every accepted candidate is compared with exact distances
   double fx = (px - g.vmin[0]) * g.inv_vs, fy = (py - g.vmin[1]) * g.inv_vs, fz = (pz - g.vmin[2]) * g.inv_vs;
@@ -453,6 +453,59 @@ __device__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, con
   }
   best_out = best;
   return besti;
+}
+
+// Fast path of the exact nearest-node search.  Almost every pixel finds its nearest centroid in
+// its own voxel or one of the 26 neighbours, and most of those cells are empty on surfaces, so:
+// (1) gather the 3x3x3 occupancy bits from 9 bitmap columns, (2) visit only occupied cells, own cell
+// first, pruning with an fp32 lower bound of the point-to-cell-box distance (with slack), exact
+// float64 distance for the survivors, (3) accept if the best distance is below one voxel edge (every
+// cell outside the 3x3x3 block is at least that far); otherwise fall back to the generic ring search.
+// Keeps all lanes of a warp on one short straight-line path (the generic search ran at 15.8/32 lanes).
+__device__ __forceinline__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
+                                         const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
+  const double fxd = (px - g.vmin[0]) * g.inv_vs, fyd = (py - g.vmin[1]) * g.inv_vs, fzd = (pz - g.vmin[2]) * g.inv_vs;
+  const int bi = (int)floor(fxd), bj = (int)floor(fyd), bk = (int)floor(fzd);
+  if (bi < 0 || bj < 0 || bk < 0 || bi >= g.nx || bj >= g.ny || bk >= g.nz) return nn_search_rings(g, bm, pf, nodes, px, py, pz, best_out);
+  const float ux = (float)(fxd - bi), uy = (float)(fyd - bj), uz = (float)(fzd - bk);   // position inside the own cell, [0,1)
+  // per-axis gap (in cells) to the neighbour at offset -1 / 0 / +1
+  auto gap = [](int dd, float u) { return dd < 0 ? u : (dd > 0 ? 1.f - u : 0.f); };
+  const float vs2f = (float)(g.vs * g.vs) * 0.9999f;      // slack: the bound must never exceed the true distance
+  double best = INFINITY; int besti = -1;
+  float bestf = INFINITY;
+  // visit order: own column first (dj = di = 0), then the rest
+#pragma unroll 1
+  for (int c = 0; c < 9; c++) {
+    const int cc = (c == 0) ? 4 : (c <= 4 ? c - 1 : c);   // 4,0,1,2,3,5,6,7,8
+    const int di = cc / 3 - 1, dj = cc % 3 - 1;
+    const int ci = bi + di, cj = bj + dj;
+    if (ci < 0 || cj < 0 || ci >= g.nx || cj >= g.ny) continue;
+    const float gxi = gap(di, ux), gyj = gap(dj, uy);
+    const float axy = gxi * gxi + gyj * gyj;
+    if (axy * vs2f > bestf) continue;
+    const long long colbase = ((long long)ci * g.ny + cj) * g.nzp;
+    // bits for k = bk-1, bk, bk+1 (a column never crosses its own nzp-padded words, but bk-1/bk+1 may sit in the neighbouring word)
+#pragma unroll
+    for (int t = 0; t < 3; t++) {
+      const int dk = (t == 0) ? 0 : (t == 1 ? -1 : 1);     // own k first
+      const int ck = bk + dk;
+      if (ck < 0 || ck >= g.nz) continue;
+      const long long lin = colbase + ck;
+      const uint32_t word = __ldg(&bm[lin >> 5]);
+      const int b = (int)(lin & 31);
+      if (!((word >> b) & 1u)) continue;
+      const float gzk = gap(dk, uz);
+      const float lb = (axy + gzk * gzk) * vs2f;
+      if (lb > bestf) continue;
+      const int idx = (int)(__ldg(&pf[lin >> 5]) + __popc(word & ((1u << b) - 1u)));
+      const double* q = nodes + (long long)idx * 3;
+      const double d2 = sqdist3(q[0], q[1], q[2], px, py, pz);
+      if (d2 < best || (d2 == best && idx < besti)) { best = d2; besti = idx; bestf = (float)d2 * 1.0001f; }
+    }
+  }
+  // every cell outside the 3x3x3 block is farther than one voxel edge minus nothing: >= (1 + min gap) * vs >= vs
+  if (besti >= 0 && best < g.vs * g.vs) { best_out = best; return besti; }
+  return nn_search_rings(g, bm, pf, nodes, px, py, pz, best_out);
 }
 
 // per-frame API kernel: idx int64 (-1 invalid), dist f64

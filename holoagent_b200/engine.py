@@ -299,6 +299,16 @@ class HmsgEngine:
         self._ck(self.lib.hmsg_make_crops(self.h, int(frame_begin), int(n), int(M), ptr(xywh), int(bbox_margin), 1 if dev else 0, C.byref(out)))
         return out.value
 
+    def encode_crops(self, frame_begin, n, M, xywh, bbox_margin, feats_out):
+        """fused crops -> patch matrix -> encoder; feats_out: torch CUDA tensor [n*(2M+1), d]"""
+        dev = _is_dev(xywh)
+        if not dev:
+            xywh = np.ascontiguousarray(xywh, dtype=np.int32)
+        else:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_encode_crops(self.h, int(frame_begin), int(n), int(M), ptr(xywh), int(bbox_margin), 1 if dev else 0, ptr(feats_out)))
+        return feats_out
+
     def crops_read(self, n_crops):
         a = np.empty((n_crops, 3, 224, 224), np.float32)
         self._ck(self.lib.hmsg_crops_read(self.h, int(n_crops), ptr(a)))

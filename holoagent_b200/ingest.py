@@ -69,8 +69,7 @@ class IngestJob:
             else:
                 eng.masks_boxes(b0, self.boxes_dev[b0:b0 + n])
             if self.crops_mode == "device":
-                crops_ptr = eng.make_crops(b0, n, M, (boxes_host if boxes_host is not None else self.boxes_dev)[b0:b0 + n], self.margin)
-                eng.encode_images_ptr(crops_ptr, B, self.feats)
+                eng.encode_crops(b0, n, M, (boxes_host if boxes_host is not None else self.boxes_dev)[b0:b0 + n], self.margin, self.feats)
             else:
                 eng.encode_images(self.syn_crops[:B], out=self.feats)
             eng.fuse_scatter(b0, n, M, self.feats[:B].view(n, 2 * M + 1, d), self.w, Fp_out=self.Fp_local[off:off + n])

@@ -114,9 +114,8 @@ class Graph:
                 for j in range(len(ms), M):       # pad with an empty mask on a 1-pixel box (never wins a pixel)
                     boxes[k, j] = (0, 0, 1, 1)
             eng.masks_dense(b0, seg)
-            crops_ptr = eng.make_crops(b0, n, M, boxes, int(p.clip_bbox_margin))
             feats = torch.empty((n * (2 * M + 1), d), dtype=torch.float32, device=dev)
-            eng.encode_images_ptr(crops_ptr, n * (2 * M + 1), feats)
+            eng.encode_crops(b0, n, M, boxes, int(p.clip_bbox_margin), feats)     # crops + preprocess + encoder, fused
             Fp = eng.fuse_scatter(b0, n, M, feats.view(n, 2 * M + 1, d), float(p.clip_masked_weight),
                                   Fp_out=torch.empty((n, M, d), dtype=torch.float32, device=dev))
             eng.torch_wait()

@@ -169,6 +169,13 @@ int32_t hmsg_gemm_f16_debug(hmsg_ctx* ctx, const void* A, const void* W, float* 
 int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
                         const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
                         float** crops_dev_out);
+/* hmsg_make_crops + hmsg_encode_images fused for the ingest path: the crops are resampled straight
+ * into the encoder's fp16 patch matrix (no fp32 crop tensor, no im2col pass).  feats_out is a
+ * DEVICE pointer [n*(2M+1), out_dim] float32 unit rows in (masked, plain, full) order per frame;
+ * xywh is host or device per on_device. */
+int32_t hmsg_encode_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                          const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
+                          float* feats_out);
 /* copy the first n_crops [3,224,224] float32 crops of the last hmsg_make_crops to host (tests) */
 int32_t hmsg_crops_read(hmsg_ctx* ctx, int64_t n_crops, float* host_out);
 

@@ -36,3 +36,22 @@ def test_crops_bit_exact(engine, H, W):
         ref = [O.clip_preprocess(c).numpy() for c in masked] + [O.clip_preprocess(c).numpy() for c in plain] + [O.clip_preprocess(img).numpy()]
         ref = np.stack(ref)
         assert np.array_equal(got[f], ref), np.abs(got[f] - ref).max()
+
+
+def test_fused_crops_encoder_equals_unfused(engine):
+    """hmsg_encode_crops (crops -> fp16 patch matrix -> encoder) == make_crops + encode_images, bit for bit"""
+    import torch
+    H, W, M, n = 240, 320, 5, 3
+    sc = scene(n_frames=3, H=H, W=W)
+    load_scene(engine, sc)
+    engine.voxel_build(); engine.radius_filter(50, 0.5)
+    engine.encoder_load(synth.make_vit_weights())
+    boxes = np.stack([synth.make_mask_boxes(int(sc["ids"][f]) + 5, H, W, M) for f in range(n)])
+    engine.masks_boxes(0, boxes)
+    B = n * (2 * M + 1)
+    a = torch.empty((B, 512), dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    engine.encode_crops(0, n, M, boxes, 50, a)
+    ptr = engine.make_crops(0, n, M, boxes, 50)
+    engine.encode_images_ptr(ptr, B, b)
+    engine.sync()
+    assert torch.equal(a, b)
