@@ -167,7 +167,7 @@ def run_reference(args):
         return
     vals = []
     for s in range(args.warmup + args.steps):
-        r = cpu_reference_sample(n_frames=2, enc_images=8, knn_rows=100_000, knn_queries=5)
+        r = cpu_reference_sample(n_frames=1, enc_images=4, knn_rows=50_000, knn_queries=2)
         if s >= args.warmup:
             vals.append(r)
     fps = float(np.mean([v["frames_per_s"] for v in vals]))

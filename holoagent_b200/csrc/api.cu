@@ -49,7 +49,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt); free_dev(ctx->nbitmap); free_dev(ctx->nprefix); free_dev(ctx->node_xyz);
   free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox); free_dev(ctx->sum_feats); free_dev(ctx->counter);
   free_dev(ctx->maskbits); free_dev(ctx->pix_idx); free_dev(ctx->win); free_dev(ctx->Fp); free_dev(ctx->feats_stage);
-  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage);
+  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage); free_dev(ctx->cbitmap); free_dev(ctx->far_list); free_dev(ctx->far_count);
   if (ctx->scratch) cudaFree(ctx->scratch);
   for (auto& pc : ctx->prof) for (auto e : pc.ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);

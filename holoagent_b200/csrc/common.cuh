@@ -43,6 +43,9 @@ struct GridDesc {
   double inv_vs;      // rn(1/vs): used only for the fast floor below and for pruning bounds
   int nx, ny, nz, nzp;   // nzp = nz rounded up to a multiple of 32: a bitmap word never spans columns
   long long nwords;
+  // coarse level for the far search: one bit per 4x4x4 block of cells (node occupancy)
+  int cnx, cny, cnz, cnzp;
+  long long cnwords;
 };
 
 struct CamDesc {
@@ -84,6 +87,10 @@ struct hmsg_ctx {
   int64_t n_nodes = 0;
   uint32_t* nbitmap = nullptr;     // occupancy of kept voxels
   uint32_t* nprefix = nullptr;
+  uint32_t* cbitmap = nullptr;     // coarse (4x4x4 blocks) occupancy of nodes
+  int* far_list = nullptr;         // worklist of (frame-in-batch * HW + pixel) needing the far search
+  size_t far_list_bytes = 0;
+  int* far_count = nullptr;
   double* node_xyz = nullptr;      // [n_nodes,3]
   double* node_rgb = nullptr;
   int32_t* node_ijk = nullptr;

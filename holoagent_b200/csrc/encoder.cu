@@ -1212,7 +1212,7 @@ static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const
   if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
   CUtensorMap ta, tb, to;
   int32_t rc;
-  if (g_gemm_2sm < 0) { const char* e = getenv("HMSG_GEMM_2SM"); g_gemm_2sm = e ? atoi(e) : 0; }
+  if (g_gemm_2sm < 0) { const char* e = getenv("HMSG_GEMM_2SM"); g_gemm_2sm = e ? atoi(e) : 1; }   // default: 2-CTA pairs
   const bool two_sm = g_gemm_2sm != 0 && M > 128;
   if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
   if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, two_sm ? 128 : BN))) return rc;

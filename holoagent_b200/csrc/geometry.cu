@@ -398,55 +398,69 @@ __global__ void __launch_bounds__(TPB) k_compact_nodes(const uint32_t* bitmap, c
 // around the query's cell are visited; a cell is skipped when the distance from the query to
 // the cell's box already exceeds the best distance; the search stops once the best distance
 // is below r*vs (every unvisited cell is at least that far).  Ties -> lower node index.
+// Far search (exact): Chebyshev ring expansion over the COARSE grid (4x4x4 blocks of cells).  A coarse
+// cell is skipped when its bit is clear or when the distance from the query to its box already exceeds
+// the best distance; occupied coarse cells are scanned cell by cell (4 bits of one bitmap word per
+// column).  The search stops when the best distance is below the distance to the next coarse shell.
 __device__ __noinline__ int nn_search_rings(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
-                                           const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
-  // fractional cell coordinates only steer the search order and the (slack-protected) pruning bounds,
-  // so the reciprocal multiply is enough here; every accepted candidate is compared with exact distances
-  double fx = (px - g.vmin[0]) * g.inv_vs, fy = (py - g.vmin[1]) * g.inv_vs, fz = (pz - g.vmin[2]) * g.inv_vs;
-  int bi = min(max((int)floor(fx), 0), g.nx - 1);
-  int bj = min(max((int)floor(fy), 0), g.ny - 1);
-  int bk = min(max((int)floor(fz), 0), g.nz - 1);
+                                           const uint32_t* __restrict__ cbm, const double* __restrict__ nodes, double px, double py, double pz,
+                                           double& best_out) {
+  const double fx = (px - g.vmin[0]) * g.inv_vs, fy = (py - g.vmin[1]) * g.inv_vs, fz = (pz - g.vmin[2]) * g.inv_vs;   // fine cell units
+  const int bi = min(max((int)floor(fx * 0.25), 0), g.cnx - 1);
+  const int bj = min(max((int)floor(fy * 0.25), 0), g.cny - 1);
+  const int bk = min(max((int)floor(fz * 0.25), 0), g.cnz - 1);
   double best = INFINITY; int besti = -1;
   const double vs2 = g.vs * g.vs;
-  // distance (in cells) from the query to the nearest face of its own cell: every centroid of another cell is
-  // at least that far away (only meaningful when the query lies inside the grid cell it was binned to)
-  double mface = fmin(fmin(fmin(fx - bi, bi + 1 - fx), fmin(fy - bj, bj + 1 - fy)), fmin(fz - bk, bk + 1 - fz));
-  long long cw = -1; uint32_t cword = 0, cpref = 0;   // one-entry cache of (bitmap word, prefix)
-  int maxr = max(g.nx, max(g.ny, g.nz));
+  const int maxr = max(g.cnx, max(g.cny, g.cnz));
   for (int r = 0; r <= maxr; r++) {
-    if (besti >= 0) {
-      if (r == 1 && mface > 0.0 && best < mface * mface * vs2) break;
-      if (r >= 2) { double lbr = (double)(r - 1) * g.vs; if (best < lbr * lbr) break; }   // every cell of ring >= r is at least this far
+    if (besti >= 0 && r >= 1) {
+      // a coarse cell of shell >= r is at least (r-1) coarse cells = 4(r-1) fine cells away (the query may sit anywhere in / outside its clamped base)
+      double lbr = 4.0 * (double)(r - 1) * g.vs;
+      if (best < lbr * lbr) break;
     }
-    int i0 = max(bi - r, 0), i1 = min(bi + r, g.nx - 1);
-    int j0 = max(bj - r, 0), j1 = min(bj + r, g.ny - 1);
+    const int i0 = max(bi - r, 0), i1 = min(bi + r, g.cnx - 1);
+    const int j0 = max(bj - r, 0), j1 = min(bj + r, g.cny - 1);
     for (int ci = i0; ci <= i1; ci++) {
-      double ax = fmax(0.0, fmax((double)ci - fx, fx - (double)(ci + 1)));
-      int adi = abs(ci - bi);
+      const double ax = fmax(0.0, fmax(4.0 * ci - fx, fx - 4.0 * (ci + 1)));
+      const int adi = abs(ci - bi);
       for (int cj = j0; cj <= j1; cj++) {
-        double ay = fmax(0.0, fmax((double)cj - fy, fy - (double)(cj + 1)));
-        double axy = ax * ax + ay * ay;
+        const double ay = fmax(0.0, fmax(4.0 * cj - fy, fy - 4.0 * (cj + 1)));
+        const double axy = ax * ax + ay * ay;
         if (axy * vs2 * 0.999999999 > best) continue;
-        int adj = abs(cj - bj);
-        bool shell = (adi == r) || (adj == r);
-        long long colbase = ((long long)ci * g.ny + cj) * g.nzp;
-        // k candidates: whole [bk-r, bk+r] if this column is on the ring's i/j shell, else the 2 end caps
-        int nk = shell ? (2 * r + 1) : 2;
+        const bool shell = (adi == r) || (abs(cj - bj) == r);
+        const long long ccol = ((long long)ci * g.cny + cj) * g.cnzp;
+        const int nk = shell ? (2 * r + 1) : 2;
         for (int t = 0; t < nk; t++) {
-          int ck = shell ? (bk - r + t) : (t == 0 ? bk - r : bk + r);
-          if (ck < 0 || ck >= g.nz) continue;
-          long long lin = colbase + ck;
-          long long w = lin >> 5;
-          if (w != cw) { cw = w; cword = __ldg(&bm[w]); cpref = 0xffffffffu; }
-          int b = lin & 31;
-          if (!((cword >> b) & 1u)) continue;                     // occupancy first: most neighbour cells are empty
-          double az = fmax(0.0, fmax((double)ck - fz, fz - (double)(ck + 1)));
+          const int ck = shell ? (bk - r + t) : (t == 0 ? bk - r : bk + r);
+          if (ck < 0 || ck >= g.cnz) continue;
+          if (!shell && r == 0 && t == 1) continue;
+          const long long cl = ccol + ck;
+          if (!((__ldg(&cbm[cl >> 5]) >> (cl & 31)) & 1u)) continue;
+          const double az = fmax(0.0, fmax(4.0 * ck - fz, fz - 4.0 * (ck + 1)));
           if ((axy + az * az) * vs2 * 0.999999999 > best) continue;
-          if (cpref == 0xffffffffu) cpref = __ldg(&pf[w]);
-          int idx = (int)(cpref + __popc(cword & ((1u << b) - 1u)));
-          const double* q = nodes + (long long)idx * 3;
-          double d2 = sqdist3(q[0], q[1], q[2], px, py, pz);
-          if (d2 < best || (d2 == best && idx < besti)) { best = d2; besti = idx; }
+          // scan the 4x4x4 fine cells of this block
+          for (int ii = 4 * ci; ii < min(4 * ci + 4, g.nx); ii++) {
+            const double bx = fmax(0.0, fmax((double)ii - fx, fx - (double)(ii + 1)));
+            for (int jj = 4 * cj; jj < min(4 * cj + 4, g.ny); jj++) {
+              const double by = fmax(0.0, fmax((double)jj - fy, fy - (double)(jj + 1)));
+              const double bxy = bx * bx + by * by;
+              if (bxy * vs2 * 0.999999999 > best) continue;
+              const long long lin0 = ((long long)ii * g.ny + jj) * g.nzp + 4 * ck;     // 4-aligned: the 4 k-cells share one word
+              const uint32_t word = __ldg(&bm[lin0 >> 5]);
+              uint32_t nib = (word >> (lin0 & 31)) & 0xFu;
+              if (!nib) continue;
+              const uint32_t pre = __ldg(&pf[lin0 >> 5]);
+              while (nib) {
+                const int kb = __ffs(nib) - 1;
+                nib &= nib - 1;
+                const int b = (int)(lin0 & 31) + kb;
+                const int idx = (int)(pre + __popc(word & ((1u << b) - 1u)));
+                const double* q = nodes + (long long)idx * 3;
+                const double d2 = sqdist3(q[0], q[1], q[2], px, py, pz);
+                if (d2 < best || (d2 == best && idx < besti)) { best = d2; besti = idx; }
+              }
+            }
+          }
         }
       }
     }
@@ -462,11 +476,11 @@ __device__ __noinline__ int nn_search_rings(const GridDesc& g, const uint32_t* _
 // float64 distance for the survivors, (3) accept if the best distance is below one voxel edge (every
 // cell outside the 3x3x3 block is at least that far); otherwise fall back to the generic ring search.
 // Keeps all lanes of a warp on one short straight-line path (the generic search ran at 15.8/32 lanes).
-__device__ __forceinline__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
-                                         const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
+__device__ __forceinline__ int nn_search_fast(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
+                                              const double* __restrict__ nodes, double px, double py, double pz, double& best_out) {
   const double fxd = (px - g.vmin[0]) * g.inv_vs, fyd = (py - g.vmin[1]) * g.inv_vs, fzd = (pz - g.vmin[2]) * g.inv_vs;
   const int bi = (int)floor(fxd), bj = (int)floor(fyd), bk = (int)floor(fzd);
-  if (bi < 0 || bj < 0 || bk < 0 || bi >= g.nx || bj >= g.ny || bk >= g.nz) return nn_search_rings(g, bm, pf, nodes, px, py, pz, best_out);
+  if (bi < 0 || bj < 0 || bk < 0 || bi >= g.nx || bj >= g.ny || bk >= g.nz) return -2;
   const float ux = (float)(fxd - bi), uy = (float)(fyd - bj), uz = (float)(fzd - bk);   // position inside the own cell, [0,1)
   // per-axis gap (in cells) to the neighbour at offset -1 / 0 / +1
   auto gap = [](int dd, float u) { return dd < 0 ? u : (dd > 0 ? 1.f - u : 0.f); };
@@ -505,12 +519,20 @@ __device__ __forceinline__ int nn_search(const GridDesc& g, const uint32_t* __re
   }
   // every cell outside the 3x3x3 block is farther than one voxel edge minus nothing: >= (1 + min gap) * vs >= vs
   if (besti >= 0 && best < g.vs * g.vs) { best_out = best; return besti; }
-  return nn_search_rings(g, bm, pf, nodes, px, py, pz, best_out);
+  return -2;   // needs the far search
+}
+
+__device__ __forceinline__ int nn_search(const GridDesc& g, const uint32_t* __restrict__ bm, const uint32_t* __restrict__ pf,
+                                         const uint32_t* __restrict__ cbm, const double* __restrict__ nodes, double px, double py, double pz,
+                                         double& best_out) {
+  int r = nn_search_fast(g, bm, pf, nodes, px, py, pz, best_out);
+  if (r == -2) r = nn_search_rings(g, bm, pf, cbm, nodes, px, py, pz, best_out);
+  return r;
 }
 
 // per-frame API kernel: idx int64 (-1 invalid), dist f64
-__global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const double* nodes,
-                                                       int64_t* idx, double* dist) {
+__global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const uint32_t* cbm,
+                                                       const double* nodes, int64_t* idx, double* dist) {
   __shared__ double sT[16];
   long long f = a.frame0;
   load_pose(a.poses, f, sT);
@@ -523,7 +545,7 @@ __global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, 
     int y = p / a.cam.W, x = p - y * a.cam.W;
     double wx, wy, wz, best;
     unproject_px(dep, x, y, a.cam, sT, wx, wy, wz);
-    o = nn_search(g, bm, pf, nodes, wx, wy, wz, best);
+    o = nn_search(g, bm, pf, cbm, nodes, wx, wy, wz, best);
     dd = sqrt(best);
   }
   idx[p] = o;
@@ -531,18 +553,22 @@ __global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, 
 }
 
 __global__ void __launch_bounds__(TPB) k_points_to_node(const double* pts, long long n, GridDesc g, const uint32_t* bm, const uint32_t* pf,
-                                                        const double* nodes, int64_t* idx, double* dist) {
+                                                        const uint32_t* cbm, const double* nodes, int64_t* idx, double* dist) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double best;
-  int o = nn_search(g, bm, pf, nodes, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], best);
+  int o = nn_search(g, bm, pf, cbm, nodes, pts[i * 3], pts[i * 3 + 1], pts[i * 3 + 2], best);
   idx[i] = o;
   if (dist) dist[i] = sqrt(best);
 }
 
-// batch kernel: NN + last-writer-wins winner election.  grid = (blocks, n_frames)
+// batch kernels: NN + last-writer-wins winner election.
+// phase 1 (grid = (blocks, n_frames)): fast 3x3x3 path for every valid pixel; pixels that need the far
+// search (own neighbourhood filtered out) are appended to a worklist so that phase 2 runs them densely
+// instead of stalling 31 finished lanes per straggler.
 __global__ void __launch_bounds__(TPB) k_nn_winner(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const double* nodes,
-                                                   int32_t* pix_idx, unsigned long long* win, long long n_nodes, uint32_t epoch) {
+                                                   int32_t* pix_idx, unsigned long long* win, long long n_nodes, uint32_t epoch, int* far_list,
+                                                   int* far_count) {
   __shared__ double sT[16];
   int fb = blockIdx.y;
   long long f = a.frame0 + fb;
@@ -556,10 +582,51 @@ __global__ void __launch_bounds__(TPB) k_nn_winner(FrameArgs a, GridDesc g, cons
     int y = p / a.cam.W, x = p - y * a.cam.W;
     double wx, wy, wz, best;
     unproject_px(dep, x, y, a.cam, sT, wx, wy, wz);
-    o = nn_search(g, bm, pf, nodes, wx, wy, wz, best);
+    o = nn_search_fast(g, bm, pf, nodes, wx, wy, wz, best);
     if (o >= 0) atomicMax(&win[(long long)fb * n_nodes + o], ((unsigned long long)epoch << 32) | (unsigned)p);
+    else far_list[atomicAdd(far_count, 1)] = fb * HW + p;
   }
   pix_idx[(long long)fb * HW + p] = o;
+}
+
+__global__ void __launch_bounds__(TPB) k_nn_far(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const uint32_t* cbm,
+                                                const double* nodes, int32_t* pix_idx, unsigned long long* win, long long n_nodes, uint32_t epoch,
+                                                const int* far_list, const int* far_count) {
+  int n = *far_count;
+  int HW = a.cam.H * a.cam.W;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int e = far_list[i];
+    int fb = e / HW, p = e - fb * HW;
+    long long f = a.frame0 + fb;
+    double T[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) T[k] = a.poses[f * 16 + k];
+    unsigned short dep = a.depth[f * HW + p];
+    int y = p / a.cam.W, x = p - y * a.cam.W;
+    double wx, wy, wz, best;
+    unproject_px(dep, x, y, a.cam, T, wx, wy, wz);
+    int o = nn_search_rings(g, bm, pf, cbm, nodes, wx, wy, wz, best);
+    if (o >= 0) atomicMax(&win[(long long)fb * n_nodes + o], ((unsigned long long)epoch << 32) | (unsigned)p);
+    pix_idx[(long long)fb * HW + p] = o;
+  }
+}
+
+// coarse occupancy: one thread per fine bitmap word (32 k-cells of one column) -> up to 8 coarse bits
+__global__ void __launch_bounds__(TPB) k_coarse_mark(const uint32_t* __restrict__ nbitmap, GridDesc g, uint32_t* cbitmap) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= g.nwords) return;
+  uint32_t word = nbitmap[w];
+  if (!word) return;
+  long long lin0 = w << 5;
+  int k0 = (int)(lin0 % g.nzp);
+  long long ij = lin0 / g.nzp;
+  int j = (int)(ij % g.ny), i = (int)(ij / g.ny);
+  for (int nb = 0; nb < 8; nb++) {
+    if ((word >> (4 * nb)) & 0xFu) {
+      long long cl = ((long long)(i >> 2) * g.cny + (j >> 2)) * g.cnzp + ((k0 >> 2) + nb);
+      atomicOr(&cbitmap[cl >> 5], 1u << (cl & 31));
+    }
+  }
 }
 
 // ======================================================================================
@@ -700,6 +767,10 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   long long ncells = (long long)g.nx * g.ny * g.nzp;
   if (ncells > (1LL << 37)) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_voxel_build: dense occupancy index would exceed 16 GiB");
   g.nwords = ncells >> 5;
+  g.cnx = (g.nx + 3) / 4; g.cny = (g.ny + 3) / 4; g.cnz = (g.nz + 3) / 4; g.cnzp = (g.cnz + 31) & ~31;
+  g.cnwords = ((long long)g.cnx * g.cny * g.cnzp) >> 5;
+  free_dev(ctx->cbitmap);
+  HMSG_CUDA(cudaMalloc((void**)&ctx->cbitmap, (size_t)std::max<long long>(g.cnwords, 1) * 4));
   free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->nbitmap); free_dev(ctx->nprefix);
   long long nb = (g.nwords + 1023) / 1024;
   HMSG_CUDA(cudaMalloc((void**)&ctx->bitmap, g.nwords * 4));
@@ -778,6 +849,9 @@ extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double r
   HMSG_LAUNCH_CHECK();
   int32_t rc = run_scan(ctx, ctx->nbitmap, g.nwords, ctx->nprefix, &ctx->n_nodes);
   if (rc) return rc;
+  HMSG_CUDA(cudaMemsetAsync(ctx->cbitmap, 0, (size_t)std::max<long long>(g.cnwords, 1) * 4, ctx->stream));
+  k_coarse_mark<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->nbitmap, g, ctx->cbitmap);
+  HMSG_LAUNCH_CHECK();
   free_dev(ctx->node_xyz); free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox);
   size_t nn = (size_t)std::max<int64_t>(ctx->n_nodes, 1);
   HMSG_CUDA(cudaMalloc((void**)&ctx->node_xyz, nn * 24));
@@ -828,7 +902,7 @@ extern "C" int32_t hmsg_pixel_to_node(hmsg_ctx* ctx, int64_t frame, int64_t* idx
   if (rc) return rc;
   int64_t* di = (int64_t*)ctx->scratch; double* dd = (double*)(di + hw);
   k_pixel_to_node<<<(unsigned)((hw + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(frame_args(ctx, frame), ctx->grid, ctx->nbitmap, ctx->nprefix,
-                                                                              ctx->node_xyz, di, dist ? dd : nullptr);
+                                                                              ctx->cbitmap, ctx->node_xyz, di, dist ? dd : nullptr);
   HMSG_LAUNCH_CHECK();
   HMSG_CUDA(cudaMemcpyAsync(idx, di, hw * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (dist) HMSG_CUDA(cudaMemcpyAsync(dist, dd, hw * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -846,8 +920,8 @@ extern "C" int32_t hmsg_points_to_node(hmsg_ctx* ctx, const double* xyz, int64_t
   if (rc) return rc;
   double* dp = (double*)ctx->scratch; int64_t* di = (int64_t*)(dp + n * 3); double* dd = (double*)(di + n);
   HMSG_CUDA(cudaMemcpyAsync(dp, xyz, n * 24, cudaMemcpyHostToDevice, ctx->stream));
-  k_points_to_node<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(dp, n, ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->node_xyz, di,
-                                                                             dist ? dd : nullptr);
+  k_points_to_node<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(dp, n, ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->cbitmap,
+                                                                             ctx->node_xyz, di, dist ? dd : nullptr);
   HMSG_LAUNCH_CHECK();
   HMSG_CUDA(cudaMemcpyAsync(idx, di, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
   if (dist) HMSG_CUDA(cudaMemcpyAsync(dist, dd, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -859,9 +933,16 @@ extern "C" int32_t hmsg_points_to_node(hmsg_ctx* ctx, const double* xyz, int64_t
 int32_t geometry_nn_winner(hmsg_ctx* ctx, int64_t frame_begin, int n_frames) {
   int HW = ctx->cam.H * ctx->cam.W;
   dim3 grid((HW + TPB - 1) / TPB, n_frames);
+  int32_t rc = ctx->reserve(&ctx->far_list, &ctx->far_list_bytes, (size_t)n_frames * HW * 4);
+  if (rc) return rc;
+  if (!ctx->far_count) HMSG_CUDA(cudaMalloc((void**)&ctx->far_count, 4));
+  HMSG_CUDA(cudaMemsetAsync(ctx->far_count, 0, 4, ctx->stream));
   ctx->prof_begin(PROF_NN);
   k_nn_winner<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, frame_begin), ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->node_xyz, ctx->pix_idx,
-                                             ctx->win, ctx->n_nodes, ctx->epoch);
+                                             ctx->win, ctx->n_nodes, ctx->epoch, ctx->far_list, ctx->far_count);
+  HMSG_LAUNCH_CHECK();
+  k_nn_far<<<ctx->sm_count * 4, TPB, 0, ctx->stream>>>(frame_args(ctx, frame_begin), ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->cbitmap, ctx->node_xyz,
+                                                       ctx->pix_idx, ctx->win, ctx->n_nodes, ctx->epoch, ctx->far_list, ctx->far_count);
   ctx->prof_end(PROF_NN, (double)HW * n_frames * 14.0);
   HMSG_LAUNCH_CHECK();
   return HMSG_OK;

@@ -97,28 +97,29 @@ k_sim_topk(const float* __restrict__ E, long long N, const float* __restrict__ Q
 
   long long gw = (long long)blockIdx.x * KNN_WARPS + wid;
   long long tw = (long long)gridDim.x * KNN_WARPS;
-  for (long long row0 = gw * RW; row0 < N; row0 += tw * RW) {
-    float4 e[RW][DV];
+  // software pipeline over the DV column chunks of a row group: chunk j+1 (or chunk 0 of the next row
+  // group) is in flight while chunk j is multiplied, so only 2*RW float4 of E live in registers and the
+  // accumulators can be packed float2 pairs (FFMA2).
+  float4 enext[RW];
+  auto load_chunk = [&](long long r0, int j, float4* dst) {
 #pragma unroll
     for (int r = 0; r < RW; r++) {
-      long long row = row0 + r;
-      if (row < N) {
-        const float4* src = reinterpret_cast<const float4*>(E + row * d);
-#pragma unroll
-        for (int j = 0; j < DV; j++) e[r][j] = ld_stream(src + lane + 32 * j);
-      } else {
-#pragma unroll
-        for (int j = 0; j < DV; j++) e[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      long long row = r0 + r;
+      dst[r] = (row < N) ? ld_stream(reinterpret_cast<const float4*>(E + row * d) + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // packed fp32 FMA (Blackwell FFMA2): the (x,y) and (z,w) halves of each float4 are multiplied as
-    // pairs, so a float4 x float4 dot step costs 2 instructions instead of 4; the two lanes of the
-    // accumulator pair are added once at the end.
+  };
+  if (gw * RW < N) load_chunk(gw * RW, 0, enext);
+  for (long long row0 = gw * RW; row0 < N; row0 += tw * RW) {
     float2 acc2[NV];
 #pragma unroll
     for (int i = 0; i < NV; i++) acc2[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int j = 0; j < DV; j++) {
+      float4 ecur[RW];
+#pragma unroll
+      for (int r = 0; r < RW; r++) ecur[r] = enext[r];
+      if (j + 1 < DV) load_chunk(row0, j + 1, enext);
+      else if (row0 + tw * RW < N) load_chunk(row0 + tw * RW, 0, enext);
 #pragma unroll
       for (int q = 0; q < BQ; q++) {
         float4 qv = sq[q * (d / 4) + lane + 32 * j];
@@ -126,8 +127,8 @@ k_sim_topk(const float* __restrict__ E, long long N, const float* __restrict__ Q
 #pragma unroll
         for (int r = 0; r < RW; r++) {
           float2 a = acc2[r * BQ + q];
-          a = __ffma2_rn(make_float2(e[r][j].x, e[r][j].y), q01, a);
-          a = __ffma2_rn(make_float2(e[r][j].z, e[r][j].w), q23, a);
+          a = __ffma2_rn(make_float2(ecur[r].x, ecur[r].y), q01, a);
+          a = __ffma2_rn(make_float2(ecur[r].z, ecur[r].w), q23, a);
           acc2[r * BQ + q] = a;
         }
       }
@@ -308,7 +309,7 @@ static int32_t launch_pass_bq(hmsg_ctx* ctx, KnnState* st, int BQ, const float* 
     case 1: return launch_pass<DV, 1, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
     case 2: return launch_pass<DV, 2, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
     case 4: return launch_pass<DV, 4, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
-    case 8: return launch_pass<DV, 8, 2, (DV <= 4 ? 3 : 2)>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    case 8: return launch_pass<DV, 8, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
     default: return launch_pass<DV, 16, 2, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
   }
 }

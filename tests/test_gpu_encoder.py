@@ -22,7 +22,7 @@ def test_gemm_tcgen05(engine, M, N, K, two_sm):
     torch.cuda.synchronize()
     engine.gemm_debug(Ad, Wd, Cd, M, N, K)
     out = Cd.cpu()
-    engine.set_option("gemm_2sm", 0)
+    engine.set_option("gemm_2sm", 1)
     err = (out - ref).abs().max().item()
     assert err <= 1e-3 * ref.abs().max().item() + 1e-5, err
 
@@ -50,7 +50,7 @@ def test_vit_forward(engine, vit, B):
     assert np.allclose(np.linalg.norm(out, axis=-1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("opt,val", [("gemm_2sm", 1), ("attn_variant", 1), ("attn_variant", 2), ("attn_variant", 3)])
+@pytest.mark.parametrize("opt,val", [("gemm_2sm", 0), ("attn_variant", 1), ("attn_variant", 2), ("attn_variant", 3)])
 def test_vit_variants_agree(engine, vit, opt, val):
     x = torch.randn(70, 3, 224, 224, generator=torch.Generator().manual_seed(5))
     base = engine.encode_images(x.numpy())
@@ -58,7 +58,7 @@ def test_vit_variants_agree(engine, vit, opt, val):
     try:
         alt = engine.encode_images(x.numpy())
     finally:
-        engine.set_option(opt, 0)
+        engine.set_option(opt, 1 if opt == "gemm_2sm" else 0)
     assert np.abs(alt - base).max() < 2e-4
 
 

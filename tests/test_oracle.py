@@ -184,3 +184,31 @@ def test_device_resampler_arithmetic_matches_cv2_and_pil():
         img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
         ref = np.asarray(Image.fromarray(img).resize((nw, nh), Image.BICUBIC))
         assert np.array_equal(ref, R.pil_resize_bicubic(img, nw, nh)), (h, w)
+
+
+def test_config0_plumbing_oracle_end_to_end():
+    """BASELINE configs[0] (reference CPU path, no GPU), scaled to keep the CPU suite fast:
+    8 frames 320x240, M=3 masks, a 2-layer ViT.  The whole build-and-retrieve path runs on the
+    oracle alone and is deterministic."""
+    H, W, F, M = 240, 320, 8, 3
+    depth, rgb, T, K = synth.make_frames_np(np.arange(F) * 5, H, W)
+    geo = O.build_geometry(depth, rgb, T, K, 1000.0, 0.05, nb_points=300, radius=0.6)
+    n = len(geo["node_xyz"])
+    assert 1000 < n <= len(geo["voxel_xyz"])
+    tree = O.build_tree(geo["node_xyz"])
+    sh = synth.VitB32Shape(image=224, patch=32, width=128, layers=2, heads=2, mlp=256, out_dim=128)
+    sd = synth.make_vit_weights(sh, seed=2)
+    sum_f = torch.zeros(n, 128); cnt = torch.zeros(n, 1)
+    for f in range(2):
+        masks = synth.make_masks(f, depth[f], M)
+        crops = O.crop_all_bounding_boxs(rgb[f], masks, True, 50) + O.crop_all_bounding_boxs(rgb[f], masks, False, 50) + [rgb[f]]
+        fe = O.get_img_feats_batch_tensor(sd, torch.stack([O.clip_preprocess(c) for c in crops]), heads=2)
+        Fp = O.fuse_mask_feats(fe[:M], fe[M:2 * M], fe[2 * M:], 0.4418)
+        O.ingest_frame(sum_f, cnt, tree, n, depth[f], rgb[f], T[f], K, 1000.0, Fp, np.stack([m["segmentation"] for m in masks]))
+        m3 = O.create_3d_masks([m["segmentation"] for m in masks], depth[f], K, 1000.0, T[f], geo["node_xyz"], geo["node_rgb"], tree, 0.05)
+        assert len(m3) == M and all(len(p) <= int(m["segmentation"].sum()) for (p, _, _), m in zip(m3, masks))
+    full = O.finalize_node_feats(sum_f, cnt)
+    hit = cnt.numpy().reshape(-1) > 0
+    assert 0 < hit.sum() < n and np.isfinite(full).all() and not full[~hit].any()
+    ids, sc = O.query_topk(full[hit][0] * 0.8, full, 5)
+    assert sc[0] >= sc[-1] and len(set(ids.tolist())) == 5
