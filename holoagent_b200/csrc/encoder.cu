@@ -944,9 +944,10 @@ __global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __h
   cp_async_wait<0>();
 }
 
-constexpr int ATT3_GROUPS = 4;                   // (image, head) tiles in flight per block, 2 warps each
-constexpr int ATT3_SMEM = ATT3_GROUPS * 2 * 3 * ATT2_TILE * 2;
 
+// GROUPS (image, head) tiles per block, 2 warps each; NBUF = 2 double-buffers the tile (prefetch while computing),
+// NBUF = 1 trades the prefetch for twice as many resident warps.
+template <int ATT3_GROUPS, int NBUF>
 __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
                                                                        int W, float scale) {
   extern __shared__ __align__(16) unsigned char att_smem[];
@@ -954,9 +955,9 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
   // and each warp handles every other 16-row query tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = warp >> 1, wsub = warp & 1, l64 = wsub * 32 + lane;
-  __half* wbase = reinterpret_cast<__half*>(att_smem) + (size_t)grp * 2 * 3 * ATT2_TILE;
+  __half* wbase = reinterpret_cast<__half*>(att_smem) + (size_t)grp * NBUF * 3 * ATT2_TILE;
   // zero both buffers once: rows >= T are never written by cp.async and V padding rows must be finite (P = 0 there)
-  for (int i = l64; i < 2 * 3 * ATT2_TILE / 8; i += 64) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = l64; i < NBUF * 3 * ATT2_TILE / 8; i += 64) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
   named_bar_sync(1 + grp, 64);
   const long long npairs = (long long)B * heads;
   const long long gw = (long long)blockIdx.x * ATT3_GROUPS + grp, tw = (long long)gridDim.x * ATT3_GROUPS;
@@ -974,15 +975,23 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
       cp_async16(dst + 2 * ATT2_TILE, src + 2 * W);
     }
   };
-  if (gw < npairs) issue(gw, 0);
-  cp_async_commit();
+  if (NBUF == 2) {
+    if (gw < npairs) issue(gw, 0);
+    cp_async_commit();
+  }
   int cur = 0;
   const int g = lane >> 2, t = lane & 3;
   const int m_tiles = (T + 15) / 16;
   for (long long pair = gw; pair < npairs; pair += tw) {
-    if (pair + tw < npairs) issue(pair + tw, cur ^ 1);
-    cp_async_commit();
-    cp_async_wait<1>();
+    if (NBUF == 2) {
+      if (pair + tw < npairs) issue(pair + tw, cur ^ 1);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      issue(pair, 0);
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
     named_bar_sync(1 + grp, 64);       // both warps' cp.async data is visible to both
     const __half* sQ = wbase + cur * 3 * ATT2_TILE;
     const __half* sK = sQ + ATT2_TILE;
@@ -1060,7 +1069,7 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
       }
     }
     named_bar_sync(1 + grp, 64);       // both warps are done with buf[cur] before it is refilled
-    cur ^= 1;
+    if (NBUF == 2) cur ^= 1;
   }
   cp_async_wait<0>();
 }
@@ -1135,6 +1144,7 @@ struct VitState {
   bool attn_simple = false;
   bool attn_v1 = false;
   bool attn_v2 = false;
+  bool attn_v3_db = false;   // v3 with 4 double-buffered tiles per SM instead of 8 single-buffered ones
   bool smem_attr_set = false;
 };
 
@@ -1200,7 +1210,7 @@ int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
   if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
-    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->smem_attr_set = false;
+    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->smem_attr_set = false;
     return HMSG_OK;
   }
   return -1;
@@ -1393,13 +1403,20 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       int grid = (int)std::min<long long>((pairs + ATT2_WARPS - 1) / ATT2_WARPS, ctx->sm_count);
       k_attention_mma2<<<grid, ATT2_WARPS * 32, ATT2_SMEM, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     } else {
+      constexpr int SM3 = 4 * 2 * 3 * ATT2_TILE * 2;   // == 8 * 1 * 3 * ATT2_TILE * 2
       if (!vs->smem_attr_set) {
-        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT3_SMEM));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
         vs->smem_attr_set = true;
       }
       long long pairs = (long long)B * d.heads;
-      int grid = (int)std::min<long long>((pairs + ATT3_GROUPS - 1) / ATT3_GROUPS, ctx->sm_count);
-      k_attention_mma3<<<grid, ATT3_GROUPS * 64, ATT3_SMEM, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+      if (vs->attn_v3_db) {
+        int grid = (int)std::min<long long>((pairs + 3) / 4, ctx->sm_count);
+        k_attention_mma3<4, 2><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+      } else {
+        int grid = (int)std::min<long long>((pairs + 7) / 8, ctx->sm_count);
+        k_attention_mma3<8, 1><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+      }
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();

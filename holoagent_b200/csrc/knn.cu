@@ -32,7 +32,6 @@ struct KnnState {
   int* out_n = nullptr;        size_t out_n_bytes = 0;
   float2* rowstate = nullptr;  size_t rowstate_bytes = 0;
   int grid = 0;
-  int last_grid = 0;   // CTAs of the most recent k_sim_topk launch (= number of per-CTA lists)
 };
 
 __device__ __forceinline__ float4 ld_stream(const float4* p) {
@@ -71,8 +70,8 @@ template <> struct Log2<1> { static constexpr int v = 0; };
 // mode 1: negative-prompt selection (graph.py:3134-3151): rows whose argmax over the Qp query rows is
 //         `query_id`, ranked by that max; list 0 holds the result.  q_base/rowstate allow Qp > BQ
 //         (multi-pass running max/argmax per row).
-template <int DV, int BQ, int RW, int MINB>
-__global__ void __launch_bounds__(KNN_TPB, MINB)
+template <int DV, int BQ, int RW>
+__global__ void __launch_bounds__(KNN_TPB, 2)
 k_sim_topk(const float* __restrict__ E, long long N, const float* __restrict__ Q, int nq, int K, const uint8_t* __restrict__ row_mask, int mode,
            int query_id, int q_base, int last_pass, float2* __restrict__ rowstate, float* __restrict__ part_s, int* __restrict__ part_i) {
   constexpr int d = 128 * DV;
@@ -97,45 +96,36 @@ k_sim_topk(const float* __restrict__ E, long long N, const float* __restrict__ Q
 
   long long gw = (long long)blockIdx.x * KNN_WARPS + wid;
   long long tw = (long long)gridDim.x * KNN_WARPS;
-  // software pipeline over the DV column chunks of a row group: chunk j+1 (or chunk 0 of the next row
-  // group) is in flight while chunk j is multiplied, so only 2*RW float4 of E live in registers and the
-  // accumulators can be packed float2 pairs (FFMA2).
-  float4 enext[RW];
-  auto load_chunk = [&](long long r0, int j, float4* dst) {
+  for (long long row0 = gw * RW; row0 < N; row0 += tw * RW) {
+    float4 e[RW][DV];
 #pragma unroll
     for (int r = 0; r < RW; r++) {
-      long long row = r0 + r;
-      dst[r] = (row < N) ? ld_stream(reinterpret_cast<const float4*>(E + row * d) + lane + 32 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-  };
-  if (gw * RW < N) load_chunk(gw * RW, 0, enext);
-  for (long long row0 = gw * RW; row0 < N; row0 += tw * RW) {
-    float2 acc2[NV];
+      long long row = row0 + r;
+      if (row < N) {
+        const float4* src = reinterpret_cast<const float4*>(E + row * d);
 #pragma unroll
-    for (int i = 0; i < NV; i++) acc2[i] = make_float2(0.f, 0.f);
+        for (int j = 0; j < DV; j++) e[r][j] = ld_stream(src + lane + 32 * j);
+      } else {
 #pragma unroll
-    for (int j = 0; j < DV; j++) {
-      float4 ecur[RW];
-#pragma unroll
-      for (int r = 0; r < RW; r++) ecur[r] = enext[r];
-      if (j + 1 < DV) load_chunk(row0, j + 1, enext);
-      else if (row0 + tw * RW < N) load_chunk(row0 + tw * RW, 0, enext);
-#pragma unroll
-      for (int q = 0; q < BQ; q++) {
-        float4 qv = sq[q * (d / 4) + lane + 32 * j];
-        const float2 q01 = make_float2(qv.x, qv.y), q23 = make_float2(qv.z, qv.w);
-#pragma unroll
-        for (int r = 0; r < RW; r++) {
-          float2 a = acc2[r * BQ + q];
-          a = __ffma2_rn(make_float2(ecur[r].x, ecur[r].y), q01, a);
-          a = __ffma2_rn(make_float2(ecur[r].z, ecur[r].w), q23, a);
-          acc2[r * BQ + q] = a;
-        }
+        for (int j = 0; j < DV; j++) e[r][j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     float acc[NV];
 #pragma unroll
-    for (int i = 0; i < NV; i++) acc[i] = acc2[i].x + acc2[i].y;
+    for (int i = 0; i < NV; i++) acc[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < DV; j++) {
+#pragma unroll
+      for (int q = 0; q < BQ; q++) {
+        float4 qv = sq[q * (d / 4) + lane + 32 * j];
+#pragma unroll
+        for (int r = 0; r < RW; r++) {
+          float a = acc[r * BQ + q];
+          a = fmaf(e[r][j].x, qv.x, a); a = fmaf(e[r][j].y, qv.y, a); a = fmaf(e[r][j].z, qv.z, a); a = fmaf(e[r][j].w, qv.w, a);
+          acc[r * BQ + q] = a;
+        }
+      }
+    }
     float score = warp_transpose_reduce<NV>(acc, lane);
     int vi = lane >> SH;
     int r = vi / BQ, q = vi % BQ;
@@ -284,18 +274,17 @@ __global__ void __launch_bounds__(1024) k_topk_merge(const float* __restrict__ p
 // ======================================================================================
 static size_t knn_smem(int BQ, int d) { return (size_t)BQ * d * 4 + (size_t)KNN_WARPS * BQ * KMAX * 8 + (size_t)KNN_WARPS * BQ * 4; }
 
-template <int DV, int BQ, int RW, int MINB>
+template <int DV, int BQ, int RW>
 static int32_t launch_pass(hmsg_ctx* ctx, KnnState* st, const float* dq, int nq, int K, const uint8_t* dmask, int mode, int query_id, int q_base,
                            int last_pass, float2* rowstate) {
   size_t smem = knn_smem(BQ, 128 * DV);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(k_sim_topk<DV, BQ, RW, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_sim_topk<DV, BQ, RW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_set = true;
   }
   ctx->prof_begin(PROF_KNN);
-  st->last_grid = st->grid * MINB / 2;
-  k_sim_topk<DV, BQ, RW, MINB><<<st->last_grid, KNN_TPB, smem, ctx->stream>>>(st->E, st->N, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate,
+  k_sim_topk<DV, BQ, RW><<<st->grid, KNN_TPB, smem, ctx->stream>>>(st->E, st->N, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate,
                                                                     st->part_s, st->part_i);
   ctx->prof_end(PROF_KNN, (double)st->N * st->d * 4.0);
   HMSG_LAUNCH_CHECK();
@@ -306,11 +295,11 @@ template <int DV>
 static int32_t launch_pass_bq(hmsg_ctx* ctx, KnnState* st, int BQ, const float* dq, int nq, int K, const uint8_t* dmask, int mode, int query_id,
                               int q_base, int last_pass, float2* rowstate) {
   switch (BQ) {
-    case 1: return launch_pass<DV, 1, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
-    case 2: return launch_pass<DV, 2, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
-    case 4: return launch_pass<DV, 4, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
-    case 8: return launch_pass<DV, 8, 4, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
-    default: return launch_pass<DV, 16, 2, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    case 1: return launch_pass<DV, 1, 4>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    case 2: return launch_pass<DV, 2, 4>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    case 4: return launch_pass<DV, 4, 4>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    case 8: return launch_pass<DV, 8, 4>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
+    default: return launch_pass<DV, 16, 2>(ctx, st, dq, nq, K, dmask, mode, query_id, q_base, last_pass, rowstate);
   }
 }
 
@@ -364,8 +353,8 @@ extern "C" int32_t hmsg_index_set(hmsg_ctx* ctx, const float* E, int64_t N, int3
   st->grid = ctx->sm_count * 2;
   if (const char* e = getenv("HMSG_KNN_BQ")) g_knn_bq_override = atoi(e);
   int32_t rc;
-  if ((rc = ctx->reserve(&st->part_s, &st->part_s_bytes, (size_t)st->grid * 2 * 16 * KMAX * 4))) return rc;
-  if ((rc = ctx->reserve(&st->part_i, &st->part_i_bytes, (size_t)st->grid * 2 * 16 * KMAX * 4))) return rc;
+  if ((rc = ctx->reserve(&st->part_s, &st->part_s_bytes, (size_t)st->grid * 16 * KMAX * 4))) return rc;
+  if ((rc = ctx->reserve(&st->part_i, &st->part_i_bytes, (size_t)st->grid * 16 * KMAX * 4))) return rc;
   return HMSG_OK;
 }
 
@@ -407,7 +396,7 @@ extern "C" int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, in
     int BQ = std::min(pick_bq(rem), BQmax);
     int cnt = std::min(rem, BQ);
     if ((rc = launch_pass_any(ctx, st, BQ, dq + (size_t)q0 * st->d, cnt, k, dmask, 0, 0, 0, 1, nullptr))) return rc;
-    k_topk_merge<<<cnt, 1024, 0, ctx->stream>>>(st->part_s, st->part_i, st->last_grid, BQ, k, oi + (size_t)q0 * k, os + (size_t)q0 * k, nullptr, k);
+    k_topk_merge<<<cnt, 1024, 0, ctx->stream>>>(st->part_s, st->part_i, st->grid, BQ, k, oi + (size_t)q0 * k, os + (size_t)q0 * k, nullptr, k);
     HMSG_LAUNCH_CHECK();
     q0 += cnt;
   }
@@ -449,7 +438,7 @@ extern "C" int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_re
         return rc;
     }
     int BQl = pick_bq(std::min(16, Qp - (passes - 1) * 16));
-    k_topk_merge<<<1, 1024, 0, ctx->stream>>>(st->part_s, st->part_i, st->last_grid, BQl, k, oi + (size_t)r * k, os + (size_t)r * k, on + r, k);
+    k_topk_merge<<<1, 1024, 0, ctx->stream>>>(st->part_s, st->part_i, st->grid, BQl, k, oi + (size_t)r * k, os + (size_t)r * k, on + r, k);
     HMSG_LAUNCH_CHECK();
   }
   if (!on_device) {

@@ -56,6 +56,22 @@ if "enc" in what:
         res[f"enc{two}_B{B}"] = {"ms": ms, "img_per_s": B / ms * 1e3, "tflops": B * 8.82e9 / ms / 1e9}
         print(two, B, res[f"enc{two}_B{B}"], flush=True)
     eng.set_option("gemm_2sm", 0)
+if "attn" in what:
+    sd = synth.make_vit_weights()
+    eng.encoder_load(sd)
+    x = torch.randn(2080, 3, 224, 224, device="cuda"); torch.cuda.synchronize()
+    for var in (0, 4, 3, 1):
+        eng.set_option("attn_variant", var)
+        eng.encode_images(x); eng.sync()
+        eng.prof_enable("attn", "gemm", "eltwise")
+        for c in ("attn", "gemm", "eltwise"): eng.prof_read(c)
+        for _ in range(3): eng.encode_images(x)
+        r = {c: eng.prof_read(c) for c in ("attn", "gemm", "eltwise")}
+        eng.prof_enable()
+        res[f"attn_var{var}"] = {"attn_ms_per_fwd": r["attn"]["ms"] / 3, "gemm_ms": r["gemm"]["ms"] / 3, "eltwise_ms": r["eltwise"]["ms"] / 3,
+                                 "gemm_tflops": r["gemm"]["work"] / r["gemm"]["ms"] / 1e9}
+        print("attn", var, res[f"attn_var{var}"], flush=True)
+    eng.set_option("attn_variant", 0)
 if "geom" in what:
     F, H, W = 200, 480, 640
     d, c, T, K = synth.make_frames(np.arange(F), H, W, device="cuda")

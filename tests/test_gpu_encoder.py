@@ -50,7 +50,7 @@ def test_vit_forward(engine, vit, B):
     assert np.allclose(np.linalg.norm(out, axis=-1), 1.0, atol=1e-5)
 
 
-@pytest.mark.parametrize("opt,val", [("gemm_2sm", 0), ("attn_variant", 1), ("attn_variant", 2), ("attn_variant", 3)])
+@pytest.mark.parametrize("opt,val", [("gemm_2sm", 0), ("attn_variant", 1), ("attn_variant", 2), ("attn_variant", 3), ("attn_variant", 4)])
 def test_vit_variants_agree(engine, vit, opt, val):
     x = torch.randn(70, 3, 224, 224, generator=torch.Generator().manual_seed(5))
     base = engine.encode_images(x.numpy())
