@@ -76,6 +76,8 @@ struct hmsg_ctx {
   uint32_t* bitmap = nullptr;      // occupancy, 1 bit per cell, k fastest
   uint32_t* prefix = nullptr;      // exclusive popcount prefix per word
   uint32_t* blocksums = nullptr;
+  size_t bitmap_cap_words = 0;     // grow-only capacities (a re-build of the same scene does not touch the allocator)
+  size_t voxel_cap = 0, node_cap = 0, cbitmap_cap_words = 0;
   int64_t n_voxels = 0;
   double* vox_acc = nullptr;       // [n_voxels,6] sum -> mean of xyz, rgb
   uint32_t* vox_cnt = nullptr;
@@ -101,6 +103,7 @@ struct hmsg_ctx {
   int d = 0;
   float* sum_feats = nullptr;      // [n_nodes,d]
   float* counter = nullptr;        // [n_nodes]
+  size_t feat_cap = 0;
   // batch scratch
   int batch_cap = 0;
   int batch_M = 0, batch_MW = 0;

@@ -415,10 +415,13 @@ extern "C" int32_t hmsg_features_begin(hmsg_ctx* ctx, int32_t d) {
   if (!ctx) return HMSG_ERR_ARG;
   if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_features_begin: call hmsg_radius_filter first");
   if (d <= 0 || d % 128 != 0 || d > 1024) return ctx->fail(HMSG_ERR_ARG, "hmsg_features_begin: d must be a multiple of 128, <= 1024");
-  free_dev(ctx->sum_feats); free_dev(ctx->counter);
   size_t nn = (size_t)std::max<int64_t>(ctx->n_nodes, 1);
-  HMSG_CUDA(cudaMalloc((void**)&ctx->sum_feats, nn * d * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->counter, nn * 4));
+  if (nn * d > ctx->feat_cap) {
+    free_dev(ctx->sum_feats); free_dev(ctx->counter);
+    HMSG_CUDA(cudaMalloc((void**)&ctx->sum_feats, nn * d * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->counter, nn * 4));
+    ctx->feat_cap = nn * d;
+  }
   HMSG_CUDA(cudaMemsetAsync(ctx->sum_feats, 0, nn * d * 4, ctx->stream));
   HMSG_CUDA(cudaMemsetAsync(ctx->counter, 0, nn * 4, ctx->stream));
   ctx->d = d;
@@ -454,7 +457,7 @@ static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfe
 extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const float* feats, float maskedd_weight,
                                      float* F_p_out, int32_t on_device) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: call hmsg_features_begin first");
   if (ctx->batch_begin != frame_begin || ctx->batch_n != n || ctx->batch_M != M)
     return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: masks of this batch were not set (hmsg_masks_*)");
   if (!feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_fuse_scatter: null feats");
@@ -498,7 +501,7 @@ extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t
 
 extern "C" int32_t hmsg_node_feats_finalize(hmsg_ctx* ctx, float* full_feats, int32_t on_device) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_finalize: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_finalize: call hmsg_features_begin first");
   if (!full_feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_node_feats_finalize: null output");
   long long n = ctx->n_nodes;
   int d = ctx->d;
@@ -521,7 +524,7 @@ extern "C" int32_t hmsg_node_feats_finalize(hmsg_ctx* ctx, float* full_feats, in
 
 extern "C" int32_t hmsg_node_feats_raw(hmsg_ctx* ctx, float* sum_features, float* counter) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_raw: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_raw: call hmsg_features_begin first");
   long long n = ctx->n_nodes;
   if (n == 0) return HMSG_OK;
   if (sum_features) HMSG_CUDA(cudaMemcpyAsync(sum_features, ctx->sum_feats, (size_t)n * ctx->d * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -532,7 +535,7 @@ extern "C" int32_t hmsg_node_feats_raw(hmsg_ctx* ctx, float* sum_features, float
 
 extern "C" int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, float** counter, int64_t* n_nodes, int32_t* d) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_device: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_device: call hmsg_features_begin first");
   if (sum_features) *sum_features = ctx->sum_feats;
   if (counter) *counter = ctx->counter;
   if (n_nodes) *n_nodes = ctx->n_nodes;
@@ -619,7 +622,7 @@ __global__ void __launch_bounds__(TPB) k_merge_partials(const float* __restrict_
 
 extern "C" int32_t hmsg_node_feats_pack(hmsg_ctx* ctx, float* dst, const float* Fp_rows, int64_t fp_floats) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats || !dst) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_pack: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0 || !dst) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_pack: call hmsg_features_begin first");
   size_t nd = (size_t)ctx->n_nodes * ctx->d;
   HMSG_CUDA(cudaMemcpyAsync(dst, ctx->sum_feats, nd * 4, cudaMemcpyDeviceToDevice, ctx->stream));
   HMSG_CUDA(cudaMemcpyAsync(dst + nd, ctx->counter, (size_t)ctx->n_nodes * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -630,7 +633,7 @@ extern "C" int32_t hmsg_node_feats_pack(hmsg_ctx* ctx, float* dst, const float* 
 
 extern "C" int32_t hmsg_node_feats_merge(hmsg_ctx* ctx, const float* gathered, int32_t world, int64_t stride_floats) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats || !gathered || world < 1) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_merge: bad state/argument");
+  if (!ctx->sum_feats || ctx->d == 0 || !gathered || world < 1) return ctx->fail(HMSG_ERR_STATE, "hmsg_node_feats_merge: bad state/argument");
   long long nd = (long long)ctx->n_nodes * ctx->d, count = nd + ctx->n_nodes;
   if (stride_floats < count) return ctx->fail(HMSG_ERR_ARG, "hmsg_node_feats_merge: stride smaller than the partial");
   if (count == 0) return HMSG_OK;

@@ -769,15 +769,21 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   g.nwords = ncells >> 5;
   g.cnx = (g.nx + 3) / 4; g.cny = (g.ny + 3) / 4; g.cnz = (g.nz + 3) / 4; g.cnzp = (g.cnz + 31) & ~31;
   g.cnwords = ((long long)g.cnx * g.cny * g.cnzp) >> 5;
-  free_dev(ctx->cbitmap);
-  HMSG_CUDA(cudaMalloc((void**)&ctx->cbitmap, (size_t)std::max<long long>(g.cnwords, 1) * 4));
-  free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->nbitmap); free_dev(ctx->nprefix);
+  if ((size_t)std::max<long long>(g.cnwords, 1) > ctx->cbitmap_cap_words) {
+    free_dev(ctx->cbitmap);
+    HMSG_CUDA(cudaMalloc((void**)&ctx->cbitmap, (size_t)std::max<long long>(g.cnwords, 1) * 4));
+    ctx->cbitmap_cap_words = (size_t)std::max<long long>(g.cnwords, 1);
+  }
   long long nb = (g.nwords + 1023) / 1024;
-  HMSG_CUDA(cudaMalloc((void**)&ctx->bitmap, g.nwords * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->prefix, g.nwords * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->nbitmap, g.nwords * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->nprefix, g.nwords * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->blocksums, (nb + 1) * 4));
+  if ((size_t)g.nwords > ctx->bitmap_cap_words) {
+    free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->nbitmap); free_dev(ctx->nprefix);
+    HMSG_CUDA(cudaMalloc((void**)&ctx->bitmap, g.nwords * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->prefix, g.nwords * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->nbitmap, g.nwords * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->nprefix, g.nwords * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->blocksums, (nb + 1) * 4));
+    ctx->bitmap_cap_words = (size_t)g.nwords;
+  }
   HMSG_CUDA(cudaMemsetAsync(ctx->bitmap, 0, g.nwords * 4, ctx->stream));
   // ---- pass 2a: occupancy
   rc = for_frame_chunks(ctx, [&](dim3 grid, int64_t f0) {
@@ -787,12 +793,15 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   rc = run_scan(ctx, ctx->bitmap, g.nwords, ctx->prefix, &ctx->n_voxels);
   if (rc) return rc;
   // ---- pass 2b: accumulate
-  free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt); free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt);
   size_t nv = (size_t)std::max<int64_t>(ctx->n_voxels, 1);
-  HMSG_CUDA(cudaMalloc((void**)&ctx->vox_acc, nv * 48));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->vox_cnt, nv * 4));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->vox_ijk, nv * 12));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->rad_cnt, nv * 4));
+  if (nv > ctx->voxel_cap) {
+    free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt); free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt);
+    HMSG_CUDA(cudaMalloc((void**)&ctx->vox_acc, nv * 48));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->vox_cnt, nv * 4));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->vox_ijk, nv * 12));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->rad_cnt, nv * 4));
+    ctx->voxel_cap = nv;
+  }
   HMSG_CUDA(cudaMemsetAsync(ctx->vox_acc, 0, nv * 48, ctx->stream));
   HMSG_CUDA(cudaMemsetAsync(ctx->vox_cnt, 0, nv * 4, ctx->stream));
   rc = for_frame_chunks(ctx, [&](dim3 grid, int64_t f0) {
@@ -852,12 +861,15 @@ extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double r
   HMSG_CUDA(cudaMemsetAsync(ctx->cbitmap, 0, (size_t)std::max<long long>(g.cnwords, 1) * 4, ctx->stream));
   k_coarse_mark<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->nbitmap, g, ctx->cbitmap);
   HMSG_LAUNCH_CHECK();
-  free_dev(ctx->node_xyz); free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox);
   size_t nn = (size_t)std::max<int64_t>(ctx->n_nodes, 1);
-  HMSG_CUDA(cudaMalloc((void**)&ctx->node_xyz, nn * 24));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->node_rgb, nn * 24));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->node_ijk, nn * 12));
-  HMSG_CUDA(cudaMalloc((void**)&ctx->node_vox, nn * 8));
+  if (nn > ctx->node_cap) {
+    free_dev(ctx->node_xyz); free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox);
+    HMSG_CUDA(cudaMalloc((void**)&ctx->node_xyz, nn * 24));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->node_rgb, nn * 24));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->node_ijk, nn * 12));
+    HMSG_CUDA(cudaMalloc((void**)&ctx->node_vox, nn * 8));
+    ctx->node_cap = nn;
+  }
   k_compact_nodes<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->bitmap, ctx->prefix, ctx->nbitmap, ctx->nprefix, g.nwords,
                                                                                    ctx->vox_acc, ctx->vox_ijk, ctx->node_xyz, ctx->node_rgb,
                                                                                    ctx->node_ijk, ctx->node_vox);
@@ -865,7 +877,7 @@ extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double r
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->nodes_built = true;
   // feature state refers to node indices: invalidate
-  free_dev(ctx->sum_feats); free_dev(ctx->counter); free_dev(ctx->win); ctx->win_bytes = 0; ctx->d = 0;
+  ctx->d = 0;   // features_begin must be called again (buffers are kept and re-zeroed there)
   if (n_nodes) *n_nodes = ctx->n_nodes;
   return HMSG_OK;
 }
