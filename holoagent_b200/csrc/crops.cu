@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   __shared__ short s_xofs[CROP_MID];
   __shared__ short s_a[CROP_MID][2];
   __shared__ int s_h[2][CROP_MID * 3];      // horizontally interpolated source rows, already >> 4
-  __shared__ uint32_t s_row[CROP_MID];
+  __shared__ uint32_t s_row[CROP_MID + 16];   // +16 zero pad: taps beyond a column's count carry zero coefficients
   __shared__ int s_ry[ROWS_PER_BLOCK][3];   // per destination row: source row index (unclamped), beta0, beta1
   const int fb = blockIdx.z, ci = blockIdx.y;
   const bool masked = ci < M;
@@ -141,6 +141,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
     cv_coef(d, scale_x, cw, true, s, a0, a1);
     s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
   }
+  if (threadIdx.x < 16) s_row[CROP_MID + threadIdx.x] = 0;
   if (threadIdx.x < ROWS_PER_BLOCK) {
     int sy, b0, b1;
     cv_coef(dy0 + threadIdx.x, scale_y, ch, false, sy, b0, b1);
@@ -148,9 +149,9 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   }
   // PIL coefficients of this thread's output column
   const int ox = threadIdx.x;
-  int kreg[KS]; int pxmin = 0, pcnt = 0;
+  int kreg[KS]; int pxmin = 0;
   if (ox < 224) {
-    pxmin = __ldg(&bounds[ox * 2]); pcnt = __ldg(&bounds[ox * 2 + 1]);
+    pxmin = __ldg(&bounds[ox * 2]);
 #pragma unroll
     for (int k = 0; k < KS; k++) kreg[k] = __ldg(&kk[ox * KS + k]);   // entries beyond pcnt are zero
   }
@@ -161,7 +162,8 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   int sl0 = 0;
   for (int r = 0; r < ROWS_PER_BLOCK; r++) {
     const int dy = dy0 + r;
-    const int sy = s_ry[r][0], b0 = s_ry[r][1], b1 = s_ry[r][2];
+    const int sy = s_ry[r][0];
+    const unsigned b0s = (unsigned)s_ry[r][1] << 16, b1s = (unsigned)s_ry[r][2] << 16;   // (b*h)>>16 == umulhi(b<<16, h)
     const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
     int need0 = 1, need1 = 1;
     if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
       uint32_t pk = 0;
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        int v = (((b0 * h0[d * 3 + c]) >> 16) + ((b1 * h1[d * 3 + c]) >> 16) + 2) >> 2;
+        int v = (int)(__umulhi(b0s, (unsigned)h0[d * 3 + c]) + __umulhi(b1s, (unsigned)h1[d * 3 + c]) + 2u) >> 2;
         pk |= (uint32_t)(v & 255) << (8 * c);
       }
       s_row[d] = pk;
@@ -201,10 +203,8 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
       int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
 #pragma unroll
       for (int k = 0; k < KS; k++) {
-        if (k < pcnt) {
-          uint32_t px = s_row[pxmin + k];
-          a0 += (int)(px & 255) * kreg[k]; a1 += (int)((px >> 8) & 255) * kreg[k]; a2 += (int)((px >> 16) & 255) * kreg[k];
-        }
+        uint32_t px = s_row[pxmin + k];
+        a0 += (int)(px & 255) * kreg[k]; a1 += (int)((px >> 8) & 255) * kreg[k]; a2 += (int)((px >> 16) & 255) * kreg[k];
       }
       a0 = min(max(a0 >> 22, 0), 255); a1 = min(max(a1 >> 22, 0), 255); a2 = min(max(a2 >> 22, 0), 255);
       dst[(long long)dy * 224 + ox] = (uint32_t)a0 | ((uint32_t)a1 << 8) | ((uint32_t)a2 << 16);

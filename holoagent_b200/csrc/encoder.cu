@@ -143,6 +143,25 @@ __device__ __forceinline__ float gelu_erf(float x) {
   float hh = 0.5f * x * (p * __expf(-z * z));   // 0.5 x erfc(|x|/sqrt2)
   return x > 0.f ? x - hh : hh;                 // 0.5 x (1 + erf(x/sqrt2))
 }
+// packed (2 x fp32) GELU on Blackwell's FFMA2/FMUL2/FADD2 pipes: ~9.5 instructions and one MUFU per element
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float2 gelu_erf2(float2 x) {
+  // erfc(z) = 1 / (1 + a1 z + ... + a6 z^6)^16  (Abramowitz-Stegun 7.1.28, |err| < 3e-7), with z = |x|/sqrt(2)
+  // folded into the coefficients: one MUFU.RCP per element, everything else on the packed FFMA2/FMUL2 pipe
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 p = __ffma2_rn(make_float2(5.38297490e-06f, 5.38297490e-06f), ax, make_float2(4.88906371e-05f, 4.88906371e-05f));
+  p = __ffma2_rn(p, ax, make_float2(3.80035744e-05f, 3.80035744e-05f));
+  p = __ffma2_rn(p, ax, make_float2(3.27762635e-03f, 3.27762635e-03f));
+  p = __ffma2_rn(p, ax, make_float2(2.11410057e-02f, 2.11410057e-02f));
+  p = __ffma2_rn(p, ax, make_float2(4.98673469e-02f, 4.98673469e-02f));
+  p = __ffma2_rn(p, ax, make_float2(1.f, 1.f));
+  float2 r = make_float2(rcp_approx(p.x), rcp_approx(p.y));
+  r = __fmul2_rn(r, r); r = __fmul2_rn(r, r); r = __fmul2_rn(r, r); r = __fmul2_rn(r, r);      // ^16 = erfc(|x|/sqrt2)
+  float2 hh = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), r);                            // 0.5 x erfc(|x|/sqrt2)
+  float2 d = __fadd2_rn(x, make_float2(-hh.x, -hh.y));
+  return make_float2(x.x > 0.f ? d.x : hh.x, x.y > 0.f ? d.y : hh.y);
+}
 __device__ __forceinline__ float gelu_quick(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -282,7 +301,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
             if (bp) {
               float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
+              float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
+              v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
             }
             if (EPI == EPI_F16_BIAS_GELU) {
               if (g.quick_gelu) {
@@ -290,7 +311,7 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = gelu_erf(v[e]);
+                for (int e = 0; e < 4; e++) { float2 gg = gelu_erf2(make_float2(v[2 * e], v[2 * e + 1])); v[2 * e] = gg.x; v[2 * e + 1] = gg.y; }
               }
             }
             uint32_t pk[4];
@@ -502,7 +523,9 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
             if (bp) {
               float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
-              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+              float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
+              float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
+              v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
             }
             if (EPI == EPI_F16_BIAS_GELU) {
               if (g.quick_gelu) {
@@ -510,7 +533,7 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
               } else {
 #pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = gelu_erf(v[e]);
+                for (int e = 0; e < 4; e++) { float2 gg = gelu_erf2(make_float2(v[2 * e], v[2 * e + 1])); v[2 * e] = gg.x; v[2 * e + 1] = gg.y; }
               }
             }
             uint32_t pk[4];
