@@ -128,6 +128,34 @@ class Graph:
         self.full_feats_array = eng.node_feats_finalize()
         return self.full_feats_array
 
+    # ------------------------------------------------------------------ N4: graphs built by the unmodified reference
+    def load_hmsg_graph(self, path):
+        """graph.py:1892-1987 (metadata only): floors / rooms / objects JSON -> node lists; the object
+        embeddings are packed into one device matrix on the first query."""
+        from holoagent_b200.memory.hmsg.graph.store import load_graph_nodes
+        self.floors, self.rooms, self.objects = load_graph_nodes(path)
+        self.objects = [o for o in self.objects if o.embedding is not None]
+        self._index_key = None
+        return self
+
+    load_graph = load_hmsg_graph
+
+    def load_full_pcd_feats(self, path):
+        """graph.py:3832-3871: full_feats.pt -> self.full_feats_array"""
+        from holoagent_b200.memory.hmsg.graph.store import load_feats_pt
+        import os
+        self.full_feats_array = load_feats_pt(os.path.join(path, "full_feats.pt"))
+        return self.full_feats_array
+
+    def save_full_pcd_feats(self, path):
+        """graph.py:3797-3830: torch.save of the node feature array (and the per-mask features)"""
+        import os
+        import torch
+        os.makedirs(path, exist_ok=True)
+        torch.save(torch.from_numpy(np.asarray(self.full_feats_array)), os.path.join(path, "full_feats.pt"))
+        if self.frames_feats:
+            torch.save([f.numpy() if hasattr(f, "numpy") else f for f in self.frames_feats], os.path.join(path, "mask_feats.pt"))
+
     # ------------------------------------------------------------------ retrieval plumbing
     def _text(self, queries: List[str], query_feats=None):
         if query_feats is not None:

@@ -122,3 +122,19 @@ def test_extract_feats_per_pixel_dropin(engine):
     assert np.allclose(outfeat.float().numpy(), dense.float().numpy(), atol=1e-3)
     f2 = get_img_feats(ds.rgb[0], O.clip_preprocess, clip)
     assert np.allclose(f2, fe[2 * M:], atol=1e-3)
+
+
+def test_query_graph_loaded_from_reference_json(engine, tmp_path):
+    """N4: a graph written in the reference's JSON schema is served by the B200 retrieval path."""
+    from holoagent_b200.memory.hmsg.graph.graph import Graph
+    from tests.test_store import _write_graph
+    embs = _write_graph(str(tmp_path), d=512)
+    g = Graph({"pipeline": {}}, engine=engine, clip_feat_dim=512).load_hmsg_graph(str(tmp_path))
+    assert len(g.objects) == 6 and len(g.rooms) == 2          # object 5 has no embedding
+    keep = [i for i in range(7) if i != 5]
+    E = embs[keep].astype(np.float32)
+    q = (embs[2] * 0.5).astype(np.float32)[None]
+    ids, rooms, scores = g.query_hmsg_object("x", top_k=3, query_feats=q)
+    top, osc = O.query_topk(q[0], E, 3)
+    assert ids == [int(t) for t in top] and np.allclose(scores, osc, rtol=1e-5, atol=1e-4)
+    assert rooms == [keep[int(t)] % 2 for t in top]
