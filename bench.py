@@ -288,9 +288,14 @@ def main():
     fps = F / ms_step * 1e3
     g = pr["gemm"]
     gemm_tf = g["work"] / max(g["ms"], 1e-9) / 1e9
-    roof = {"bound": "tensor", "kernel": "k_gemm_f16 (tcgen05.mma cta_group::1 kind::f16, TMA 128B-swizzle operands, TMEM accumulators)",
+    traffic = {}
+    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp))
+    roof = {"bound": "tensor", "kernel": "k_gemm_f16_2sm (tcgen05.mma cta_group::2 kind::f16 M256 N256 K16, TMA 128B-swizzle operand ring, TMEM accumulators, TMA store / reduce-add epilogue)",
             "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
-            "peak_source": peaks["src"] + " bf16 cuBLAS sustained (kernel timed inside a long step)", "traffic": None,
+            "peak_source": peaks["src"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",
+            "traffic": traffic.get("gemm", {}).get("traffic_bytes_per_launch"), "traffic_note": traffic.get("gemm", {}).get("kernel"),
             "launches": g["launches"], "avg_launch_ms": g["ms"] / max(g["launches"], 1),
             "flops_per_launch": g["work"] / max(g["launches"], 1),
             "gemm_share_of_step": g["ms"] / (ms_step * args.steps),
@@ -324,7 +329,8 @@ def main():
                "passes_per_s": kp["launches"] / (ms_knn * 2) * 1e3, "queries_per_pass": KNN_Q * 2 / max(kp["launches"], 1),
                "roofline": {"bound": "hbm", "kernel": "k_sim_topk (fused fp32 matvec + warp top-k)", "achieved": gbs, "peak": peaks["hbm_gbs"],
                             "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"], "peak_source": peaks["src"] + " copy bandwidth",
-                            "bytes_per_launch": KNN_N * D * 4, "avg_launch_ms": kp["ms"] / max(kp["launches"], 1), "traffic": None},
+                            "bytes_per_launch": KNN_N * D * 4, "avg_launch_ms": kp["ms"] / max(kp["launches"], 1),
+                            "traffic": traffic.get("knn", {}).get("traffic_bytes_per_launch")},
                "replicas": world}
         del E, Q
 
