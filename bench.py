@@ -187,7 +187,7 @@ def workload_config(args, n_gpus):
                         f"{2 * M + 1} crops/frame through ViT-B/32 (d=512), voxel 0.05 m",
             "frames": args.frames, "frame_batch": args.batch, "masks_per_frame": M, "encoder": "ViT-B/32 fp16 operands / fp32 accumulate",
             "crops": args.crops, "l2_policy": "inputs (15 GB of frames, 2 GB kNN table) are larger than the 126 MB L2",
-            "parallelism": f"frame-batch shard x{n_gpus}, geometry replicated, 1 all-gather" if n_gpus > 1 else "single GPU",
+            "parallelism": f"frame-batch shard x{n_gpus} (geometry + features), 3 tiny geometry collectives + 1 NCCL all-gather of node embeddings / feature partials" if n_gpus > 1 else "single GPU",
             "knn": f"N={KNN_N} d={D} Q={KNN_Q} top-{KNN_K}"}
 
 
@@ -208,6 +208,7 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     import torch.distributed as dist
     from holoagent_b200 import synth

@@ -34,6 +34,15 @@ SIGNATURES = {
     "hmsg_scene_num_frames": (_i64, [_vp]),
     "hmsg_unproject_frame": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "hmsg_voxel_build": (_i32, [_vp, C.POINTER(_i64), _vp]),
+    "hmsg_voxel_bounds": (_i32, [_vp, _i64, _i64, _vp]),
+    "hmsg_voxel_grid_set": (_i32, [_vp, _vp]),
+    "hmsg_voxel_mark": (_i32, [_vp, _i64, _i64]),
+    "hmsg_voxel_bitmap": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    "hmsg_voxel_bitmap_or": (_i32, [_vp, _vp, _i32]),
+    "hmsg_voxel_scan": (_i32, [_vp, C.POINTER(_i64)]),
+    "hmsg_voxel_accumulate": (_i32, [_vp, _i64, _i64]),
+    "hmsg_voxel_acc": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64)]),
+    "hmsg_voxel_finalize": (_i32, [_vp]),
     "hmsg_voxels_read": (_i32, [_vp, _vp, _vp, _vp, _vp]),
     "hmsg_radius_filter": (_i32, [_vp, _i32, _f64, C.POINTER(_i64)]),
     "hmsg_radius_counts_read": (_i32, [_vp, _vp]),

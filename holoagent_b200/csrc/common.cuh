@@ -84,6 +84,7 @@ struct hmsg_ctx {
   int32_t* vox_ijk = nullptr;
   uint32_t* rad_cnt = nullptr;
   bool voxels_built = false;
+  bool grid_set = false;
 
   // ---- nodes (A3)
   int64_t n_nodes = 0;

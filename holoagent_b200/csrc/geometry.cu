@@ -729,13 +729,27 @@ static int32_t for_frame_chunks(hmsg_ctx* ctx, F&& launch) {
   return HMSG_OK;
 }
 
-extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* min_bound_out) {
+// launch a per-frame-block kernel over the frame range [f_begin, f_begin+n) in chunks (gridDim.y limit)
+template <typename F>
+static int32_t for_frame_range(hmsg_ctx* ctx, int64_t f_begin, int64_t n, F&& launch) {
+  int HW = ctx->cam.H * ctx->cam.W;
+  unsigned bpf = (unsigned)((HW + TPB * 4 - 1) / (TPB * 4));
+  for (int64_t f0 = f_begin; f0 < f_begin + n; f0 += 32768) {
+    unsigned nf = (unsigned)std::min<int64_t>(32768, f_begin + n - f0);
+    launch(dim3(bpf, nf), f0);
+    HMSG_LAUNCH_CHECK();
+  }
+  return HMSG_OK;
+}
+
+static bool range_ok(hmsg_ctx* ctx, int64_t fb, int64_t n) { return fb >= 0 && n >= 0 && fb + n <= ctx->nframes; }
+
+// ---- staged voxel build (each stage works on a frame range so that ranks can split the frames and
+// merge with tiny collectives: min/max of 6 doubles, OR of the bitmap, sum of the accumulators)
+extern "C" int32_t hmsg_voxel_bounds(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames, double minmax[6]) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (ctx->nframes <= 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_build: no frames");
+  if (!range_ok(ctx, frame_begin, n_frames) || !minmax) return ctx->fail(HMSG_ERR_ARG, "hmsg_voxel_bounds: bad frame range");
   HMSG_CUDA(cudaSetDevice(ctx->device));
-  ctx->prof_begin(PROF_GEOM);
-  // ---- pass 1: global bounds (graph.py:344-348: voxel keys are relative to the min bound of
-  // the concatenated cloud)
   long long init[6];
   {
     double pinf = INFINITY, ninf = -INFINITY;
@@ -743,15 +757,24 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
     long long op = a, on = b ^ 0x7FFFFFFFFFFFFFFFLL;
     init[0] = init[1] = init[2] = op; init[3] = init[4] = init[5] = on;
   }
+  ctx->prof_begin(PROF_GEOM);
   HMSG_CUDA(cudaMemcpyAsync(ctx->d_bounds, init, sizeof(init), cudaMemcpyHostToDevice, ctx->stream));
-  int32_t rc = for_frame_chunks(ctx, [&](dim3 grid, int64_t f0) {
+  int32_t rc = for_frame_range(ctx, frame_begin, n_frames, [&](dim3 grid, int64_t f0) {
     k_bounds<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, f0), ctx->d_bounds);
   });
   if (rc) return rc;
+  ctx->prof_end(PROF_GEOM, (double)n_frames * ctx->cam.H * ctx->cam.W * 2.0);
   long long hb[6];
   HMSG_CUDA(cudaMemcpyAsync(hb, ctx->d_bounds, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (int k = 0; k < 3; k++) { ctx->min_bound[k] = ord2d_host(hb[k]); ctx->max_bound[k] = ord2d_host(hb[3 + k]); }
+  for (int k = 0; k < 6; k++) minmax[k] = ord2d_host(hb[k]);
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_grid_set(hmsg_ctx* ctx, const double minmax[6]) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!minmax) return ctx->fail(HMSG_ERR_ARG, "hmsg_voxel_grid_set: null bounds");
+  for (int k = 0; k < 3; k++) { ctx->min_bound[k] = minmax[k]; ctx->max_bound[k] = minmax[3 + k]; }
   if (!(ctx->min_bound[0] <= ctx->max_bound[0])) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_build: no valid depth pixel in any frame");
   GridDesc& g = ctx->grid;
   g.vs = ctx->vs;
@@ -785,14 +808,52 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
     ctx->bitmap_cap_words = (size_t)g.nwords;
   }
   HMSG_CUDA(cudaMemsetAsync(ctx->bitmap, 0, g.nwords * 4, ctx->stream));
-  // ---- pass 2a: occupancy
-  rc = for_frame_chunks(ctx, [&](dim3 grid, int64_t f0) {
-    k_mark<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, f0), g, ctx->bitmap);
+  ctx->voxels_built = false; ctx->nodes_built = false; ctx->grid_set = true;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_mark(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_mark: call hmsg_voxel_grid_set first");
+  if (!range_ok(ctx, frame_begin, n_frames)) return ctx->fail(HMSG_ERR_ARG, "hmsg_voxel_mark: bad frame range");
+  ctx->prof_begin(PROF_GEOM);
+  int32_t rc = for_frame_range(ctx, frame_begin, n_frames, [&](dim3 grid, int64_t f0) {
+    k_mark<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, f0), ctx->grid, ctx->bitmap);
   });
+  ctx->prof_end(PROF_GEOM, (double)n_frames * ctx->cam.H * ctx->cam.W * 2.0);
+  return rc;
+}
+
+__global__ void __launch_bounds__(TPB) k_bitmap_or(const uint32_t* __restrict__ gathered, int world, long long nwords, uint32_t* __restrict__ bitmap) {
+  long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= nwords) return;
+  uint32_t v = 0;
+  for (int r = 0; r < world; r++) v |= gathered[(long long)r * nwords + w];
+  bitmap[w] = v;
+}
+
+extern "C" int32_t hmsg_voxel_bitmap(hmsg_ctx* ctx, uint32_t** bitmap_dev, int64_t* nwords) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_bitmap: call hmsg_voxel_grid_set first");
+  if (bitmap_dev) *bitmap_dev = ctx->bitmap;
+  if (nwords) *nwords = ctx->grid.nwords;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_bitmap_or(hmsg_ctx* ctx, const uint32_t* gathered, int32_t world) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set || !gathered || world < 1) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_bitmap_or: bad state/argument");
+  long long nw = ctx->grid.nwords;
+  k_bitmap_or<<<(unsigned)((nw + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(gathered, world, nw, ctx->bitmap);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_scan(hmsg_ctx* ctx, int64_t* n_voxels) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_scan: call hmsg_voxel_grid_set first");
+  int32_t rc = run_scan(ctx, ctx->bitmap, ctx->grid.nwords, ctx->prefix, &ctx->n_voxels);
   if (rc) return rc;
-  rc = run_scan(ctx, ctx->bitmap, g.nwords, ctx->prefix, &ctx->n_voxels);
-  if (rc) return rc;
-  // ---- pass 2b: accumulate
   size_t nv = (size_t)std::max<int64_t>(ctx->n_voxels, 1);
   if (nv > ctx->voxel_cap) {
     free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt); free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt);
@@ -804,17 +865,56 @@ extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* mi
   }
   HMSG_CUDA(cudaMemsetAsync(ctx->vox_acc, 0, nv * 48, ctx->stream));
   HMSG_CUDA(cudaMemsetAsync(ctx->vox_cnt, 0, nv * 4, ctx->stream));
-  rc = for_frame_chunks(ctx, [&](dim3 grid, int64_t f0) {
-    k_accumulate<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, f0), g, ctx->bitmap, ctx->prefix, ctx->vox_acc, ctx->vox_cnt);
+  if (n_voxels) *n_voxels = ctx->n_voxels;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_accumulate(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set || !ctx->vox_acc) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_accumulate: call hmsg_voxel_scan first");
+  if (!range_ok(ctx, frame_begin, n_frames)) return ctx->fail(HMSG_ERR_ARG, "hmsg_voxel_accumulate: bad frame range");
+  ctx->prof_begin(PROF_GEOM);
+  int32_t rc = for_frame_range(ctx, frame_begin, n_frames, [&](dim3 grid, int64_t f0) {
+    k_accumulate<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, f0), ctx->grid, ctx->bitmap, ctx->prefix, ctx->vox_acc, ctx->vox_cnt);
   });
-  if (rc) return rc;
+  ctx->prof_end(PROF_GEOM, (double)n_frames * ctx->cam.H * ctx->cam.W * 5.0);
+  return rc;
+}
+
+extern "C" int32_t hmsg_voxel_acc(hmsg_ctx* ctx, double** acc_dev, uint32_t** cnt_dev, int64_t* n_voxels) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->vox_acc) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_acc: call hmsg_voxel_scan first");
+  if (acc_dev) *acc_dev = ctx->vox_acc;
+  if (cnt_dev) *cnt_dev = ctx->vox_cnt;
+  if (n_voxels) *n_voxels = ctx->n_voxels;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_voxel_finalize(hmsg_ctx* ctx) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->grid_set || !ctx->vox_acc) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_finalize: call hmsg_voxel_scan first");
+  size_t nv = (size_t)std::max<int64_t>(ctx->n_voxels, 1);
   k_finalize_voxels<<<(unsigned)((nv + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->vox_acc, ctx->vox_cnt, ctx->n_voxels);
   HMSG_LAUNCH_CHECK();
-  k_write_ijk<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->bitmap, ctx->prefix, g, ctx->vox_ijk);
+  k_write_ijk<<<(unsigned)((ctx->grid.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->bitmap, ctx->prefix, ctx->grid, ctx->vox_ijk);
   HMSG_LAUNCH_CHECK();
-  ctx->prof_end(PROF_GEOM, (double)ctx->nframes * ctx->cam.H * ctx->cam.W * (2.0 + 2.0 + 5.0));
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->voxels_built = true; ctx->nodes_built = false;
+  return HMSG_OK;
+}
+
+// single-GPU composition of the stages over all stored frames
+extern "C" int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* min_bound_out) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (ctx->nframes <= 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_voxel_build: no frames");
+  double mm[6];
+  int32_t rc;
+  if ((rc = hmsg_voxel_bounds(ctx, 0, ctx->nframes, mm))) return rc;       // graph.py:344-348: keys are relative to the GLOBAL min bound (H3)
+  if ((rc = hmsg_voxel_grid_set(ctx, mm))) return rc;
+  if ((rc = hmsg_voxel_mark(ctx, 0, ctx->nframes))) return rc;
+  if ((rc = hmsg_voxel_scan(ctx, nullptr))) return rc;
+  if ((rc = hmsg_voxel_accumulate(ctx, 0, ctx->nframes))) return rc;
+  if ((rc = hmsg_voxel_finalize(ctx))) return rc;
   if (n_voxels) *n_voxels = ctx->n_voxels;
   if (min_bound_out) for (int k = 0; k < 3; k++) min_bound_out[k] = ctx->min_bound[k];
   return HMSG_OK;

@@ -39,6 +39,17 @@ def pack_vit_blob(state_dict, layers: int) -> np.ndarray:
     return np.concatenate(parts)
 
 
+def _wrap_dev(ptr_value: int, numel: int, dtype, device):
+    """Zero-copy torch view of library-owned device memory (plumbing for torch.distributed)."""
+    import torch
+    itemsize = torch.empty((), dtype=dtype).element_size()
+
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (int(numel),), "typestr": {torch.int32: "<i4", torch.float64: "<f8", torch.float32: "<f4"}[dtype],
+                                    "data": (int(ptr_value), False), "version": 2, "strides": None}
+    return torch.as_tensor(_Holder(), device=device)
+
+
 def _is_dev(a) -> bool:
     return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
 
@@ -155,6 +166,46 @@ class HmsgEngine:
         self._ck(self.lib.hmsg_voxel_build(self.h, C.byref(n), ptr(mb)))
         self.n_voxels = n.value
         return n.value, mb
+
+    def voxel_build_sharded(self, ranges, world):
+        """Stage-wise voxel build where this rank only touches its own frame ranges [(begin, n), ...];
+        partial results are merged with torch.distributed collectives (NCCL)."""
+        import torch
+        import torch.distributed as dist
+        dev = torch.device("cuda", self.device)
+        mm = np.array([np.inf] * 3 + [-np.inf] * 3)
+        for (b0, n) in ranges:
+            t = np.zeros(6)
+            self._ck(self.lib.hmsg_voxel_bounds(self.h, int(b0), int(n), ptr(t)))
+            mm[:3] = np.minimum(mm[:3], t[:3]); mm[3:] = np.maximum(mm[3:], t[3:])
+        lo = torch.from_numpy(mm[:3].copy()).to(dev); hi = torch.from_numpy(mm[3:].copy()).to(dev)
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        mm = np.concatenate([lo.cpu().numpy(), hi.cpu().numpy()])
+        self._ck(self.lib.hmsg_voxel_grid_set(self.h, ptr(mm)))
+        for (b0, n) in ranges:
+            self._ck(self.lib.hmsg_voxel_mark(self.h, int(b0), int(n)))
+        bp, nw = C.c_void_p(), C.c_int64()
+        self._ck(self.lib.hmsg_voxel_bitmap(self.h, C.byref(bp), C.byref(nw)))
+        mine = _wrap_dev(bp.value, nw.value, torch.int32, dev)
+        gathered = torch.empty(world * nw.value, dtype=torch.int32, device=dev)
+        self.torch_wait()
+        dist.all_gather_into_tensor(gathered, mine)
+        self.wait_torch()
+        self._ck(self.lib.hmsg_voxel_bitmap_or(self.h, ptr(gathered), int(world)))
+        nv = C.c_int64()
+        self._ck(self.lib.hmsg_voxel_scan(self.h, C.byref(nv)))
+        for (b0, n) in ranges:
+            self._ck(self.lib.hmsg_voxel_accumulate(self.h, int(b0), int(n)))
+        pa, pc = C.c_void_p(), C.c_void_p()
+        self._ck(self.lib.hmsg_voxel_acc(self.h, C.byref(pa), C.byref(pc), C.byref(nv)))
+        acc = _wrap_dev(pa.value, nv.value * 6, torch.float64, dev)
+        cnt = _wrap_dev(pc.value, nv.value, torch.int32, dev)
+        self.torch_wait()
+        dist.all_reduce(acc, op=dist.ReduceOp.SUM); dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        self.wait_torch()
+        self._ck(self.lib.hmsg_voxel_finalize(self.h))
+        self.n_voxels = nv.value
+        return nv.value, mm[:3]
 
     def voxels_read(self):
         n = self.n_voxels

@@ -1,11 +1,14 @@
 """Frame-batched HMSG ingest driver: the loop body of Graph.create_feature_map
 (fsr_vln/memory/hmsg/graph/graph.py:339-415) expressed over C-ABI calls, for one rank.
 
-Multi-GPU (option B): every rank builds the (identical) node table from all
-frames - the geometry passes read 5 B/pixel and cost ~1 % of the step - and owns the frame
-batches b with b % world == rank for crops -> encoder -> fusion -> scatter.  One NCCL
-all-gather then carries each rank's packed [partial sum_features | counter | F_p rows]; the
-partials are summed in rank order by hmsg_node_feats_merge (deterministic)."""
+Multi-GPU (option A): rank r owns the frame batches b with b % world == r for BOTH
+phases.  Geometry: local bounds / occupancy / accumulation over the rank's frames merged by three
+tiny collectives (min-max of 6 doubles, all-gather + OR of the bitmap, sum of the f64 voxel
+accumulators) so that every rank ends with the identical voxel / node table; the radius filter runs
+replicated on the merged table.  Features: crops -> encoder -> fusion -> scatter on the rank's frames,
+then ONE NCCL all-gather carries each rank's packed [partial sum_features | counter | F_p rows]; the
+partials are summed in rank order by hmsg_node_feats_merge (deterministic).  (The fp64-pipe-bound
+geometry passes cost ~15 us/frame; replicating them on every rank would cap 8-GPU efficiency at ~88 %.)"""
 from __future__ import annotations
 
 import numpy as np
@@ -93,10 +96,17 @@ class IngestJob:
         eng.wait_torch()
         eng.merge_partials(self.gather_buf, self.world, stride)
 
+    def _geometry(self):
+        """voxel table: single GPU = all frames; world > 1 = this rank's frame batches + tiny collectives"""
+        if self.world == 1:
+            self.eng.voxel_build()
+        else:
+            self.eng.voxel_build_sharded(self.my_batches, self.world)
+
     def step_device(self):
         """One whole build with frames resident in HBM."""
         eng = self.eng
-        eng.voxel_build()
+        self._geometry()
         eng.radius_filter(self.nb, self.radius)
         eng.features_begin(self.d)
         self._features_pass()
@@ -120,7 +130,7 @@ class IngestJob:
         for f0 in range(0, self.F, CH):
             f1 = min(self.F, f0 + CH)
             eng.add_frames_host(hd[f0:f1], hr[f0:f1], poses[f0:f1])
-        eng.voxel_build()
+        self._geometry()
         eng.radius_filter(self.nb, self.radius)
         eng.features_begin(self.d)
         self._features_pass(boxes_host=boxes)

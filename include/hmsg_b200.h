@@ -80,6 +80,19 @@ int32_t hmsg_unproject_frame(hmsg_ctx* ctx, int64_t frame, double* xyz, double* 
  * (graph.py:339-348, Open3D 0.18.0 VoxelDownSample semantics).  Builds the voxel table in
  * canonical ascending (i,j,k) order.  min_bound_out [3] = min over all points (nullable). */
 int32_t hmsg_voxel_build(hmsg_ctx* ctx, int64_t* n_voxels, double* min_bound_out);
+/* The same build in stages over frame ranges, so that ranks can split the frames (SURVEY 8e option A):
+ *   bounds(range) -> [all-reduce min/max of 6 doubles] -> grid_set -> mark(range) -> [all-gather bitmap,
+ *   bitmap_or] -> scan -> accumulate(range) -> [all-reduce sum of acc [n,6] f64 and cnt [n] u32] -> finalize.
+ * hmsg_voxel_build is exactly this sequence over all frames on one GPU. */
+int32_t hmsg_voxel_bounds(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames, double minmax[6]);
+int32_t hmsg_voxel_grid_set(hmsg_ctx* ctx, const double minmax[6]);
+int32_t hmsg_voxel_mark(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames);
+int32_t hmsg_voxel_bitmap(hmsg_ctx* ctx, uint32_t** bitmap_dev, int64_t* nwords);
+int32_t hmsg_voxel_bitmap_or(hmsg_ctx* ctx, const uint32_t* gathered, int32_t world);
+int32_t hmsg_voxel_scan(hmsg_ctx* ctx, int64_t* n_voxels);
+int32_t hmsg_voxel_accumulate(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames);
+int32_t hmsg_voxel_acc(hmsg_ctx* ctx, double** acc_dev, uint32_t** cnt_dev, int64_t* n_voxels);
+int32_t hmsg_voxel_finalize(hmsg_ctx* ctx);
 int32_t hmsg_voxels_read(hmsg_ctx* ctx, double* xyz, double* rgb, int32_t* ijk,
                          uint32_t* count);           /* any pointer may be NULL */
 
