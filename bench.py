@@ -231,9 +231,15 @@ def main():
     eng.scene_begin(H, W, K, 1000.0, 0.05, F)
     host_depth = host_rgb = None
     want_e2e = not args.no_e2e
+    _, my_batches = ingest.shard_batches(F, FB, world, rank)
+    n_local = sum(n for _, n in my_batches)
+    mine = np.zeros(F, dtype=bool)
+    for (b0, n) in my_batches:
+        mine[b0:b0 + n] = True
+    local_of = np.cumsum(mine) - 1          # frame id -> slot in this rank's pinned host buffers (my_batches order)
     if want_e2e:
-        host_depth = torch.empty((F, H, W), dtype=torch.int16).pin_memory()
-        host_rgb = torch.empty((F, H, W, 3), dtype=torch.uint8).pin_memory()
+        host_depth = torch.empty((max(n_local, 1), H, W), dtype=torch.int16).pin_memory()
+        host_rgb = torch.empty((max(n_local, 1), H, W, 3), dtype=torch.uint8).pin_memory()
     poses_all = synth.poses(np.arange(F)).reshape(F, 16)
     for f0 in range(0, F, 256):
         ids = np.arange(f0, min(F, f0 + 256))
@@ -241,8 +247,12 @@ def main():
         d16 = d.view(torch.int16)
         eng.add_frames(d16, c, torch.from_numpy(T.reshape(-1, 16)).to(dev))
         if want_e2e:
-            host_depth[f0:f0 + len(ids)].copy_(d16, non_blocking=True)
-            host_rgb[f0:f0 + len(ids)].copy_(c, non_blocking=True)
+            sel = np.nonzero(mine[ids])[0]
+            if len(sel):
+                st = torch.from_numpy(sel).to(dev)
+                slots = torch.from_numpy(local_of[ids[sel]])
+                host_depth[slots] = d16[st].cpu()
+                host_rgb[slots] = c[st].cpu()
         eng.sync(); torch.cuda.synchronize()
     boxes_np = np.stack([synth.make_mask_boxes(i, H, W, M) for i in range(F)])
     boxes_dev = torch.from_numpy(boxes_np).to(dev)

@@ -31,6 +31,8 @@ SIGNATURES = {
     "hmsg_prof_read": (_i32, [_vp, _i32, C.POINTER(_f64), C.POINTER(_i64), C.POINTER(_f64)]),
     "hmsg_scene_begin": (_i32, [_vp, _i32, _i32, _vp, _f32, _f64, _i64]),
     "hmsg_scene_add_frames": (_i32, [_vp, _vp, _vp, _vp, _i32, _i32]),
+    "hmsg_scene_put_frames": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32]),
+    "hmsg_scene_set_num_frames": (_i32, [_vp, _i64]),
     "hmsg_scene_num_frames": (_i64, [_vp]),
     "hmsg_unproject_frame": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "hmsg_voxel_build": (_i32, [_vp, C.POINTER(_i64), _vp]),

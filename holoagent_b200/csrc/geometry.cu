@@ -675,6 +675,29 @@ extern "C" int32_t hmsg_scene_add_frames(hmsg_ctx* ctx, const uint16_t* depth, c
   return HMSG_OK;
 }
 
+extern "C" int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, const uint16_t* depth, const uint8_t* rgb, const double* poses,
+                                         int32_t n, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->depth) return ctx->fail(HMSG_ERR_STATE, "hmsg_scene_put_frames: call hmsg_scene_begin first");
+  if (!depth || !rgb || !poses || n < 0 || frame_begin < 0) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_put_frames: bad argument");
+  if (frame_begin + n > ctx->cap) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_scene_put_frames: frame capacity exceeded");
+  size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
+  cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  HMSG_CUDA(cudaMemcpyAsync(ctx->depth + hw * frame_begin, depth, hw * 2 * n, kind, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(ctx->rgb + hw * 3 * frame_begin, rgb, hw * 3 * n, kind, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(ctx->poses + 16 * frame_begin, poses, 16 * sizeof(double) * n, kind, ctx->stream));
+  if (frame_begin + n > ctx->nframes) ctx->nframes = frame_begin + n;
+  ctx->voxels_built = false; ctx->nodes_built = false;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (n < 0 || n > ctx->cap) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_set_num_frames: out of range");
+  ctx->nframes = n;
+  return HMSG_OK;
+}
+
 extern "C" int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx) {
   if (!ctx) return HMSG_ERR_ARG;
   ctx->nframes = 0; ctx->voxels_built = false; ctx->nodes_built = false; ctx->batch_begin = -1;

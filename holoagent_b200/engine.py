@@ -167,6 +167,24 @@ class HmsgEngine:
         self.n_voxels = n.value
         return n.value, mb
 
+    def voxel_build_staged(self, ranges):
+        """single-process walk through the staged entry points (no collectives): must equal voxel_build()"""
+        mm = np.array([np.inf] * 3 + [-np.inf] * 3)
+        for (b0, n) in ranges:
+            t = np.zeros(6)
+            self._ck(self.lib.hmsg_voxel_bounds(self.h, int(b0), int(n), ptr(t)))
+            mm[:3] = np.minimum(mm[:3], t[:3]); mm[3:] = np.maximum(mm[3:], t[3:])
+        self._ck(self.lib.hmsg_voxel_grid_set(self.h, ptr(mm)))
+        for (b0, n) in ranges:
+            self._ck(self.lib.hmsg_voxel_mark(self.h, int(b0), int(n)))
+        nv = C.c_int64()
+        self._ck(self.lib.hmsg_voxel_scan(self.h, C.byref(nv)))
+        for (b0, n) in ranges:
+            self._ck(self.lib.hmsg_voxel_accumulate(self.h, int(b0), int(n)))
+        self._ck(self.lib.hmsg_voxel_finalize(self.h))
+        self.n_voxels = nv.value
+        return nv.value, mm[:3]
+
     def voxel_build_sharded(self, ranges, world):
         """Stage-wise voxel build where this rank only touches its own frame ranges [(begin, n), ...];
         partial results are merged with torch.distributed collectives (NCCL)."""
@@ -373,6 +391,14 @@ class HmsgEngine:
         """pinned torch CPU tensors (depth int16-viewed uint16, rgb uint8) + float64 poses"""
         poses_np = np.ascontiguousarray(poses_np, dtype=np.float64)
         self._ck(self.lib.hmsg_scene_add_frames(self.h, ptr(depth_t), ptr(rgb_t), ptr(poses_np), int(depth_t.shape[0]), 0))
+
+    def set_num_frames(self, n):
+        """declare the scene length when frames were put at explicit ids (ranks hold only their own)"""
+        self._ck(self.lib.hmsg_scene_set_num_frames(self.h, int(n)))
+
+    def put_frames_host(self, frame_begin, depth_t, rgb_t, poses_np):
+        poses_np = np.ascontiguousarray(poses_np, dtype=np.float64)
+        self._ck(self.lib.hmsg_scene_put_frames(self.h, int(frame_begin), ptr(depth_t), ptr(rgb_t), ptr(poses_np), int(depth_t.shape[0]), 0))
 
     def node_feats_finalize_host(self, out_t):
         self._ck(self.lib.hmsg_node_feats_finalize(self.h, ptr(out_t), 0))

@@ -117,8 +117,10 @@ class IngestJob:
 
     # ------------------------------------------------------------------
     def bind_host(self, host_depth, host_rgb, poses, boxes_np):
+        """host_depth / host_rgb: pinned tensors holding THIS RANK's frames in my_batches order
+        ([n_local,H,W] / [n_local,H,W,3]); poses / boxes: full [F,...] arrays."""
         self.host = (host_depth, host_rgb, np.ascontiguousarray(poses, dtype=np.float64), np.ascontiguousarray(boxes_np, dtype=np.int32))
-        self.h2d_bytes = host_depth.numel() * 2 + host_rgb.numel() + poses.size * 8 + self.n_local * self.M * 16
+        self.h2d_bytes = host_depth.numel() * 2 + host_rgb.numel() + self.n_local * 16 * 8 + self.n_local * self.M * 16
         self.host_out = None
 
     def step_host(self):
@@ -126,10 +128,11 @@ class IngestJob:
         eng = self.eng
         hd, hr, poses, boxes = self.host
         eng.scene_reset_frames()
-        CH = 512
-        for f0 in range(0, self.F, CH):
-            f1 = min(self.F, f0 + CH)
-            eng.add_frames_host(hd[f0:f1], hr[f0:f1], poses[f0:f1])
+        off = 0
+        for (b0, n) in self.my_batches:       # only this rank's frames cross PCIe
+            eng.put_frames_host(b0, hd[off:off + n], hr[off:off + n], poses[b0:b0 + n])
+            off += n
+        eng.set_num_frames(self.F)
         self._geometry()
         eng.radius_filter(self.nb, self.radius)
         eng.features_begin(self.d)

@@ -66,6 +66,12 @@ int32_t hmsg_scene_begin(hmsg_ctx* ctx, int32_t H, int32_t W, const double K[9],
  * camera-to-world poses float64 [n,16] row-major.  Frames get ids in arrival order. */
 int32_t hmsg_scene_add_frames(hmsg_ctx* ctx, const uint16_t* depth, const uint8_t* rgb,
                               const double* poses, int32_t n_frames, int32_t on_device);
+/* same, but at explicit frame ids [frame_begin, frame_begin+n) (a rank that owns a subset of the
+ * frames under frame-batch sharding only uploads its own); asynchronous on the ctx stream */
+int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, const uint16_t* depth,
+                              const uint8_t* rgb, const double* poses, int32_t n_frames,
+                              int32_t on_device);
+int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n_frames);
 int64_t hmsg_scene_num_frames(const hmsg_ctx* ctx);
 /* forget the stored frames (capacity and intrinsics stay): the next add starts at frame id 0 */
 int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx);

@@ -128,3 +128,17 @@ def test_mask_nodes(engine, built):
         assert np.array_equal(ijk[a:b], k)
         assert np.allclose(xyz[a:b], p, rtol=1e-12, atol=1e-12)
         assert np.allclose(rgb[a:b], c, rtol=1e-12, atol=1e-12)
+
+
+def test_staged_voxel_build_equals_monolithic(engine, built):
+    """the per-frame-range stages used for multi-GPU sharding rebuild the same voxel table"""
+    sc = built["sc"]
+    load_scene(engine, sc)
+    engine.voxel_build()
+    a = engine.voxels_read()
+    F = len(sc["ids"])
+    nv, mb = engine.voxel_build_staged([(0, 3), (3, 4), (7, F - 7)])
+    b = engine.voxels_read()
+    assert nv == len(a[0]) and np.array_equal(mb, built["mb"])
+    assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
+    assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-12) and np.allclose(a[1], b[1], rtol=1e-12, atol=1e-12)
