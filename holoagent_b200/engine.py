@@ -149,6 +149,8 @@ class HmsgEngine:
             n = depth.shape[0]
             self.wait_torch()
         self._ck(self.lib.hmsg_scene_add_frames(self.h, ptr(depth), ptr(rgb), ptr(poses), int(n), 1 if dev else 0))
+        if dev:
+            self.torch_wait()     # torch may recycle the (possibly temporary) input tensors only after our copy
 
     @property
     def num_frames(self):
@@ -196,9 +198,15 @@ class HmsgEngine:
             t = np.zeros(6)
             self._ck(self.lib.hmsg_voxel_bounds(self.h, int(b0), int(n), ptr(t)))
             mm[:3] = np.minimum(mm[:3], t[:3]); mm[3:] = np.maximum(mm[3:], t[3:])
+        import os, sys
+        dbg = os.environ.get("HMSG_DEBUG")
+        if dbg:
+            print(f"[rank {dist.get_rank()}] local bounds {mm} over {len(ranges)} ranges", file=sys.stderr, flush=True)
         lo = torch.from_numpy(mm[:3].copy()).to(dev); hi = torch.from_numpy(mm[3:].copy()).to(dev)
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         mm = np.concatenate([lo.cpu().numpy(), hi.cpu().numpy()])
+        if dbg:
+            print(f"[rank {dist.get_rank()}] merged bounds {mm}", file=sys.stderr, flush=True)
         self._ck(self.lib.hmsg_voxel_grid_set(self.h, ptr(mm)))
         for (b0, n) in ranges:
             self._ck(self.lib.hmsg_voxel_mark(self.h, int(b0), int(n)))
@@ -276,6 +284,8 @@ class HmsgEngine:
         if dev:
             self.wait_torch()
         self._ck(self.lib.hmsg_masks_dense(self.h, int(frame_begin), int(n), int(M), ptr(seg), 1 if dev else 0))
+        if dev:
+            self.torch_wait()
 
     def masks_boxes(self, frame_begin, xywh):
         dev = _is_dev(xywh)
@@ -285,6 +295,8 @@ class HmsgEngine:
         if dev:
             self.wait_torch()
         self._ck(self.lib.hmsg_masks_boxes(self.h, int(frame_begin), int(n), int(M), ptr(xywh), 1 if dev else 0))
+        if dev:
+            self.torch_wait()
 
     def fuse_scatter(self, frame_begin, n, M, feats, maskedd_weight, Fp_out=None):
         dev = _is_dev(feats)
@@ -296,13 +308,19 @@ class HmsgEngine:
             self.wait_torch()
         self._ck(self.lib.hmsg_fuse_scatter(self.h, int(frame_begin), int(n), int(M), ptr(feats), float(maskedd_weight), ptr(Fp_out),
                                             1 if dev else 0))
+        if dev:
+            self.torch_wait()
         return Fp_out
 
     def node_feats_finalize(self, out=None):
         dev = out is not None and _is_dev(out)
         if out is None:
             out = np.empty((self.n_nodes, self.d), np.float32)
+        if dev:
+            self.wait_torch()
         self._ck(self.lib.hmsg_node_feats_finalize(self.h, ptr(out), 1 if dev else 0))
+        if dev:
+            self.torch_wait()
         return out
 
     def node_feats_raw(self):
@@ -351,6 +369,7 @@ class HmsgEngine:
     def encode_images_ptr(self, x_ptr: int, B: int, out, normalize=True):
         """device pointer in (e.g. the ctx crop buffer), torch CUDA tensor out"""
         self._ck(self.lib.hmsg_encode_images(self.h, C.c_void_p(x_ptr), int(B), ptr(out), 1 if normalize else 0, 1))
+        self.torch_wait()
         return out
 
     # ------------------------------------------------------------------ crops (A8 / N3)
@@ -366,6 +385,8 @@ class HmsgEngine:
             self.wait_torch()
         out = C.c_void_p()
         self._ck(self.lib.hmsg_make_crops(self.h, int(frame_begin), int(n), int(M), ptr(xywh), int(bbox_margin), 1 if dev else 0, C.byref(out)))
+        if dev:
+            self.torch_wait()
         return out.value
 
     def encode_crops(self, frame_begin, n, M, xywh, bbox_margin, feats_out):
@@ -376,6 +397,7 @@ class HmsgEngine:
         else:
             self.wait_torch()
         self._ck(self.lib.hmsg_encode_crops(self.h, int(frame_begin), int(n), int(M), ptr(xywh), int(bbox_margin), 1 if dev else 0, ptr(feats_out)))
+        self.torch_wait()
         return feats_out
 
     def crops_read(self, n_crops):
@@ -406,9 +428,11 @@ class HmsgEngine:
     def pack_partials(self, dst, Fp_rows, fp_floats):
         self.wait_torch()
         self._ck(self.lib.hmsg_node_feats_pack(self.h, ptr(dst), ptr(Fp_rows), int(fp_floats)))
+        self.torch_wait()
 
     def merge_partials(self, gathered, world, stride):
         self._ck(self.lib.hmsg_node_feats_merge(self.h, ptr(gathered), int(world), int(stride)))
+        self.torch_wait()
 
     def gemm_debug(self, A_f16, W_f16, C_f32, M, N, K):
         self.wait_torch()
@@ -424,6 +448,8 @@ class HmsgEngine:
         if dev:
             self.wait_torch()
         self._ck(self.lib.hmsg_index_set(self.h, ptr(E), int(E.shape[0]), int(E.shape[1]), (2 if borrow else 1) if dev else 0))
+        if dev:
+            self.torch_wait()
 
     def query_topk(self, Q, k, row_mask=None, ids=None, scores=None):
         dev = _is_dev(Q)
