@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--frames", type=int, default=10000)
-    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=0, help="frames per batch (0 = auto: 64 on one GPU, 32 when sharded)")
     ap.add_argument("--crops", default="auto", choices=["auto", "device", "synthetic"])
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -216,6 +216,8 @@ def main():
     from holoagent_b200 import ingest
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.batch <= 0:
+        args.batch = 64 if world == 1 else 32
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
