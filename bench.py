@@ -165,9 +165,13 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.batch <= 0:
+        args.batch = 64 if args.gpus == 1 else 32
+    if args.crops == "auto":
+        args.crops = "device"
     vals = []
     for s in range(args.warmup + args.steps):
-        r = cpu_reference_sample(n_frames=1, enc_images=4, knn_rows=50_000, knn_queries=2)
+        r = cpu_reference_sample(n_frames=1, enc_images=16, knn_rows=100_000, knn_queries=4)
         if s >= args.warmup:
             vals.append(r)
     fps = float(np.mean([v["frames_per_s"] for v in vals]))
