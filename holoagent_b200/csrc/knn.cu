@@ -13,6 +13,7 @@
 // lists.  Ties are broken towards the lower row index.
 #include "common.cuh"
 #include <algorithm>
+#include <cub/device/device_radix_sort.cuh>
 
 #define KNN_TPB 256
 #define KNN_WARPS (KNN_TPB / 32)
@@ -31,6 +32,10 @@ struct KnnState {
   long long* out_i = nullptr;  size_t out_i_bytes = 0;
   int* out_n = nullptr;        size_t out_n_bytes = 0;
   float2* rowstate = nullptr;  size_t rowstate_bytes = 0;
+  // k > KMAX ("return everything" calls, e.g. top_k = len(objects)): dense scores + 64-bit key sort
+  float* dense = nullptr;                size_t dense_bytes = 0;
+  unsigned long long* keys = nullptr;    size_t keys_bytes = 0;
+  unsigned char* sort_tmp = nullptr;     size_t sort_tmp_bytes = 0;
   int grid = 0;
 };
 
@@ -328,6 +333,7 @@ int32_t knn_destroy(hmsg_ctx* ctx) {
   if (!st) return HMSG_OK;
   free_dev(st->E_owned); free_dev(st->q_dev); free_dev(st->mask_dev); free_dev(st->part_s); free_dev(st->part_i);
   free_dev(st->out_s); free_dev(st->out_i); free_dev(st->out_n); free_dev(st->rowstate);
+  free_dev(st->dense); free_dev(st->keys); free_dev(st->sort_tmp);
   delete st;
   ctx->knn = nullptr;
   return HMSG_OK;
@@ -375,12 +381,83 @@ static int32_t stage_inputs(hmsg_ctx* ctx, KnnState* st, const float* Q, size_t 
   return HMSG_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// k > KMAX: the reference's argsort has no k limit (callers pass top_k = len(objects) to rank a whole
+// room).  Dense scores [Qp][N] -> one 64-bit key per row (score descending, row ascending; rows that
+// are masked out or - in object mode - not won by query_id get the sentinel) -> CUB radix sort ->
+// first k.  Not the hot path: one extra N*8-byte key stream on top of the matvec.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sim_dense(const float* __restrict__ E, long long N, int d, const float* __restrict__ Q, int nq,
+                                                   float* __restrict__ out);
+
+__device__ __forceinline__ unsigned int f32_desc_key(float s) {          // larger score -> smaller key
+  unsigned int u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);                       // ascending-orderable
+  return ~u;
+}
+
+__global__ void __launch_bounds__(256) k_rank_keys(const float* __restrict__ sc, long long N, int Qp, int mode, int query_id,
+                                                   const uint8_t* __restrict__ mask, unsigned long long* __restrict__ keys) {
+  long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= N) return;
+  unsigned long long key = ~0ull;
+  if (!mask || mask[row]) {
+    float s = sc[(long long)query_id * N + row];
+    bool ok = true;
+    if (mode == 1) {                                                     // np.argmax(sim, axis=0) == query_id (first maximum wins)
+      for (int q = 0; q < Qp; q++) {
+        float o = sc[(long long)q * N + row];
+        if (o > s || (o == s && q < query_id)) { ok = false; break; }
+      }
+    }
+    if (ok) key = ((unsigned long long)f32_desc_key(s) << 32) | (unsigned long long)(unsigned int)row;
+  }
+  keys[row] = key;
+}
+
+__global__ void k_rank_emit(const unsigned long long* __restrict__ keys, long long N, const float* __restrict__ sc_q, int k,
+                            long long* __restrict__ out_i, float* __restrict__ out_s, int* __restrict__ out_n) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j == 0 && out_n) {
+    int lo = 0, hi = (int)std::min<long long>(N, (long long)k);          // valid keys sort before the sentinel: binary search the count
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (keys[mid] != ~0ull) lo = mid + 1; else hi = mid; }
+    *out_n = lo;
+  }
+  if (j >= k) return;
+  unsigned long long key = j < N ? keys[j] : ~0ull;
+  if (key == ~0ull) { out_i[j] = -1; out_s[j] = -INFINITY; return; }
+  long long row = (long long)(key & 0xffffffffull);
+  out_i[j] = row;
+  out_s[j] = sc_q[row];
+}
+
+// one request: Qp query rows at dq (device), results to oi/os/on (device)
+static int32_t ranked_request(hmsg_ctx* ctx, KnnState* st, const float* dq, int Qp, int mode, int query_id, int k, const uint8_t* dmask,
+                              long long* oi, float* os, int* on) {
+  int32_t rc;
+  long long N = st->N;
+  if ((rc = ctx->reserve(&st->dense, &st->dense_bytes, (size_t)Qp * N * 4))) return rc;
+  if ((rc = ctx->reserve(&st->keys, &st->keys_bytes, (size_t)2 * N * 8))) return rc;
+  size_t tmp = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp, st->keys, st->keys + N, (int)N, 0, 64, ctx->stream);
+  if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, tmp))) return rc;
+  long long warps = N * Qp;
+  ctx->prof_begin(PROF_KNN);
+  k_sim_dense<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, ctx->stream>>>(st->E, N, st->d, dq, Qp, st->dense);
+  ctx->prof_end(PROF_KNN, (double)N * st->d * 4.0);
+  k_rank_keys<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(st->dense, N, Qp, mode, query_id, dmask, st->keys);
+  HMSG_CUDA(cub::DeviceRadixSort::SortKeys(st->sort_tmp, tmp, st->keys, st->keys + N, (int)N, 0, 64, ctx->stream));
+  k_rank_emit<<<(k + 255) / 256, 256, 0, ctx->stream>>>(st->keys + N, N, st->dense + (size_t)query_id * N, k, oi, os, on);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
 extern "C" int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, int32_t k, const uint8_t* row_mask, int64_t* ids, float* scores,
                                    int32_t on_device) {
   if (!ctx) return HMSG_ERR_ARG;
   KnnState* st = ctx->knn;
   if (!st || !st->E) return ctx->fail(HMSG_ERR_STATE, "hmsg_query_topk: call hmsg_index_set first");
-  if (!Q || nq <= 0 || k <= 0 || k > KMAX || !ids || !scores) return ctx->fail(HMSG_ERR_ARG, "hmsg_query_topk: bad argument (1 <= k <= 32)");
+  if (!Q || nq <= 0 || k <= 0 || !ids || !scores) return ctx->fail(HMSG_ERR_ARG, "hmsg_query_topk: bad argument (k >= 1)");
   const float* dq; const uint8_t* dmask;
   int32_t rc = stage_inputs(ctx, st, Q, (size_t)nq * st->d, row_mask, on_device, &dq, &dmask);
   if (rc) return rc;
@@ -391,7 +468,11 @@ extern "C" int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, in
     oi = st->out_i; os = st->out_s;
   }
   int BQmax = g_knn_bq_override > 0 ? pick_bq(g_knn_bq_override) : 8;
-  for (int q0 = 0; q0 < nq;) {
+  if (k > KMAX) {                                   // ranked path, one query at a time
+    for (int q0 = 0; q0 < nq; q0++)
+      if ((rc = ranked_request(ctx, st, dq + (size_t)q0 * st->d, 1, 0, 0, k, dmask, oi + (size_t)q0 * k, os + (size_t)q0 * k, nullptr))) return rc;
+  }
+  for (int q0 = 0; k <= KMAX && q0 < nq;) {
     int rem = nq - q0;
     int BQ = std::min(pick_bq(rem), BQmax);
     int cnt = std::min(rem, BQ);
@@ -413,8 +494,8 @@ extern "C" int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_re
   if (!ctx) return HMSG_ERR_ARG;
   KnnState* st = ctx->knn;
   if (!st || !st->E) return ctx->fail(HMSG_ERR_STATE, "hmsg_query_object: call hmsg_index_set first");
-  if (!Q || n_req <= 0 || Qp <= 0 || query_id < 0 || query_id >= Qp || k <= 0 || k > KMAX || !ids || !scores || !n_found)
-    return ctx->fail(HMSG_ERR_ARG, "hmsg_query_object: bad argument (1 <= k <= 32, 0 <= query_id < Qp)");
+  if (!Q || n_req <= 0 || Qp <= 0 || query_id < 0 || query_id >= Qp || k <= 0 || !ids || !scores || !n_found)
+    return ctx->fail(HMSG_ERR_ARG, "hmsg_query_object: bad argument (k >= 1, 0 <= query_id < Qp)");
   const float* dq; const uint8_t* dmask;
   int32_t rc = stage_inputs(ctx, st, Q, (size_t)n_req * Qp * st->d, row_mask, on_device, &dq, &dmask);
   if (rc) return rc;
@@ -429,6 +510,10 @@ extern "C" int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_re
   if (passes > 1 && (rc = ctx->reserve(&st->rowstate, &st->rowstate_bytes, (size_t)st->N * 8))) return rc;
   for (int r = 0; r < n_req; r++) {
     const float* qr = dq + (size_t)r * Qp * st->d;
+    if (k > KMAX) {
+      if ((rc = ranked_request(ctx, st, qr, Qp, 1, query_id, k, dmask, oi + (size_t)r * k, os + (size_t)r * k, on + r))) return rc;
+      continue;
+    }
     for (int p = 0; p < passes; p++) {
       int q_base = p * 16;
       int cnt = std::min(16, Qp - q_base);

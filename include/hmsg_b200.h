@@ -205,7 +205,9 @@ int32_t hmsg_index_set(hmsg_ctx* ctx, const float* E, int64_t N, int32_t d, int3
 /* np.dot(q, E.T); np.argsort(...)[::-1][:k] per query row (graph.py:2196-2200, :3127-3133,
  * :2888-2897).  Q [nq,d]; ids [nq,k] int64; scores [nq,k] float32 (descending; ties -> lower
  * index).  row_mask: optional uint8 [N] device/host like Q (rows with 0 are skipped; the
- * room filter of graph.py:3112-3122). */
+ * room filter of graph.py:3112-3122).  Any k >= 1: k <= 32 runs the fused matvec + top-k pass,
+ * larger k (callers that rank a whole room) a dense-score + key-sort pass; slots past the number
+ * of eligible rows hold id -1 / score -inf. */
 int32_t hmsg_query_topk(hmsg_ctx* ctx, const float* Q, int32_t nq, int32_t k,
                         const uint8_t* row_mask, int64_t* ids, float* scores,
                         int32_t on_device);

@@ -63,3 +63,28 @@ def test_query_object_negative_prompts(engine, Qp):
             if not np.array_equal(ids[r][:n], top[:n]):
                 assert np.allclose(np.sort(sim[qid][ids[r][:n]]), np.sort(sim[qid][top[:n]]), atol=2e-6)
             assert np.allclose(sc[r][:n], sim[qid][ids[r][:n]], rtol=1e-3, atol=1e-6)
+
+
+def test_large_k_ranked_path(engine):
+    """k > 32 (callers rank a whole room: top_k = len(objects)) -> dense scores + key sort on the GPU."""
+    N, d = 5000, 512
+    E, Q = synth.make_knn_tables(N, 6, d)
+    E, Q = E.numpy(), Q.numpy()
+    engine.index_set(E)
+    for k in (33, 100, N):
+        ids, sc = engine.query_topk(Q[:2], k)
+        for i in range(2):
+            _check_topk(E, Q[i], ids[i], sc[i], k)
+    mask = (np.arange(N) % 7 != 0).astype(np.uint8)
+    ids, sc = engine.query_topk(Q[:1], 64, row_mask=mask)
+    sub = np.nonzero(mask)[0]
+    oid, _ = O.query_topk(Q[0], E[sub], 64)
+    assert np.array_equal(ids[0], sub[oid])
+    Qr = Q.reshape(2, 3, d)
+    ids, sc, nf = engine.query_object(Qr, 1, 4000)
+    for r in range(2):
+        top, osc = O.query_object_core(Qr[r], E, 1, 4000, True)
+        n = int(nf[r])
+        assert n == len(top)
+        assert np.array_equal(ids[r][:n], top) and np.all(ids[r][n:] == -1)
+        assert np.allclose(sc[r][:n], osc, rtol=1e-3, atol=1e-6)
