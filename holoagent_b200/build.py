@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhmsg_b200.so")
-SOURCES = ["api.cu", "geometry.cu", "features.cu", "knn.cu", "encoder.cu", "crops.cu"]
+SOURCES = ["api.cu", "geometry.cu", "features.cu", "knn.cu", "encoder.cu", "crops.cu", "objects.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",

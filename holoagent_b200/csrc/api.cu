@@ -43,6 +43,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   vit_destroy(ctx);
   knn_destroy(ctx);
+  objects_destroy(ctx);
   crops_destroy(ctx);
   free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->d_bounds);
   free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt);

@@ -36,6 +36,7 @@ struct ProfClass {
 
 struct VitState;   // encoder.cu
 struct KnnState;   // knn.cu
+struct ObjState;   // objects.cu
 
 struct GridDesc {
   double vmin[3];     // min_bound - vs/2  (Open3D voxel_min_bound)
@@ -131,6 +132,7 @@ struct hmsg_ctx {
 
   VitState* vit = nullptr;
   KnnState* knn = nullptr;
+  ObjState* obj = nullptr;
 
   uint32_t prof_mask = 0;
   ProfClass prof[PROF_NCLASS];
@@ -242,4 +244,5 @@ __device__ __forceinline__ double sqdist3(double ax, double ay, double az, doubl
 int32_t vit_destroy(hmsg_ctx* ctx);
 int32_t knn_destroy(hmsg_ctx* ctx);
 int32_t crops_destroy(hmsg_ctx* ctx);
+int32_t objects_destroy(hmsg_ctx* ctx);
 int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, int normalize);

@@ -343,6 +343,36 @@ class HmsgEngine:
             self._ck(self.lib.hmsg_mask_nodes(self.h, int(frame), float(down_size), ptr(off), ptr(xyz), ptr(rgb), ptr(ijk)))
         return off, xyz, rgb, ijk
 
+    # ------------------------------------------------------------------ N1 object instances
+    def objects_begin(self, overlap_thresh=0.75, down_size=0.05, iou_thresh=0.05):
+        """seq_merge(frames_pcd, th, down_size, proxy_th) state reset (graph_utils.py:1015-1021)"""
+        self._ck(self.lib.hmsg_objects_begin(self.h, float(overlap_thresh), float(down_size), float(iou_thresh)))
+
+    def objects_add_masks(self, off, xyz, rgb=None):
+        """one seq_merge iteration: ragged frame masks (host arrays: off int64 [n+1], xyz/rgb float64 [P,3])"""
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        if rgb is not None:
+            rgb = np.ascontiguousarray(rgb, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.lib.hmsg_objects_add_masks(self.h, int(len(off) - 1), ptr(off), ptr(xyz) if len(xyz) else None,
+                                                 ptr(rgb) if (rgb is not None and len(rgb)) else None, 0))
+
+    def objects_finish(self, min_points=10):
+        n, p = C.c_int64(), C.c_int64()
+        self._ck(self.lib.hmsg_objects_finish(self.h, int(min_points), C.byref(n), C.byref(p)))
+        return n.value, p.value
+
+    def objects_count(self):
+        n, p, g = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.hmsg_objects_count(self.h, C.byref(n), C.byref(p), C.byref(g)))
+        return n.value, p.value, g.value
+
+    def objects_read(self):
+        n, p, _ = self.objects_count()
+        off = np.zeros(n + 1, np.int64); xyz = np.empty((p, 3), np.float64); rgb = np.empty((p, 3), np.float64)
+        self._ck(self.lib.hmsg_objects_read(self.h, ptr(off), ptr(xyz) if p else None, ptr(rgb) if p else None))
+        return off, xyz, rgb
+
     # ------------------------------------------------------------------ encoder
     def encoder_load(self, state_dict, image=224, patch=32, width=768, layers=12, heads=12, mlp=3072, out_dim=512, quick_gelu=False):
         blob = pack_vit_blob(state_dict, layers)

@@ -222,6 +222,27 @@ int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_req, int32_t 
                           int32_t query_id, int32_t k, const uint8_t* row_mask,
                           int64_t* ids, float* scores, int32_t* n_found, int32_t on_device);
 
+/* ---- N1 object instances: 3-D mask merging across frames ------------------------------- */
+/* seq_merge(frames_pcd, init_overlap_thresh, voxel_size, iou_thresh) (graph.py:437-442 ->
+ * utils/graph_utils.py:1015-1038): hmsg_objects_begin resets the global mask list; every
+ * hmsg_objects_add_masks call is one loop iteration (`global = merge_3d_masks(global + frame
+ * masks)`; the first call only stores its masks); hmsg_objects_finish applies the final merge and
+ * the small-mask removal of graph.py:444-448 (`is_empty() or len(points) < min_points`).
+ * merge_3d_masks = AABB-IoU gate (compute_3d_bbox_iou, float64) -> find_overlapping_ratio_faiss
+ * (float32 exact-L2: fraction of points with a neighbour within 1.5*down_size, both ways, max) ->
+ * connected components of `ratio > overlap_thresh` -> concat in list order ->
+ * pcd_denoise_dbscan(eps 0.1, min_points 10) keeping the largest cluster unless it has < 5 points
+ * (graph_utils.py:620-679, :827-956).  A frame's masks are ragged: offsets int64 [n_masks+1] (HOST,
+ * offsets[0] = 0), xyz / rgb float64 [offsets[n_masks], 3] host or device per on_device (rgb may be
+ * NULL).  All point data stays in HBM between calls. */
+int32_t hmsg_objects_begin(hmsg_ctx* ctx, double overlap_thresh, double down_size, double iou_thresh);
+int32_t hmsg_objects_add_masks(hmsg_ctx* ctx, int32_t n_masks, const int64_t* offsets,
+                               const double* xyz, const double* rgb, int32_t on_device);
+int32_t hmsg_objects_finish(hmsg_ctx* ctx, int32_t min_points, int64_t* n_objects, int64_t* n_points);
+/* current list (after finish: the objects, self.mask_pcds): offsets [n+1], xyz / rgb [n_points,3] -> host */
+int32_t hmsg_objects_read(hmsg_ctx* ctx, int64_t* offsets, double* xyz, double* rgb);
+int32_t hmsg_objects_count(hmsg_ctx* ctx, int64_t* n_masks, int64_t* n_points, int64_t* gated_pairs);
+
 /* ---- multi-GPU ------------------------------------------------------------ */
 /* One ncclAllGather of this rank's F_p rows + partial sum_features/counter is issued by the
  * caller's communicator; see holoagent_b200/dist.py.  The library exposes the device
