@@ -75,9 +75,11 @@ SIGNATURES = {
     "hmsg_query_object": (_i32, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, _i32]),
     "hmsg_objects_begin": (_i32, [_vp, C.c_double, C.c_double, C.c_double]),
     "hmsg_objects_add_masks": (_i32, [_vp, _i32, _vp, _vp, _vp, _i32]),
+    "hmsg_objects_add_frame": (_i32, [_vp, _i64, C.c_double, C.c_double]),
     "hmsg_objects_finish": (_i32, [_vp, _i32, C.POINTER(_i64), C.POINTER(_i64)]),
     "hmsg_objects_read": (_i32, [_vp, _vp, _vp, _vp]),
     "hmsg_objects_count": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "hmsg_object_feats": (_i32, [_vp, _vp, _i32, C.c_double, C.c_double, C.c_float, _i32, _vp, _i32]),
     "hmsg_node_feats_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
 }
 

@@ -114,6 +114,7 @@ struct hmsg_ctx {
   uint32_t* maskbits = nullptr;    // [batch_cap, H*W, MW]
   size_t maskbits_bytes = 0;
   int32_t* pix_idx = nullptr;      // [batch_cap, H*W]
+  int64_t pix_idx_for = -1;        // batch_begin the pixel->node map was last computed for (-1: stale)
   size_t pix_idx_bytes = 0;
   unsigned long long* win = nullptr;   // [batch_cap, n_nodes]
   size_t win_bytes = 0;
@@ -245,4 +246,6 @@ int32_t vit_destroy(hmsg_ctx* ctx);
 int32_t knn_destroy(hmsg_ctx* ctx);
 int32_t crops_destroy(hmsg_ctx* ctx);
 int32_t objects_destroy(hmsg_ctx* ctx);
+int32_t features_ensure_pix_idx(hmsg_ctx* ctx);
+int32_t geometry_points_to_node_dev(hmsg_ctx* ctx, const double* d_pts, long long n, int64_t* d_idx, double* d_dist);
 int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, int normalize);

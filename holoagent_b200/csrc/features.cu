@@ -369,6 +369,7 @@ static int32_t ensure_batch(hmsg_ctx* ctx, int n_frames, int M) {
   if ((rc = ctx->reserve(&ctx->maskbits, &ctx->maskbits_bytes, (size_t)n_frames * hw * MW * 4))) return rc;
   if ((rc = ctx->reserve(&ctx->pix_idx, &ctx->pix_idx_bytes, (size_t)n_frames * hw * 4))) return rc;
   ctx->batch_M = M; ctx->batch_MW = MW; ctx->batch_n = n_frames;
+  ctx->pix_idx_for = -1;
   return HMSG_OK;
 }
 
@@ -478,6 +479,7 @@ extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t
     dfeats = ctx->feats_stage;
   }
   if ((rc = geometry_nn_winner(ctx, frame_begin, n))) return rc;
+  ctx->pix_idx_for = frame_begin;
   // numpy: maskedd_weight * a + (1 - maskedd_weight) * b with float32 arrays and a Python float:
   // both scalars are rounded to float32 (extractor.py:159-160)
   float w_masked = maskedd_weight;
@@ -543,6 +545,20 @@ extern "C" int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, f
   return HMSG_OK;
 }
 
+// pixel -> node map of the current mask batch (computed by hmsg_fuse_scatter; recomputed here when a
+// caller asks for 3-D masks without having scattered features for this batch)
+int32_t features_ensure_pix_idx(hmsg_ctx* ctx) {
+  if (ctx->batch_begin < 0) return ctx->fail(HMSG_ERR_STATE, "no mask batch (hmsg_masks_*)");
+  if (ctx->pix_idx_for == ctx->batch_begin) return HMSG_OK;
+  int32_t rc;
+  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)ctx->batch_n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
+  if (ctx->epoch == 0 || ctx->epoch == 0xFFFFFFFFu) { HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream)); ctx->epoch = 0; }
+  ctx->epoch++;
+  if ((rc = geometry_nn_winner(ctx, ctx->batch_begin, ctx->batch_n))) return rc;
+  ctx->pix_idx_for = ctx->batch_begin;
+  return HMSG_OK;
+}
+
 // A7: one frame (must be inside the current mask batch).
 extern "C" int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t* offsets, double* xyz, double* rgb, int32_t* ijk) {
   if (!ctx) return HMSG_ERR_ARG;
@@ -552,12 +568,8 @@ extern "C" int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_siz
   int M = ctx->batch_M, MW = ctx->batch_MW;
   int HW = ctx->cam.H * ctx->cam.W;
   int fb = (int)(frame - ctx->batch_begin);
-  // pixel -> node for this frame (no winner election needed): reuse k_nn_winner into pix_idx with a scratch win row
   int32_t rc;
-  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)ctx->batch_n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
-  if (ctx->epoch == 0) { HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream)); }
-  ctx->epoch++;
-  if ((rc = geometry_nn_winner(ctx, ctx->batch_begin, ctx->batch_n))) return rc;
+  if ((rc = features_ensure_pix_idx(ctx))) return rc;
   // count mask pixels to size the table
   size_t cap = 1;
   while (cap < (size_t)HW * 2) cap <<= 1;       // >= 2x the largest possible number of distinct (mask,cell) pairs per mask pixel

@@ -1064,6 +1064,16 @@ extern "C" int32_t hmsg_points_to_node(hmsg_ctx* ctx, const double* xyz, int64_t
   return HMSG_OK;
 }
 
+// used by objects.cu (N2): device points -> nearest node index + euclidean distance, all on device
+int32_t geometry_points_to_node_dev(hmsg_ctx* ctx, const double* d_pts, long long n, int64_t* d_idx, double* d_dist) {
+  if (!ctx->nodes_built || ctx->n_nodes == 0) return ctx->fail(HMSG_ERR_STATE, "points_to_node: node table missing or empty");
+  if (n <= 0) return HMSG_OK;
+  k_points_to_node<<<(unsigned)((n + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(d_pts, n, ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->cbitmap, ctx->node_xyz,
+                                                                             d_idx, d_dist);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
 // used by features.cu
 int32_t geometry_nn_winner(hmsg_ctx* ctx, int64_t frame_begin, int n_frames) {
   int HW = ctx->cam.H * ctx->cam.W;

@@ -27,7 +27,25 @@
 #define OTPB 256
 static const unsigned long long EMPTY_KEY = ~0ull;
 
+struct ObjFeatScratch {
+  long long* d_idx = nullptr; size_t d_idx_bytes = 0;
+  double* d_dist = nullptr; size_t d_dist_bytes = 0;
+  double* vox = nullptr; size_t vox_bytes = 0;
+  int* heads = nullptr; size_t heads_bytes = 0;
+  int* hscan = nullptr; size_t hscan_bytes = 0;
+  int* valid = nullptr; size_t valid_bytes = 0;
+  int* vscan = nullptr; size_t vscan_bytes = 0;
+  int* row_node = nullptr; size_t row_node_bytes = 0;
+  long long* d_voff = nullptr; size_t d_voff_bytes = 0;
+  float* X = nullptr; size_t X_bytes = 0;
+  float* Xn = nullptr; size_t Xn_bytes = 0;
+  uint32_t* adj = nullptr; size_t adj_bytes = 0;
+  float* ff_stage = nullptr; size_t ff_stage_bytes = 0;
+  float* out_stage = nullptr; size_t out_stage_bytes = 0;
+};
+
 struct ObjState {
+  ObjFeatScratch of;
   double th = 0.75, radius = 0.05, iou_thresh = 0.05;
   int frames_added = 0;
   bool finished = false;
@@ -578,6 +596,9 @@ int32_t objects_destroy(hmsg_ctx* ctx) {
   free_dev(st->spts); free_dev(st->sort_tmp); free_dev(st->hkeys); free_dev(st->hvals); free_dev(st->pt_comp); free_dev(st->uf); free_dev(st->core);
   free_dev(st->label); free_dev(st->csize); free_dev(st->cfirst); free_dev(st->best); free_dev(st->keep); free_dev(st->keep_scan);
   free_dev(st->in_xyz); free_dev(st->in_rgb);
+  ObjFeatScratch& S = st->of;
+  free_dev(S.d_idx); free_dev(S.d_dist); free_dev(S.vox); free_dev(S.heads); free_dev(S.hscan); free_dev(S.valid); free_dev(S.vscan);
+  free_dev(S.row_node); free_dev(S.d_voff); free_dev(S.X); free_dev(S.Xn); free_dev(S.adj); free_dev(S.ff_stage); free_dev(S.out_stage);
   delete st;
   ctx->obj = nullptr;
   return HMSG_OK;
@@ -691,3 +712,508 @@ extern "C" int32_t hmsg_objects_count(hmsg_ctx* ctx, int64_t* n_masks, int64_t* 
   if (gated_pairs) *gated_pairs = st->stat_pairs;
   return HMSG_OK;
 }
+
+// =================================================================================================
+// N2: per-object feature = largest cosine-DBSCAN cluster mean of its node features
+// Reference: fsr_vln/memory/hmsg/graph/graph.py:451-488 and utils/graph_utils.py:682-728
+//   for mask_3d in self.mask_pcds:
+//     mask_3d = mask_3d.voxel_down_sample(voxel_size)          -> (object, cell) stable sort, run means in input order
+//     dist, idx = tree_pcd.query(points, k=1); valid = dist <= 0.8 -> node NN on the occupancy bitmap (A4 machinery)
+//     feats = np.nan_to_num(self.full_feats_array[idx[valid]])
+//     feats = feats_denoise_dbscan(feats, eps=0.01, min_points=100)
+//       sklearn DBSCAN(metric="cosine"): neighbours = rows with 1 - <x/|x|, y/|y|> <= eps (float32), core iff
+//       >= min_points of them (self included), clusters = components of core points numbered by their first
+//       core row, border rows take the lowest-numbered adjacent cluster; Counter.most_common(1) -> largest
+//       cluster (ties: first met); result = mean of its rows, or the mean of all rows when nothing clusters.
+// Per object: rows are gathered + normalised (warp per row), the n x n thresholded similarity is built once
+// as a bit matrix by a 64x64-tile fp32 kernel (GEMM-shaped but it must be fp32: the threshold sits 1e-2 from
+// 1.0), then core / union-find / border / sizes run on the bit rows.  Objects with fewer rows than
+// min_points cannot have a core point and skip the n^2 work.
+// =================================================================================================
+
+__global__ void __launch_bounds__(OTPB) k_obj_vox_keys(const double* __restrict__ xyz, long long npts, const long long* __restrict__ off, int n,
+                                                       const double* __restrict__ lo, double vs, unsigned long long* __restrict__ keys,
+                                                       int* __restrict__ idx, int* __restrict__ counters) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts) return;
+  int o = mask_of_point(off, n, p);
+  unsigned long long key = (unsigned long long)o << 42;
+  for (int a = 0; a < 3; a++) {
+    double vmin = __dsub_rn(lo[o * 3 + a], __dmul_rn(vs, 0.5));       // Open3D voxel_min_bound = min_bound - voxel_size / 2
+    long long c = (long long)floor(cell_coord(xyz[p * 3 + a], vmin, vs));
+    if (c < 0 || c > 16383) { atomicExch(&counters[1], 1); c = 0; }
+    key |= (unsigned long long)c << (28 - 14 * a);
+  }
+  keys[p] = key;
+  idx[p] = (int)p;
+}
+
+__global__ void __launch_bounds__(OTPB) k_run_heads(const unsigned long long* __restrict__ skeys, long long npts, int* __restrict__ heads) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < npts) heads[p] = (p == 0 || skeys[p - 1] != skeys[p]) ? 1 : 0;
+}
+
+// one thread per run: sequential float64 sum in input order (stable sort), then / count  (Open3D AccumulatedPoint)
+__global__ void __launch_bounds__(OTPB) k_run_means(const unsigned long long* __restrict__ skeys, const int* __restrict__ sidx,
+                                                    const int* __restrict__ heads, const int* __restrict__ hscan, long long npts,
+                                                    const double* __restrict__ xyz, double* __restrict__ vox) {
+  long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= npts || !heads[p]) return;
+  unsigned long long key = skeys[p];
+  double sx = 0, sy = 0, sz = 0; int c = 0;
+  for (long long q = p; q < npts && skeys[q] == key; q++) {
+    long long o = sidx[q];
+    sx = __dadd_rn(sx, xyz[o * 3]); sy = __dadd_rn(sy, xyz[o * 3 + 1]); sz = __dadd_rn(sz, xyz[o * 3 + 2]);
+    c++;
+  }
+  long long v = hscan[p];
+  vox[v * 3] = __ddiv_rn(sx, (double)c); vox[v * 3 + 1] = __ddiv_rn(sy, (double)c); vox[v * 3 + 2] = __ddiv_rn(sz, (double)c);
+}
+
+__global__ void k_pick_offsets(const int* __restrict__ scan, const int* __restrict__ flag, const long long* __restrict__ off, int n, long long total,
+                               long long* __restrict__ out) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o > n) return;
+  long long p = off[o];
+  out[o] = p < total ? scan[p] : (total ? scan[total - 1] + flag[total - 1] : 0);
+}
+
+__global__ void __launch_bounds__(OTPB) k_valid_rows(const double* __restrict__ dist, long long nv, double max_dist, int* __restrict__ valid) {
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv) valid[v] = dist[v] <= max_dist ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(OTPB) k_compact_rows(const long long* __restrict__ idx, const int* __restrict__ valid, const int* __restrict__ vscan,
+                                                       long long nv, int* __restrict__ row_node) {
+  long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < nv && valid[v]) row_node[vscan[v]] = (int)idx[v];
+}
+
+// warp per row: X = nan_to_num(full_feats[node]); Xn = X / (|X| or 1)   (sklearn normalize: zero norms -> 1)
+__global__ void __launch_bounds__(OTPB) k_gather_norm(const float* __restrict__ full, const int* __restrict__ row_node, int n, int d,
+                                                      float* __restrict__ X, float* __restrict__ Xn) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const float* src = full + (long long)row_node[r] * d;
+  float ss = 0.f;
+  for (int j = lane; j < d; j += 32) {
+    float v = src[j];
+    if (isnan(v)) v = 0.f; else if (isinf(v)) v = v > 0 ? 3.4028234663852886e38f : -3.4028234663852886e38f;     // np.nan_to_num
+    X[(long long)r * d + j] = v;
+    ss = fmaf(v, v, ss);
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  float nrm = sqrtf(ss);
+  if (nrm == 0.f) nrm = 1.f;
+  for (int j = lane; j < d; j += 32) Xn[(long long)r * d + j] = __fdiv_rn(X[(long long)r * d + j], nrm);
+}
+
+// adj[i][j] = (1 - <Xn_i, Xn_j> <= eps), 64x64 tile per block, 4x4 per thread, fp32
+__global__ void __launch_bounds__(256) k_cos_adj(const float* __restrict__ Xn, int n, int d, float eps, uint32_t* __restrict__ adj, int W) {
+  __shared__ float sa[32][65], sb[32][65];
+  __shared__ uint32_t bits[64][2];
+  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+  float acc[4][4] = {};
+  if (threadIdx.x < 128) bits[threadIdx.x >> 1][threadIdx.x & 1] = 0u;
+  for (int k0 = 0; k0 < d; k0 += 32) {
+    for (int e = threadIdx.x; e < 64 * 32; e += 256) {
+      int rr = e >> 5, kk = e & 31;
+      sa[kk][rr] = (r0 + rr < n && k0 + kk < d) ? Xn[(long long)(r0 + rr) * d + k0 + kk] : 0.f;
+      sb[kk][rr] = (c0 + rr < n && k0 + kk < d) ? Xn[(long long)(c0 + rr) * d + k0 + kk] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int kk = 0; kk < 32; kk++) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; i++) { a[i] = sa[kk][ty * 4 + i]; b[i] = sb[kk][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      int col = c0 + tx * 4 + j;
+      float dist = __fsub_rn(1.0f, acc[i][j]);
+      if (col < n && dist <= eps) m |= 1u << (((tx & 7) * 4) + j);
+    }
+    if (m) atomicOr(&bits[ty * 4 + i][tx >> 3], m);
+  }
+  __syncthreads();
+  if (threadIdx.x < 128) {
+    int rr = threadIdx.x >> 1, w = threadIdx.x & 1;
+    if (r0 + rr < n) adj[(long long)(r0 + rr) * W + blockIdx.x * 2 + w] = bits[rr][w];
+  }
+}
+
+__global__ void __launch_bounds__(OTPB) k_adj_core(const uint32_t* __restrict__ adj, int n, int W, int min_points, unsigned char* __restrict__ core) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  int c = 0;
+  for (int w = lane; w < W; w += 32) c += __popc(adj[(long long)r * W + w]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) core[r] = c >= min_points ? 1 : 0;
+}
+
+__global__ void __launch_bounds__(OTPB) k_adj_union(const uint32_t* __restrict__ adj, int n, int W, const unsigned char* __restrict__ core,
+                                                    int* __restrict__ uf) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n || !core[r]) return;
+  for (int w = lane; w * 32 < r; w += 32) {
+    uint32_t b = adj[(long long)r * W + w];
+    while (b) {
+      int j = w * 32 + __ffs(b) - 1;
+      b &= b - 1;
+      if (j < r && core[j]) uf_union(uf, r, j);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OTPB) k_adj_label(const uint32_t* __restrict__ adj, int n, int W, const unsigned char* __restrict__ core,
+                                                    int* __restrict__ uf, int* __restrict__ label, int* __restrict__ csize, int* __restrict__ cfirst) {
+  int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  int lab;
+  if (core[r]) {
+    lab = uf_find(uf, r);
+  } else {
+    int best = 0x7fffffff;
+    for (int w = lane; w < W; w += 32) {
+      uint32_t b = adj[(long long)r * W + w];
+      while (b) {
+        int j = w * 32 + __ffs(b) - 1;
+        b &= b - 1;
+        if (core[j]) best = min(best, uf_find(uf, j));
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    lab = best == 0x7fffffff ? -1 : best;
+  }
+  if (lane == 0) {
+    label[r] = lab;
+    if (lab >= 0) { atomicAdd(&csize[lab], 1); atomicMin(&cfirst[lab], r); }
+  }
+}
+
+__global__ void __launch_bounds__(OTPB) k_obj_best(const int* __restrict__ label, const int* __restrict__ csize, const int* __restrict__ cfirst, int n,
+                                                   unsigned long long* __restrict__ best) {
+  int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n || label[r] != r) return;
+  atomicMax(best, ((unsigned long long)(unsigned int)csize[r] << 32) | (unsigned long long)(0xFFFFFFFFu - (unsigned int)cfirst[r]));
+}
+
+// out[j] = mean over the selected rows (largest cluster, or all rows when best == 0), rows added in order in float32
+__global__ void __launch_bounds__(OTPB) k_mean_rows(const float* __restrict__ X, int n, int d, const int* __restrict__ label,
+                                                    const unsigned long long* __restrict__ best, float* __restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= d) return;
+  unsigned long long b = best ? *best : 0ull;
+  int want = -2;
+  if (b) want = label[0xFFFFFFFFu - (unsigned int)(b & 0xFFFFFFFFu)];
+  float s = 0.f; int c = 0;
+  for (int r = 0; r < n; r++)
+    if (want == -2 || label[r] == want) { s = __fadd_rn(s, X[(long long)r * d + j]); c++; }
+  out[j] = __fdiv_rn(s, (float)c);
+}
+
+extern "C" int32_t hmsg_object_feats(hmsg_ctx* ctx, const float* full_feats, int32_t d, double voxel_size, double max_dist, float eps,
+                                     int32_t min_points, float* out, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  ObjState* st = ctx->obj;
+  if (!st || !st->finished) return ctx->fail(HMSG_ERR_STATE, "hmsg_object_feats: call hmsg_objects_finish first");
+  if (!full_feats || !out || d <= 0 || !(voxel_size > 0) || min_points < 1) return ctx->fail(HMSG_ERR_ARG, "hmsg_object_feats: bad argument");
+  if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_object_feats: no node table (hmsg_radius_filter)");
+  ObjFeatScratch& S = st->of;
+  int32_t rc;
+  int n_obj = (int)st->a_off.size() - 1;
+  long long npts = st->a_off.back();
+  if (n_obj == 0) return HMSG_OK;
+  const float* dfull = full_feats; float* dout = out;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&S.ff_stage, &S.ff_stage_bytes, (size_t)std::max<int64_t>(ctx->n_nodes, 1) * d * 4))) return rc;
+    if ((rc = ctx->reserve(&S.out_stage, &S.out_stage_bytes, (size_t)n_obj * d * 4))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(S.ff_stage, full_feats, (size_t)ctx->n_nodes * d * 4, cudaMemcpyHostToDevice, ctx->stream));
+    dfull = S.ff_stage; dout = S.out_stage;
+  }
+  HMSG_CUDA(cudaMemsetAsync(dout, 0, (size_t)n_obj * d * 4, ctx->stream));      // objects without rows: np.zeros((1, dim))
+  std::vector<long long> roff(n_obj + 1, 0);
+  if (npts > 0) {
+    // ---- voxel_down_sample of every object at once
+    if ((rc = ctx->reserve(&st->d_off, &st->d_off_bytes, (size_t)(n_obj + 1) * 8))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(st->d_off, st->a_off.data(), (size_t)(n_obj + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = ctx->reserve(&st->d_lo, &st->d_lo_bytes, (size_t)n_obj * 24 + 64))) return rc;
+    if ((rc = ctx->reserve(&st->d_hi, &st->d_hi_bytes, (size_t)n_obj * 24))) return rc;
+    if ((rc = ctx->reserve(&st->keys, &st->keys_bytes, (size_t)npts * 16))) return rc;
+    if ((rc = ctx->reserve(&st->pidx, &st->pidx_bytes, (size_t)npts * 8))) return rc;
+    if (!st->d_counters) { HMSG_CUDA(cudaMalloc((void**)&st->d_counters, 16)); HMSG_CUDA(cudaMalloc((void**)&st->d_glob, 24)); }
+    HMSG_CUDA(cudaMemsetAsync(st->d_counters, 0, 16, ctx->stream));
+    k_mask_aabb<<<n_obj, 128, 0, ctx->stream>>>(st->a_xyz, st->d_off, st->d_lo, st->d_hi);
+    k_obj_vox_keys<<<blocks_for(npts), OTPB, 0, ctx->stream>>>(st->a_xyz, npts, st->d_off, n_obj, st->d_lo, voxel_size, st->keys, st->pidx, st->d_counters);
+    size_t tmp = 0;
+    unsigned long long* kout = st->keys + npts; int* iout = st->pidx + npts;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, st->keys, kout, st->pidx, iout, (int)npts, 0, 63, ctx->stream);
+    if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, tmp))) return rc;
+    HMSG_CUDA(cub::DeviceRadixSort::SortPairs(st->sort_tmp, tmp, st->keys, kout, st->pidx, iout, (int)npts, 0, 63, ctx->stream));
+    if ((rc = ctx->reserve(&S.heads, &S.heads_bytes, (size_t)npts * 4))) return rc;
+    if ((rc = ctx->reserve(&S.hscan, &S.hscan_bytes, (size_t)npts * 4))) return rc;
+    k_run_heads<<<blocks_for(npts), OTPB, 0, ctx->stream>>>(kout, npts, S.heads);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, S.heads, S.hscan, (int)npts, ctx->stream);
+    if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, tmp))) return rc;
+    HMSG_CUDA(cub::DeviceScan::ExclusiveSum(st->sort_tmp, tmp, S.heads, S.hscan, (int)npts, ctx->stream));
+    if ((rc = ctx->reserve(&S.d_voff, &S.d_voff_bytes, (size_t)(n_obj + 1) * 8 * 2))) return rc;
+    k_pick_offsets<<<blocks_for(n_obj + 1), OTPB, 0, ctx->stream>>>(S.hscan, S.heads, st->d_off, n_obj, npts, S.d_voff);
+    HMSG_LAUNCH_CHECK();
+    std::vector<long long> voff(n_obj + 1);
+    int flag[2];
+    HMSG_CUDA(cudaMemcpyAsync(voff.data(), S.d_voff, (size_t)(n_obj + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaMemcpyAsync(flag, st->d_counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (flag[1]) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_object_feats: an object spans more than 2^14 voxels per axis");
+    long long nv = voff[n_obj];
+    if ((rc = ctx->reserve(&S.vox, &S.vox_bytes, (size_t)nv * 24))) return rc;
+    if ((rc = ctx->reserve(&S.d_idx, &S.d_idx_bytes, (size_t)nv * 8))) return rc;
+    if ((rc = ctx->reserve(&S.d_dist, &S.d_dist_bytes, (size_t)nv * 8))) return rc;
+    if ((rc = ctx->reserve(&S.valid, &S.valid_bytes, (size_t)nv * 4))) return rc;
+    if ((rc = ctx->reserve(&S.vscan, &S.vscan_bytes, (size_t)nv * 4))) return rc;
+    if ((rc = ctx->reserve(&S.row_node, &S.row_node_bytes, (size_t)nv * 4))) return rc;
+    k_run_means<<<blocks_for(npts), OTPB, 0, ctx->stream>>>(kout, iout, S.heads, S.hscan, npts, st->a_xyz, S.vox);
+    HMSG_LAUNCH_CHECK();
+    // ---- nearest node + distance gate (graph.py:459-473)
+    if ((rc = geometry_points_to_node_dev(ctx, S.vox, nv, (int64_t*)S.d_idx, S.d_dist))) return rc;
+    k_valid_rows<<<blocks_for(nv), OTPB, 0, ctx->stream>>>(S.d_dist, nv, max_dist, S.valid);
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp, S.valid, S.vscan, (int)nv, ctx->stream);
+    if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, tmp))) return rc;
+    HMSG_CUDA(cub::DeviceScan::ExclusiveSum(st->sort_tmp, tmp, S.valid, S.vscan, (int)nv, ctx->stream));
+    k_compact_rows<<<blocks_for(nv), OTPB, 0, ctx->stream>>>(S.d_idx, S.valid, S.vscan, nv, S.row_node);
+    long long* d_roff = S.d_voff + (n_obj + 1);
+    HMSG_CUDA(cudaMemcpyAsync(S.d_voff, voff.data(), (size_t)(n_obj + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    k_pick_offsets<<<blocks_for(n_obj + 1), OTPB, 0, ctx->stream>>>(S.vscan, S.valid, S.d_voff, n_obj, nv, d_roff);
+    HMSG_LAUNCH_CHECK();
+    HMSG_CUDA(cudaMemcpyAsync(roff.data(), d_roff, (size_t)(n_obj + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  // ---- per object: gather, cosine DBSCAN, cluster mean
+  long long nmax = 0;
+  for (int o = 0; o < n_obj; o++) nmax = std::max(nmax, roff[o + 1] - roff[o]);
+  if (nmax == 0) goto done;
+  if (nmax > 65536) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_object_feats: an object has more than 65536 node rows (bit-matrix DBSCAN limit)");
+  {
+    int Wmax = (int)(((nmax + 63) / 64) * 2);
+    if ((rc = ctx->reserve(&S.X, &S.X_bytes, (size_t)nmax * d * 4))) return rc;
+    if ((rc = ctx->reserve(&S.Xn, &S.Xn_bytes, (size_t)nmax * d * 4))) return rc;
+    if (nmax >= min_points && (rc = ctx->reserve(&S.adj, &S.adj_bytes, (size_t)nmax * Wmax * 4))) return rc;
+    if ((rc = ctx->reserve(&st->core, &st->core_bytes, (size_t)nmax))) return rc;
+    if ((rc = ctx->reserve(&st->uf, &st->uf_bytes, (size_t)nmax * 4))) return rc;
+    if ((rc = ctx->reserve(&st->label, &st->label_bytes, (size_t)nmax * 4))) return rc;
+    if ((rc = ctx->reserve(&st->csize, &st->csize_bytes, (size_t)nmax * 4))) return rc;
+    if ((rc = ctx->reserve(&st->cfirst, &st->cfirst_bytes, (size_t)nmax * 4))) return rc;
+    if ((rc = ctx->reserve(&st->best, &st->best_bytes, 8))) return rc;
+    for (int o = 0; o < n_obj; o++) {
+      int n = (int)(roff[o + 1] - roff[o]);
+      if (n == 0) continue;
+      unsigned wb = blocks_for((long long)n * 32);
+      k_gather_norm<<<wb, OTPB, 0, ctx->stream>>>(dfull, S.row_node + roff[o], n, d, S.X, S.Xn);
+      HMSG_CUDA(cudaMemsetAsync(st->best, 0, 8, ctx->stream));
+      if (n >= min_points) {
+        int W = ((n + 63) / 64) * 2;
+        dim3 tg((n + 63) / 64, (n + 63) / 64);
+        k_cos_adj<<<tg, 256, 0, ctx->stream>>>(S.Xn, n, d, eps, S.adj, W);
+        k_adj_core<<<wb, OTPB, 0, ctx->stream>>>(S.adj, n, W, min_points, st->core);
+        k_iota<<<blocks_for(n), OTPB, 0, ctx->stream>>>(st->uf, n);
+        k_adj_union<<<wb, OTPB, 0, ctx->stream>>>(S.adj, n, W, st->core, st->uf);
+        HMSG_CUDA(cudaMemsetAsync(st->csize, 0, (size_t)n * 4, ctx->stream));
+        HMSG_CUDA(cudaMemsetAsync(st->cfirst, 0x7f, (size_t)n * 4, ctx->stream));
+        k_adj_label<<<wb, OTPB, 0, ctx->stream>>>(S.adj, n, W, st->core, st->uf, st->label, st->csize, st->cfirst);
+        k_obj_best<<<blocks_for(n), OTPB, 0, ctx->stream>>>(st->label, st->csize, st->cfirst, n, st->best);
+      }
+      k_mean_rows<<<blocks_for(d), OTPB, 0, ctx->stream>>>(S.X, n, d, st->label, st->best, dout + (size_t)o * d);
+      HMSG_LAUNCH_CHECK();
+    }
+  }
+done:
+  if (!on_device) {
+    HMSG_CUDA(cudaMemcpyAsync(out, dout, (size_t)n_obj * d * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return HMSG_OK;
+}
+
+// =================================================================================================
+// A7 -> N1 chained on the device: the 3-D masks of one frame (generic.py:141-190 create_3d_masks) go
+// straight into the merge without visiting the host.
+//   pcd_masked = create_pcd(mask, depth, pose, mask_img=True, filter_distance)   -> the frame's pixel->node map
+//   pcd_masked = pcd[indices]                  one node centroid PER MASK PIXEL (multiplicity kept)
+//   pcd_mask.voxel_down_sample(down_size)      relative to the mask's own min bound
+// Entries (mask, pixel) are ordered by a first radix sort, keyed by (mask, cell) and ordered by a second
+// STABLE sort, so each voxel's float64 sum runs over its pixels in row-major order exactly like Open3D's
+// sequential accumulation: the mask point sets are bit-identical to the reference's, not just close.
+// filter_distance: a mask whose mean depth exceeds it yields an empty cloud (generic.py:126-127; the mean is
+// taken in float64 here, float32 pairwise in numpy - they differ only within 1e-7 of the threshold).
+// =================================================================================================
+__global__ void __launch_bounds__(OTPB) k_fm_stats(const int32_t* __restrict__ pidx, const uint32_t* __restrict__ mbits, const uint16_t* __restrict__ depth,
+                                                   float scale, int HW, int MW, const double* __restrict__ nodes, int* __restrict__ cnt,
+                                                   double* __restrict__ dsum, long long* __restrict__ mb) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  int n = pidx[p];
+  if (n < 0) return;
+  double df = (double)__fdiv_rn((float)depth[p], scale);
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = mbits[(long long)p * MW + w];
+    while (bits) {
+      int m = __ffs(bits) - 1 + 32 * w;
+      bits &= bits - 1;
+      atomicAdd(&cnt[m], 1);
+      atomicAdd(&dsum[m], df);
+      for (int k = 0; k < 3; k++) atomicMin(&mb[m * 3 + k], d2ord(nodes[(long long)n * 3 + k]));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OTPB) k_fm_entries(const int32_t* __restrict__ pidx, const uint32_t* __restrict__ mbits, int HW, int MW,
+                                                     const long long* __restrict__ eoff, const unsigned char* __restrict__ keepm, int* __restrict__ cursor,
+                                                     unsigned long long* __restrict__ ekey) {
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW || pidx[p] < 0) return;
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = mbits[(long long)p * MW + w];
+    while (bits) {
+      int m = __ffs(bits) - 1 + 32 * w;
+      bits &= bits - 1;
+      if (!keepm[m]) continue;
+      long long pos = eoff[m] + atomicAdd(&cursor[m], 1);
+      ekey[pos] = ((unsigned long long)m << 32) | (unsigned int)p;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(OTPB) k_fm_cellkeys(const unsigned long long* __restrict__ ekey, long long E, const int32_t* __restrict__ pidx,
+                                                      const double* __restrict__ nodes, const long long* __restrict__ mb, double vs,
+                                                      unsigned long long* __restrict__ keys, int* __restrict__ vals, int* __restrict__ counters) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  unsigned long long ek = ekey[e];
+  int m = (int)(ek >> 32), p = (int)(ek & 0xffffffffu);
+  int n = pidx[p];
+  unsigned long long key = (unsigned long long)m << 42;
+  for (int k = 0; k < 3; k++) {
+    long long o = mb[m * 3 + k];
+    long long bb = o >= 0 ? o : (o ^ 0x7FFFFFFFFFFFFFFFLL);
+    double vmin = __dsub_rn(__longlong_as_double(bb), __dmul_rn(vs, 0.5));
+    long long c = (long long)floor(cell_coord(nodes[(long long)n * 3 + k], vmin, vs));
+    if (c < 0 || c > 16383) { atomicExch(&counters[1], 1); c = 0; }
+    key |= (unsigned long long)c << (28 - 14 * k);
+  }
+  keys[e] = key;
+  vals[e] = n;
+}
+
+__global__ void __launch_bounds__(OTPB) k_fm_means(const unsigned long long* __restrict__ skeys, const int* __restrict__ snode, const int* __restrict__ heads,
+                                                   const int* __restrict__ hscan, long long E, const double* __restrict__ nodes,
+                                                   const double* __restrict__ nrgb, double* __restrict__ oxyz, double* __restrict__ orgb) {
+  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E || !heads[e]) return;
+  unsigned long long key = skeys[e];
+  double s[6] = {0, 0, 0, 0, 0, 0}; int c = 0;
+  for (long long q = e; q < E && skeys[q] == key; q++) {
+    long long n = snode[q];
+    for (int k = 0; k < 3; k++) { s[k] = __dadd_rn(s[k], nodes[n * 3 + k]); s[3 + k] = __dadd_rn(s[3 + k], nrgb[n * 3 + k]); }
+    c++;
+  }
+  long long v = hscan[e];
+  for (int k = 0; k < 3; k++) { oxyz[v * 3 + k] = __ddiv_rn(s[k], (double)c); orgb[v * 3 + k] = __ddiv_rn(s[3 + k], (double)c); }
+}
+
+extern "C" int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double down_size, double filter_distance) {
+  if (!ctx) return HMSG_ERR_ARG;
+  ObjState* st = ctx->obj;
+  if (!st || st->finished) return ctx->fail(HMSG_ERR_STATE, "hmsg_objects_add_frame: call hmsg_objects_begin first");
+  if (ctx->batch_begin < 0 || frame < ctx->batch_begin || frame >= ctx->batch_begin + ctx->batch_n)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_objects_add_frame: frame is not in the current mask batch (hmsg_masks_*)");
+  if (!(down_size > 0)) return ctx->fail(HMSG_ERR_ARG, "hmsg_objects_add_frame: bad down_size");
+  int32_t rc;
+  if ((rc = features_ensure_pix_idx(ctx))) return rc;
+  ObjFeatScratch& S = st->of;
+  int M = ctx->batch_M, MW = ctx->batch_MW, HW = ctx->cam.H * ctx->cam.W;
+  int fb = (int)(frame - ctx->batch_begin);
+  const int32_t* pidx = ctx->pix_idx + (size_t)fb * HW;
+  const uint32_t* mbits = ctx->maskbits + (size_t)fb * HW * MW;
+  const uint16_t* depth = ctx->depth + (size_t)frame * HW;
+  // per-mask scratch: cnt[M] int | cursor[M] int | dsum[M] double | mb[3M] ll | eoff[M+1] ll | keep[M] u8
+  size_t need = (size_t)M * 4 * 2 + (size_t)M * 8 + (size_t)M * 24 + (size_t)(M + 1) * 8 + M + 64;
+  if ((rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, need))) return rc;
+  char* base = (char*)ctx->scratch;
+  double* dsum = (double*)base;
+  long long* mb = (long long*)(dsum + M);
+  long long* d_eoff = mb + 3 * M;
+  int* cnt = (int*)(d_eoff + M + 1);
+  int* cursor = cnt + M;
+  unsigned char* d_keep = (unsigned char*)(cursor + M);
+  std::vector<long long> init(3 * M);
+  { double pinf = INFINITY; long long a; memcpy(&a, &pinf, 8); for (auto& v : init) v = a; }
+  HMSG_CUDA(cudaMemsetAsync(base, 0, need, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(mb, init.data(), (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+  k_fm_stats<<<blocks_for(HW), OTPB, 0, ctx->stream>>>(pidx, mbits, depth, ctx->cam.scale, HW, MW, ctx->node_xyz, cnt, dsum, mb);
+  HMSG_LAUNCH_CHECK();
+  std::vector<int> hcnt(M); std::vector<double> hsum(M);
+  HMSG_CUDA(cudaMemcpyAsync(hcnt.data(), cnt, (size_t)M * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(hsum.data(), dsum, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<long long> eoff(M + 1, 0); std::vector<unsigned char> keepm(M, 0);
+  for (int m = 0; m < M; m++) {
+    bool keep = hcnt[m] > 0 && !(hsum[m] / (double)hcnt[m] > filter_distance);     // `if Z.mean() > filter_distance: return empty`
+    keepm[m] = keep ? 1 : 0;
+    eoff[m + 1] = eoff[m] + (keep ? hcnt[m] : 0);
+  }
+  long long E = eoff[M];
+  std::vector<int64_t> voff(M + 1, 0);
+  if (E == 0) return hmsg_objects_add_masks(ctx, M, voff.data(), nullptr, nullptr, 1);
+  if (E >= (1LL << 31)) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_objects_add_frame: too many mask pixels");
+  HMSG_CUDA(cudaMemcpyAsync(d_eoff, eoff.data(), (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(d_keep, keepm.data(), (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
+  if ((rc = ctx->reserve(&st->keys, &st->keys_bytes, (size_t)E * 16))) return rc;
+  if ((rc = ctx->reserve(&st->pidx, &st->pidx_bytes, (size_t)E * 8))) return rc;
+  if (!st->d_counters) { HMSG_CUDA(cudaMalloc((void**)&st->d_counters, 16)); HMSG_CUDA(cudaMalloc((void**)&st->d_glob, 24)); }
+  HMSG_CUDA(cudaMemsetAsync(st->d_counters, 0, 16, ctx->stream));
+  unsigned long long* k0 = st->keys; unsigned long long* k1 = st->keys + E;
+  int* v0 = st->pidx; int* v1 = st->pidx + E;
+  k_fm_entries<<<blocks_for(HW), OTPB, 0, ctx->stream>>>(pidx, mbits, HW, MW, d_eoff, d_keep, cursor, k0);
+  size_t tmp = 0, tmp2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, tmp, k0, k1, (int)E, 0, 43, ctx->stream);
+  cub::DeviceRadixSort::SortPairs(nullptr, tmp2, k0, k1, v0, v1, (int)E, 0, 53, ctx->stream);
+  if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, std::max(tmp, tmp2)))) return rc;
+  HMSG_CUDA(cub::DeviceRadixSort::SortKeys(st->sort_tmp, tmp, k0, k1, (int)E, 0, 43, ctx->stream));                 // (mask, pixel) order
+  k_fm_cellkeys<<<blocks_for(E), OTPB, 0, ctx->stream>>>(k1, E, pidx, ctx->node_xyz, mb, down_size, k0, v0, st->d_counters);
+  HMSG_CUDA(cub::DeviceRadixSort::SortPairs(st->sort_tmp, tmp2, k0, k1, v0, v1, (int)E, 0, 53, ctx->stream));        // stable: (mask, cell), pixels in order
+  if ((rc = ctx->reserve(&S.heads, &S.heads_bytes, (size_t)E * 4))) return rc;
+  if ((rc = ctx->reserve(&S.hscan, &S.hscan_bytes, (size_t)E * 4))) return rc;
+  k_run_heads<<<blocks_for(E), OTPB, 0, ctx->stream>>>(k1, E, S.heads);
+  cub::DeviceScan::ExclusiveSum(nullptr, tmp, S.heads, S.hscan, (int)E, ctx->stream);
+  if ((rc = ctx->reserve(&st->sort_tmp, &st->sort_tmp_bytes, tmp))) return rc;
+  HMSG_CUDA(cub::DeviceScan::ExclusiveSum(st->sort_tmp, tmp, S.heads, S.hscan, (int)E, ctx->stream));
+  if ((rc = ctx->reserve(&S.d_voff, &S.d_voff_bytes, (size_t)(M + 1) * 8 * 2))) return rc;
+  k_pick_offsets<<<blocks_for(M + 1), OTPB, 0, ctx->stream>>>(S.hscan, S.heads, d_eoff, M, E, S.d_voff);
+  HMSG_LAUNCH_CHECK();
+  int flag[2];
+  std::vector<long long> hv(M + 1);
+  HMSG_CUDA(cudaMemcpyAsync(hv.data(), S.d_voff, (size_t)(M + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaMemcpyAsync(flag, st->d_counters, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (flag[1]) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_objects_add_frame: a mask spans more than 2^14 voxels per axis");
+  long long nv = hv[M];
+  if ((rc = ctx->reserve(&st->in_xyz, &st->in_xyz_bytes, (size_t)nv * 24))) return rc;
+  if ((rc = ctx->reserve(&st->in_rgb, &st->in_rgb_bytes, (size_t)nv * 24))) return rc;
+  k_fm_means<<<blocks_for(E), OTPB, 0, ctx->stream>>>(k1, v1, S.heads, S.hscan, E, ctx->node_xyz, ctx->node_rgb, st->in_xyz, st->in_rgb);
+  HMSG_LAUNCH_CHECK();
+  for (int m = 0; m <= M; m++) voff[m] = hv[m];
+  return hmsg_objects_add_masks(ctx, M, voff.data(), st->in_xyz, st->in_rgb, 1);
+}
+
+// the frame masks staged by the last hmsg_objects_add_frame are not kept; this reads the CURRENT global list instead

@@ -357,6 +357,10 @@ class HmsgEngine:
         self._ck(self.lib.hmsg_objects_add_masks(self.h, int(len(off) - 1), ptr(off), ptr(xyz) if len(xyz) else None,
                                                  ptr(rgb) if (rgb is not None and len(rgb)) else None, 0))
 
+    def objects_add_frame(self, frame, down_size, filter_distance=float("inf")):
+        """one seq_merge iteration fed from the device: create_3d_masks(frame) -> merge, nothing visits the host"""
+        self._ck(self.lib.hmsg_objects_add_frame(self.h, int(frame), float(down_size), float(filter_distance)))
+
     def objects_finish(self, min_points=10):
         n, p = C.c_int64(), C.c_int64()
         self._ck(self.lib.hmsg_objects_finish(self.h, int(min_points), C.byref(n), C.byref(p)))
@@ -372,6 +376,15 @@ class HmsgEngine:
         off = np.zeros(n + 1, np.int64); xyz = np.empty((p, 3), np.float64); rgb = np.empty((p, 3), np.float64)
         self._ck(self.lib.hmsg_objects_read(self.h, ptr(off), ptr(xyz) if p else None, ptr(rgb) if p else None))
         return off, xyz, rgb
+
+    def object_feats(self, full_feats, voxel_size, max_dist=0.8, eps=0.01, min_points=100):
+        """graph.py:451-488: one feature row per object of objects_finish() (host numpy in / out)"""
+        full_feats = np.ascontiguousarray(full_feats, dtype=np.float32)
+        n, _, _ = self.objects_count()
+        out = np.zeros((n, full_feats.shape[1]), np.float32)
+        self._ck(self.lib.hmsg_object_feats(self.h, ptr(full_feats), int(full_feats.shape[1]), float(voxel_size), float(max_dist), float(eps),
+                                            int(min_points), ptr(out), 0))
+        return out
 
     # ------------------------------------------------------------------ encoder
     def encoder_load(self, state_dict, image=224, patch=32, width=768, layers=12, heads=12, mlp=3072, out_dim=512, quick_gelu=False):

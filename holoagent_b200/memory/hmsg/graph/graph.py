@@ -1,5 +1,6 @@
 """Drop-in for the hot half of fsr_vln/memory/hmsg/graph/graph.py: ``Graph.create_feature_map``
-(:262-415) and the retrieval cores ``query_hmsg_object`` (:3056-3162), ``query_object``
+(:262-491: node table, node features, 3-D mask merging into objects, per-object features) and the
+retrieval cores ``query_hmsg_object`` (:3056-3162), ``query_object``
 (:3363-3481), ``query_graph`` (:2189-2214), ``identify_object`` (:1441-1454),
 ``query_hmsg_room`` (:3164-3272) and ``query_room`` (:3277-3359), all on libhmsg_b200.so.
 
@@ -55,6 +56,7 @@ class Graph:
         self.floors = []
         self._index_key = None
         self.frame_batch = 16
+        self.keep_frames_pcd = True      # per-frame 3-D masks as host point clouds (the reference's local `frames_pcd`)
 
     # ------------------------------------------------------------------ build (graph.py:262-415)
     def create_feature_map(self, save_path=None):
@@ -96,6 +98,12 @@ class Graph:
         # ---- pass 2 (graph.py:373-411)
         d = self.clip_feat_dim
         eng.features_begin(d)
+        g = lambda k, dflt: getattr(p, k, dflt) if not isinstance(p, dict) else p.get(k, dflt)
+        merge_type = g("merge_type", "sequential")
+        if merge_type != "sequential":
+            raise NotImplementedError("pipeline.merge_type=%r: only the reference's default 'sequential' merge is on the device" % (merge_type,))
+        max_mask_distance = float(g("max_mask_distance", float("inf")))
+        eng.objects_begin(float(g("init_overlap_thresh", 0.75)), float(p.voxel_size), float(g("iou_thresh", 0.05)))   # seq_merge args, graph.py:437-442
         self.frames_pcd, self.frames_feats = [], []
         dev = f"cuda:{eng.device}"
         for b0 in range(0, len(ids), self.frame_batch):
@@ -122,10 +130,20 @@ class Graph:
             Fp = Fp.cpu()
             for k, ms in enumerate(all_masks):
                 self.frames_feats.append(Fp[k, :len(ms)])
-                off, mx, mc, _ = eng.mask_nodes(b0 + k, float(p.voxel_size), M)
-                self.frames_pcd.append([to_o3d(PointCloud(mx[off[j]:off[j + 1]], mc[off[j]:off[j + 1]])) for j in range(len(ms))])
+                if self.keep_frames_pcd:
+                    off, mx, mc, _ = eng.mask_nodes(b0 + k, float(p.voxel_size), M)
+                    self.frames_pcd.append([to_o3d(PointCloud(mx[off[j]:off[j + 1]], mc[off[j]:off[j + 1]])) for j in range(len(ms))])
+                # create_3d_masks + one seq_merge iteration (graph.py:391-402, :437-442), on the device
+                eng.objects_add_frame(b0 + k, float(p.voxel_size), max_mask_distance)
         # ---- graph.py:413-415
         self.full_feats_array = eng.node_feats_finalize()
+        # ---- graph.py:424-448: final merge + removal of masks with < 10 points -> self.mask_pcds
+        eng.objects_finish(10)
+        off, ox, oc = eng.objects_read()
+        self.mask_pcds = [to_o3d(PointCloud(ox[off[j]:off[j + 1]], oc[off[j]:off[j + 1]])) for j in range(len(off) - 1)]
+        # ---- graph.py:451-488: one feature per object (cosine-DBSCAN largest-cluster mean) -> self.mask_feats
+        feats = eng.object_feats(self.full_feats_array, float(p.voxel_size), 0.8, 0.01, 100) if len(self.mask_pcds) else np.zeros((0, d), np.float32)
+        self.mask_feats = [feats[j] for j in range(len(self.mask_pcds))]
         return self.full_feats_array
 
     # ------------------------------------------------------------------ N4: graphs built by the unmodified reference

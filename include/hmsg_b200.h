@@ -238,10 +238,27 @@ int32_t hmsg_query_object(hmsg_ctx* ctx, const float* Q, int32_t n_req, int32_t 
 int32_t hmsg_objects_begin(hmsg_ctx* ctx, double overlap_thresh, double down_size, double iou_thresh);
 int32_t hmsg_objects_add_masks(hmsg_ctx* ctx, int32_t n_masks, const int64_t* offsets,
                                const double* xyz, const double* rgb, int32_t on_device);
+/* Same iteration fed from the device: the 3-D masks of `frame` (create_3d_masks, generic.py:141-190,
+ * with filter_distance = cfg.pipeline.max_mask_distance) are built from the current mask batch
+ * (hmsg_masks_*) and merged without leaving HBM.  Voxel sums run over the mask's pixels in row-major
+ * order (stable sort), so the point sets are bit-identical to Open3D's sequential accumulation. */
+int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double down_size, double filter_distance);
 int32_t hmsg_objects_finish(hmsg_ctx* ctx, int32_t min_points, int64_t* n_objects, int64_t* n_points);
 /* current list (after finish: the objects, self.mask_pcds): offsets [n+1], xyz / rgb [n_points,3] -> host */
 int32_t hmsg_objects_read(hmsg_ctx* ctx, int64_t* offsets, double* xyz, double* rgb);
 int32_t hmsg_objects_count(hmsg_ctx* ctx, int64_t* n_masks, int64_t* n_points, int64_t* gated_pairs);
+
+/* ---- N2 per-object feature ------------------------------------------------------------ */
+/* graph.py:451-488 over the objects of hmsg_objects_finish: voxel_down_sample(voxel_size) ->
+ * nearest node (tree_pcd.query) -> keep matches with dist <= max_dist (0.8) ->
+ * np.nan_to_num(full_feats[idx]) -> feats_denoise_dbscan(eps, min_points) (utils/graph_utils.py:
+ * 682-728: sklearn DBSCAN(metric="cosine"), largest cluster mean, or the mean of all rows when
+ * nothing clusters; objects without rows get zeros).  full_feats [n_nodes,d] float32 is
+ * self.full_feats_array (hmsg_node_feats_finalize); out [n_objects,d] float32 = self.mask_feats.
+ * Both host or both device per on_device. */
+int32_t hmsg_object_feats(hmsg_ctx* ctx, const float* full_feats, int32_t d, double voxel_size,
+                          double max_dist, float eps, int32_t min_points, float* out,
+                          int32_t on_device);
 
 /* ---- multi-GPU ------------------------------------------------------------ */
 /* One ncclAllGather of this rank's F_p rows + partial sum_features/counter is issued by the

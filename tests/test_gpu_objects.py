@@ -95,3 +95,97 @@ def test_objects_edge_cases(engine):
     engine.objects_add_masks(np.zeros(1, np.int64), np.zeros((0, 3)))         # a frame without masks
     engine.objects_add_masks(np.array([0, 0, 0], np.int64), np.zeros((0, 3)))  # two empty masks
     assert engine.objects_finish(10) == (0, 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# fixture scene helpers (the scene of tests/golden/ref_build.npz)
+# ------------------------------------------------------------------------------------------------
+def _fixture_scene(engine):
+    z = np.load(os.path.join(GOLD, "ref_build.npz"))
+    H, W = int(z["H"]), int(z["W"])
+    depth, rgb, T, K = synth.make_frames_np(z["frame_ids"], H, W)
+    segs = np.unpackbits(z["segs"], axis=-1)[..., :W].astype(bool)
+    vs = float(z["voxel_size"])
+    engine.scene_begin(H, W, K, 1000.0, vs, len(depth))
+    engine.add_frames(depth, rgb, T.reshape(len(depth), 16))
+    engine.voxel_build()
+    engine.radius_filter(1000, 1.0)
+    nxyz, nrgb, _, _ = engine.nodes_read()
+    assert nxyz.shape == z["node_xyz"].shape
+    return z, depth, rgb, T, K, segs, vs, nxyz, nrgb
+
+
+def test_add_frame_chained_on_device(engine):
+    """create_3d_masks + seq_merge without leaving HBM == the oracle run on the GPU's own node table,
+    bit for bit (voxel sums follow the row-major pixel order like Open3D's sequential accumulation)."""
+    z, depth, rgb, T, K, segs, vs, nxyz, nrgb = _fixture_scene(engine)
+    tree = O.build_tree(nxyz)
+    frames_masks = []
+    for f in range(len(depth)):
+        pts, _, _ = O.create_pcd(rgb[f], depth[f], K, 1000.0, T[f])
+        gidx, _ = engine.pixel_to_node(f, want_dist=False)                      # stage-wise: exact NN ties are implementation-defined
+        full = np.asarray(gidx)
+        fm = []
+        for seg in segs[f]:
+            sel = (seg & (depth[f] > 0)).reshape(-1)
+            idx = full[sel]
+            p, c, _, _ = O.voxel_down_sample(nxyz[idx], nrgb[idx], vs) if sel.any() else (np.zeros((0, 3)), np.zeros((0, 3)), None, None)
+            fm.append((p, c))
+        frames_masks.append(fm)
+    ref = [o for o in O.seq_merge(frames_masks, 0.75, vs, 0.05) if len(o[0]) >= 10]
+    engine.objects_begin(0.75, vs, 0.05)
+    for f in range(len(depth)):
+        engine.masks_dense(f, segs[f][None].astype(np.uint8))
+        engine.objects_add_frame(f, vs, 6.0)
+    engine.objects_finish(10)
+    off, xyz, col = engine.objects_read()
+    assert len(off) - 1 == len(ref)
+    for i, (p, c) in enumerate(ref):
+        assert np.array_equal(xyz[off[i]:off[i + 1]], p), i
+        assert np.array_equal(col[off[i]:off[i + 1]], c), i
+    # and within float64 noise of what the reference run itself produced (its node centroids were summed sequentially)
+    assert np.array_equal(off, z["obj_off"]) and np.allclose(xyz, z["obj_pts"], rtol=1e-11, atol=1e-11)
+    # filter_distance: every mask farther than 0.5 m on average is dropped -> nothing survives
+    engine.objects_begin(0.75, vs, 0.05)
+    for f in range(len(depth)):
+        engine.masks_dense(f, segs[f][None].astype(np.uint8))
+        engine.objects_add_frame(f, vs, 0.5)
+    assert engine.objects_finish(10) == (0, 0)
+
+
+def test_object_feats_vs_oracle(engine):
+    """N2: voxel_down_sample -> NN gate -> nan_to_num -> cosine DBSCAN largest-cluster mean (graph.py:451-488)."""
+    z, depth, rgb, T, K, segs, vs, nxyz, nrgb = _fixture_scene(engine)
+    off = z["obj_off"]
+    objs = [z["obj_pts"][off[i]:off[i + 1]] for i in range(len(off) - 1)]
+    # extra objects: a tiny one (< min_points rows), one far from every node (all rows gated out), an empty one
+    objs.append(nxyz[:40] + 1e-3)
+    objs.append(nxyz[:30] + np.array([50.0, 0, 0]))
+    engine.objects_begin(0.75, vs, 0.05)
+    o2 = np.zeros(len(objs) + 1, np.int64)
+    for i, p in enumerate(objs):
+        o2[i + 1] = o2[i] + len(p)
+    # a single frame whose masks are the objects; th = 2 > any ratio: nothing merges, DBSCAN(0.1, 10) may trim
+    engine.objects_begin(2.0, vs, 0.05)
+    engine.objects_add_masks(o2, np.concatenate(objs, 0))
+    engine.objects_finish(1)
+    goff, gxyz, _ = engine.objects_read()
+    kept = [gxyz[goff[i]:goff[i + 1]] for i in range(len(goff) - 1)]
+    n, d = len(nxyz), 256
+    rs = np.random.RandomState(4)
+    base = rs.randn(7, d).astype(np.float32); base /= np.linalg.norm(base, axis=1, keepdims=True)
+    region = (np.floor(nxyz[:, 0] / 0.7).astype(np.int64) + 3 * np.floor(nxyz[:, 1] / 0.9).astype(np.int64)) % 7
+    full = base[region] * (0.5 + rs.rand(n, 1).astype(np.float32)) + 0.004 * rs.randn(n, d).astype(np.float32)
+    scatter = rs.rand(n) < 0.15                         # rows that belong to no cluster
+    full[scatter] = rs.randn(int(scatter.sum()), d).astype(np.float32)
+    full[rs.rand(n) < 0.02] = 0.0                       # nodes no pixel ever hit
+    full[5, 3] = np.nan; full[9, 1] = np.inf
+    full = full.astype(np.float32)
+    got = engine.object_feats(full, vs, 0.8, 0.01, 100)
+    tree = O.build_tree(nxyz)
+    ref = O.object_feats(kept, nxyz, tree, full, vs, d)
+    ref = np.stack([np.asarray(r, np.float32).reshape(-1) for r in ref])
+    assert got.shape == ref.shape
+    fin = np.isfinite(ref).all(1)
+    assert np.allclose(got[fin], ref[fin], rtol=1e-4, atol=1e-5)
+    assert np.all(got[-1] == 0)                         # the far object: no valid rows -> zeros
