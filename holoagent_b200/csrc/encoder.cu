@@ -613,6 +613,22 @@ __global__ void __launch_bounds__(256) k_im2col(const float* __restrict__ x, __h
     *reinterpret_cast<uint2*>(a0 + ((b * G * G + py * G + px)) * Kpad + c * P * P + iy * P + ix) = pk;
   }
 }
+// any patch size (ViT-L/14: P = 14, Kc = 588 -> Kpad = 640): one thread per A0 element, pad columns zero filled
+__global__ void __launch_bounds__(256) k_im2col_generic(const float* __restrict__ x, __half* __restrict__ a0, long long n, int S, int P, int G, int Kc,
+                                                        int Kpad) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int col = (int)(i % Kpad);
+  const long long row = i / Kpad;
+  float v = 0.f;
+  if (col < Kc) {
+    const int c = col / (P * P), rem = col - c * P * P, iy = rem / P, ix = rem - iy * P;
+    const int pidx = (int)(row % (G * G)); const long long b = row / (G * G);
+    const int py = pidx / G, px = pidx - py * G;
+    v = __ldg(x + ((b * 3 + c) * S + py * P + iy) * (long long)S + px * P + ix);
+  }
+  a0[i] = __float2half_rn(v);
+}
 __global__ void k_zero_pad_cols(__half* a0, long long rows, int Kc, int Kpad) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int padw = Kpad - Kc;
@@ -1097,6 +1113,144 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------
+// attention for any T (ViT-L/14 = the reference's default `models.clip.type`: 257 tokens, graph.py:98-104).
+// One CTA per (image, head): K and V of the head are staged once in shared memory (cp.async, rows padded to a
+// multiple of 16 and zero filled); each warp owns 16-row query tiles (staged through a private smem slab for
+// ldmatrix) and walks the keys in blocks of 64 with an online softmax (running max / sum in fp32), so the
+// 16 x T score row never exists.  Same mma.sync m16n8k16 fragments as the T <= 64 kernels above.
+// ------------------------------------------------------------------------------------------
+constexpr int ATTF_WARPS = 6;
+static inline int attf_smem_bytes(int Tp) { return (2 * Tp + ATTF_WARPS * 16) * ATT_LD * 2; }
+
+__global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
+                                                                    int W, float scale, int Tp) {
+  extern __shared__ __align__(16) unsigned char att_smem[];
+  __half* sK = reinterpret_cast<__half*>(att_smem);
+  __half* sV = sK + (size_t)Tp * ATT_LD;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __half* sQ = sV + (size_t)Tp * ATT_LD + (size_t)warp * 16 * ATT_LD;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int ld = 3 * W;
+  const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
+  for (int i = threadIdx.x; i < Tp * 8; i += ATTF_WARPS * 32) {
+    const int r = i >> 3, ch = i & 7;
+    __half* dk = sK + r * ATT_LD + ch * 8;
+    __half* dv = sV + r * ATT_LD + ch * 8;
+    if (r < T) {
+      const __half* src = src0 + (long long)r * ld + ch * 8;
+      cp_async16(dk, src + W);
+      cp_async16(dv, src + 2 * W);
+    } else {   // padding keys: finite zeros (their scores are masked, P = 0 there)
+      *reinterpret_cast<uint4*>(dk) = make_uint4(0, 0, 0, 0);
+      *reinterpret_cast<uint4*>(dv) = make_uint4(0, 0, 0, 0);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
+  const int g = lane >> 2, t = lane & 3;
+  const int m_tiles = (T + 15) / 16;
+  for (int mi = warp; mi < m_tiles; mi += ATTF_WARPS) {
+    // stage this warp's 16 query rows
+    __syncwarp();
+    for (int i = lane; i < 16 * 8; i += 32) {
+      const int r = i >> 3, ch = i & 7, row = mi * 16 + r;
+      __half* dq = sQ + r * ATT_LD + ch * 8;
+      if (row < T) cp_async16(dq, src0 + (long long)row * ld + ch * 8);
+      else *reinterpret_cast<uint4*>(dq) = make_uint4(0, 0, 0, 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncwarp();
+    uint32_t aq[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ks++) ldsm_x4(aq[ks], sQ + (lane & 15) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float oacc[8][4];
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+    for (int kb = 0; kb < Tp; kb += 64) {
+      const int nt = min(4, (Tp - kb) >> 4);   // 16-key steps in this block (warp uniform)
+      float s[8][4];
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < 4; ks++) {
+#pragma unroll
+        for (int np = 0; np < 4; np++) {
+          if (np < nt) {
+            uint32_t bb[4];
+            ldsm_x4(bb, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+            mma_16816(s[np * 2], aq[ks], bb);
+            mma_16816(s[np * 2 + 1], aq[ks], bb + 2);
+          }
+        }
+      }
+      float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const int col = kb + ni * 8 + 2 * t + e;
+          const float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
+          const float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
+          s[ni][e] = v0; s[ni][2 + e] = v1;
+          bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1);
+        }
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      // every block holds at least one valid key (kb < T), so the new maxima are finite
+      const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+      const float al0 = __expf(m0 - n0), al1 = __expf(m1 - n1);   // exp(-inf) = 0 on the first block
+      m0 = n0; m1 = n1;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const float p0 = __expf(s[ni][e] - n0), p1 = __expf(s[ni][2 + e] - n1);
+          s[ni][e] = p0; s[ni][2 + e] = p1;
+          ps0 += p0; ps1 += p1;
+        }
+      }
+      l0 = l0 * al0 + ps0; l1 = l1 * al1 + ps1;   // per-thread partial row sums (the quad is reduced once at the end)
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) { oacc[ni][0] *= al0; oacc[ni][1] *= al0; oacc[ni][2] *= al1; oacc[ni][3] *= al1; }
+#pragma unroll
+      for (int kk = 0; kk < 4; kk++) {
+        if (kk < nt) {
+          uint32_t a[4];
+          __half2 h0 = __floats2half2_rn(s[2 * kk][0], s[2 * kk][1]);
+          __half2 h1 = __floats2half2_rn(s[2 * kk][2], s[2 * kk][3]);
+          __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+          a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
+          a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+#pragma unroll
+          for (int np = 0; np < 4; np++) {
+            uint32_t bb[4];
+            ldsm_x4_t(bb, sV + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + (np * 2 + (lane >> 4)) * 8);
+            mma_16816(oacc[np * 2], a, bb);
+            mma_16816(oacc[np * 2 + 1], a, bb + 2);
+          }
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = mi * 16 + g, r1 = r0 + 8;
+#pragma unroll
+    for (int ni = 0; ni < 8; ni++) {
+      const int col = h * 64 + ni * 8 + 2 * t;
+      if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0] * inv0, oacc[ni][1] * inv0);
+      if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2] * inv1, oacc[ni][3] * inv1);
+    }
+  }
+}
+
 // straightforward fp32 reference attention (debug: HMSG_ATTN_SIMPLE=1), one block per (image, head)
 __global__ void __launch_bounds__(128) k_attention_simple(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads, int W,
                                                           float scale) {
@@ -1168,6 +1322,8 @@ struct VitState {
   bool attn_v1 = false;
   bool attn_v2 = false;
   bool attn_v3_db = false;   // v3 with 4 double-buffered tiles per SM instead of 8 single-buffered ones
+  bool attn_flash = false;   // force the any-T kernel (always used when T > 64)
+  int flash_smem_set = 0;
   bool smem_attr_set = false;
 };
 
@@ -1231,9 +1387,9 @@ static int32_t launch_gemm2_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtens
 static int g_gemm_2sm = -1;
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
-  if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2
+  if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2, 4: v3 double buffered, 5: any-T online-softmax kernel
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
-    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->smem_attr_set = false;
+    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->attn_flash = value == 5; ctx->vit->smem_attr_set = false;
     return HMSG_OK;
   }
   return -1;
@@ -1290,11 +1446,13 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
   if (!ctx) return HMSG_ERR_ARG;
   if (!desc || !blob) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: null argument");
   const hmsg_vit_desc& d = *desc;
-  if (d.image % 4 != 0 || d.patch % 4 != 0 || d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
+  if (d.image <= 0 || d.patch <= 0 || d.layers <= 0 || d.heads <= 0 || d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
       (3 * d.width) % 256 != 0 || d.width % 256 != 0)
     return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: unsupported ViT shape (need head_dim 64, width/mlp/out_dim multiples of 256)");
   int G = d.image / d.patch, T = G * G + 1;
-  if (T > 64) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: more than 64 tokens per image is not supported yet (ViT-B/32 has 50)");
+  if (T > 4096) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: more than 4096 tokens per image is not supported");
+  if (attf_smem_bytes((T + 15) / 16 * 16) > 220 * 1024)
+    return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: K/V of one head do not fit in shared memory (T too large)");
   vit_destroy(ctx);
   VitState* vs = new VitState();
   ctx->vit = vs;
@@ -1383,12 +1541,20 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
   int32_t rc;
   __half* a0 = vs->gbuf;
   float* patch = reinterpret_cast<float*>(vs->qkv);
-  if (!patches_ready && vs->Kpad != vs->Kc) {
+  const bool fast_im2col = d.image % 4 == 0 && d.patch % 4 == 0;
+  if (!patches_ready && !fast_im2col) {
+    ctx->prof_begin(PROF_ELTWISE);
+    long long n = RP * vs->Kpad;
+    k_im2col_generic<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(dx, a0, n, d.image, d.patch, G, vs->Kc, vs->Kpad);
+    ctx->prof_end(PROF_ELTWISE, (double)B * 3 * d.image * d.image * 6);
+    HMSG_LAUNCH_CHECK();
+  }
+  if (!patches_ready && fast_im2col && vs->Kpad != vs->Kc) {
     long long n = RP * (vs->Kpad - vs->Kc);
     k_zero_pad_cols<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(a0, RP, vs->Kc, vs->Kpad);
     HMSG_LAUNCH_CHECK();
   }
-  if (!patches_ready) {
+  if (!patches_ready && fast_im2col) {
     ctx->prof_begin(PROF_ELTWISE);
     long long nrows = (long long)B * 3 * d.image;
     k_im2col<<<(unsigned)((nrows * 32 + 255) / 256), 256, 0, ctx->stream>>>(dx, a0, nrows, d.image, d.patch, G, vs->Kpad);
@@ -1407,7 +1573,15 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     HMSG_LAUNCH_CHECK();
     if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
     ctx->prof_begin(PROF_ATTN);
-    if (vs->attn_simple) {
+    if (T > 64 || vs->attn_flash) {
+      const int Tp = (T + 15) / 16 * 16;
+      const int sm = attf_smem_bytes(Tp);
+      if (vs->flash_smem_set != sm) {
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_flash, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        vs->flash_smem_set = sm;
+      }
+      k_attention_flash<<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp);
+    } else if (vs->attn_simple) {
       k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     } else if (vs->attn_v1) {
       size_t sm = (size_t)4 * 3 * 64 * ATT_LD * 2;

@@ -203,6 +203,10 @@ class VitB32Shape:
         return (self.image // self.patch) ** 2 + 1
 
 
+# the reference's default `models.clip.type: ViT-L/14` (graph.py:98-104, clip_feat_dim 768): 257 tokens, width 1024
+VIT_L14 = VitB32Shape(image=224, patch=14, width=1024, layers=24, heads=16, mlp=4096, out_dim=768)
+
+
 def make_vit_weights(shape: VitB32Shape = VitB32Shape(), seed: int = 0) -> dict:
     """Seeded N(0,0.02) weights rounded to fp16 (stored as float32 of the rounded
     values), named like open_clip's ``VisionTransformer.state_dict()``."""

@@ -1,0 +1,73 @@
+"""GPU parity for ViT shapes beyond ViT-B/32: the any-T online-softmax attention kernel and the
+generic (patch 14) im2col, i.e. the reference's default encoder ViT-L/14 (graph.py:98-104,
+clip_feat_dim 768, 257 tokens) vs the fp32 torch oracle (A9)."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import hmsg_oracle as O
+from holoagent_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _load(engine, shape, seed=0):
+    sd = synth.make_vit_weights(shape, seed=seed)
+    kw = dataclasses.asdict(shape)
+    engine.encoder_load(sd, **kw)
+    return sd
+
+
+def _check(out, ref, tol=1e-3):
+    err = np.abs(out - ref).max()
+    cos = np.sum(out * ref, axis=-1)
+    print("max abs err", err, "min cos", cos.min())
+    assert err <= tol                     # contract: 1e-3 of the unit norm per component
+    assert np.all(cos > 1 - 1e-5)
+    assert np.allclose(np.linalg.norm(out, axis=-1), 1.0, atol=1e-5)
+
+
+def test_flash_attention_agrees_on_vit_b32(engine):
+    """attn_variant 5 forces the any-T kernel on the 50-token model: same result as the T<=64 kernel."""
+    sd = _load(engine, synth.VitB32Shape())
+    x = torch.randn(70, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    base = engine.encode_images(x.numpy())
+    engine.set_option("attn_variant", 5)
+    try:
+        alt = engine.encode_images(x.numpy())
+    finally:
+        engine.set_option("attn_variant", 0)
+    assert np.abs(alt - base).max() < 2e-4
+    _check(alt[:4], O.get_img_feats_batch_tensor(sd, x[:4]))
+
+
+@pytest.mark.parametrize("patch,B", [(14, 3), (14, 37), (16, 5), (28, 4)])
+def test_small_long_sequence_vit(engine, patch, B):
+    """2-layer towers with 257 / 197 / 65 tokens (ragged last key block, ragged last query tile)."""
+    shape = synth.VitB32Shape(image=224, patch=patch, width=256, layers=2, heads=4, mlp=1024, out_dim=256)
+    sd = _load(engine, shape, seed=patch)
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(B)) * 1.2
+    ref = O.get_img_feats_batch_tensor(sd, x, heads=shape.heads)
+    _check(engine.encode_images(x.numpy()), ref)
+    # device-resident input takes the same path
+    assert np.array_equal(engine.encode_images(x.cuda()).cpu().numpy(), engine.encode_images(x.numpy()))
+
+
+def test_vit_l14_full_size(engine):
+    """The reference's default encoder at full size (24 layers, width 1024, 16 heads, d = 768)."""
+    sd = _load(engine, synth.VIT_L14, seed=3)
+    x = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(9)) * 1.2
+    ref = O.get_img_feats_batch_tensor(sd, x, heads=16)
+    out = engine.encode_images(x.numpy())
+    assert out.shape == (2, 768)
+    _check(out, ref)
+
+
+def test_encoder_load_rejects_unsupported_shapes(engine):
+    sd = synth.make_vit_weights(synth.VitB32Shape(width=256, layers=1, heads=4, mlp=1024, out_dim=256))
+    with pytest.raises(RuntimeError):      # head dim must be 64
+        engine.encoder_load(sd, image=224, patch=32, width=256, layers=1, heads=8, mlp=1024, out_dim=256)
+    with pytest.raises(RuntimeError):      # image not a multiple of the patch
+        engine.encoder_load(sd, image=230, patch=32, width=256, layers=1, heads=4, mlp=1024, out_dim=256)
