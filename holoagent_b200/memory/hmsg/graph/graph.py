@@ -2,7 +2,11 @@
 (:262-491: node table, node features, 3-D mask merging into objects, per-object features) and the
 retrieval cores ``query_hmsg_object`` (:3056-3162), ``query_object``
 (:3363-3481), ``query_graph`` (:2189-2214), ``identify_object`` (:1441-1454),
-``query_hmsg_room`` (:3164-3272) and ``query_room`` (:3277-3359), all on libhmsg_b200.so.
+``query_hmsg_room`` (:3164-3272), ``query_room`` (:3277-3359), the slow-path global view retrieval
+(:2864-2897, ``query_views``) and the re-match inside the chosen view (:2977-2984,
+``rematch_in_view``), all on libhmsg_b200.so.  The per-frame global embedding ``F_g`` the build computes
+anyway is kept in ``self.frame_global_feats`` so that room building (graph.py:1119-1136, which
+re-encodes every kept frame once per floor - SURVEY A9b) can reuse it instead of a third encoder pass.
 
 Outside the hot path (and therefore injected by the caller instead of re-implemented):
 SAM (``mask_generator.generate``), the CLIP text tower (``clip_model.text_encoder`` or
@@ -51,6 +55,7 @@ class Graph:
         self.mask_pcds = []
         self.frames_feats = []
         self.frames_pcd = []
+        self.frame_global_feats = {}     # frame id -> F_g [d] (== get_img_feats(full frame), graph.py:1125-1129)
         self.objects = []
         self.rooms = []
         self.floors = []
@@ -104,7 +109,7 @@ class Graph:
             raise NotImplementedError("pipeline.merge_type=%r: only the reference's default 'sequential' merge is on the device" % (merge_type,))
         max_mask_distance = float(g("max_mask_distance", float("inf")))
         eng.objects_begin(float(g("init_overlap_thresh", 0.75)), float(p.voxel_size), float(g("iou_thresh", 0.05)))   # seq_merge args, graph.py:437-442
-        self.frames_pcd, self.frames_feats = [], []
+        self.frames_pcd, self.frames_feats, self.frame_global_feats = [], [], {}
         dev = f"cuda:{eng.device}"
         for b0 in range(0, len(ids), self.frame_batch):
             chunk = ids[b0:b0 + self.frame_batch]
@@ -128,7 +133,9 @@ class Graph:
                                   Fp_out=torch.empty((n, M, d), dtype=torch.float32, device=dev))
             eng.torch_wait()
             Fp = Fp.cpu()
+            Fg = feats.view(n, 2 * M + 1, d)[:, 2 * M].cpu().numpy()
             for k, ms in enumerate(all_masks):
+                self.frame_global_feats[chunk[k]] = Fg[k]
                 self.frames_feats.append(Fp[k, :len(ms)])
                 if self.keep_frames_pcd:
                     off, mx, mc, _ = eng.mask_nodes(b0 + k, float(p.voxel_size), M)
@@ -285,6 +292,46 @@ class Graph:
         order = sorted(range(len(rooms_list)), key=lambda r: room_max[r], reverse=True)
         out = [int(str(rooms_list[r].room_id).split("_")[-1]) for r in order]                             # :3262-3267
         return out[:min(len(out), 5 if is_room_text_valid else 10)]
+
+    # graph.py:2864-2897 (slow path: the goal view over ALL rooms' view embeddings)
+    def query_views(self, query, rooms_list=None, top_k: int = 24, query_feats=None):
+        """-> (best_image_id, top_image_ids, top_scores): `sims = dot(query_feats[0], stack(clip_embeddings).T)`,
+        `argmax`, `argsort(sims)[-top_k:][::-1]` with `top_k = min(24, len(sims))`; image ids come from
+        `room.sample_images` (asserted to align with `room.clip_embeddings`, :2870-2871)."""
+        rooms_list = self.rooms if rooms_list is None else rooms_list
+        q = self._text([query], query_feats)
+        ids, embs = [], []
+        for room in rooms_list:
+            assert len(room.sample_images) == len(room.clip_embeddings), \
+                f"Number of images ({len(room.sample_images)}) != embeddings ({len(room.clip_embeddings)})"
+            ids.extend(room.sample_images)
+            embs.extend(room.clip_embeddings)
+        if not embs:
+            return None, [], []
+        eng = self._set_index(("views", len(embs), id(rooms_list)), np.stack(embs))
+        k = min(top_k, len(embs))
+        top, sc = eng.query_topk(q[:1], k)
+        return ids[int(top[0][0])], [ids[int(i)] for i in top[0]], [float(v) for v in sc[0]]
+
+    # graph.py:2977-2984 (slow path: best object among those visible in the chosen view)
+    def rematch_in_view(self, query, object_ids_in_view, query_feats=None):
+        """-> (object_id, score) = argmax / max of dot(query_feats[0], embeddings of the view's objects)."""
+        q = self._text([query], query_feats)
+        by_id = {o.object_id: o for o in self.objects}
+        objs = [by_id[i] for i in object_ids_in_view]
+        if not objs:
+            return None, None
+        eng = self._set_index(("inview", tuple(object_ids_in_view)), [o.embedding for o in objs])
+        top, sc = eng.query_topk(q[:1], 1)
+        return objs[int(top[0][0])].object_id, float(sc[0][0])
+
+    # graph.py:2238-2251 (clip branch; floors are few: the text embeddings of "floor i" are injected)
+    def query_floor(self, query, floor_name_feats, query_feats=None, zero_level_order_ids=None):
+        q = self._text([query], query_feats)
+        eng = self._set_index(("floors", id(floor_name_feats)), floor_name_feats)
+        top, _ = eng.query_topk(q[:1], 1)
+        i = int(top[0][0])
+        return zero_level_order_ids[i] if zero_level_order_ids is not None else i
 
     # graph.py:3277-3359 (view-embedding branch: per-room max, top 3)
     def query_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):

@@ -138,3 +138,39 @@ def test_query_graph_loaded_from_reference_json(engine, tmp_path):
     top, osc = O.query_topk(q[0], E, 3)
     assert ids == [int(t) for t in top] and np.allclose(scores, osc, rtol=1e-5, atol=1e-4)
     assert rooms == [keep[int(t)] % 2 for t in top]
+
+
+def test_view_and_room_retrieval_variants(engine, tmp_path):
+    """Appendix A sites served from a reference-schema graph: global view top-24 (graph.py:2864-2897), re-match inside
+    a view (:2977-2984), per-room max over view embeddings (:3250-3272, :3345-3359), floor by name (:2248-2251)."""
+    import json, os
+    from holoagent_b200.memory.hmsg.graph.graph import Graph
+    from tests.test_store import _write_graph
+    embs = _write_graph(str(tmp_path), d=512)
+    g = Graph({"pipeline": {}}, engine=engine, clip_feat_dim=512).load_hmsg_graph(str(tmp_path))
+    rs = np.random.RandomState(3)
+    q = rs.randn(1, 512).astype(np.float32) * 0.05
+    # global view retrieval: numpy restatement of the reference lines
+    ids, em = [], []
+    for r in g.rooms:
+        ids.extend(r.sample_images); em.extend(r.clip_embeddings)
+    sims = np.dot(q[0], np.stack(em).astype(np.float32).T)
+    top_k = min(24, sims.shape[0])
+    top_idx = np.argsort(sims)[-top_k:][::-1]
+    best, top_ids, sc = g.query_views("x", query_feats=q)
+    assert best == ids[int(np.argmax(sims))] and top_ids == [ids[i] for i in top_idx]
+    assert np.allclose(sc, sims[top_idx], rtol=1e-5, atol=1e-5)
+    # re-match inside a view
+    in_view = ["0_0_2", "0_1_3", "0_0_6"]
+    e = np.stack([o.embedding for o in g.objects if o.object_id in in_view]).astype(np.float32)
+    oid, s = g.rematch_in_view("x", in_view, query_feats=q)
+    ref = np.dot(q[0], e.T)
+    assert oid == in_view[int(np.argmax(ref))] and abs(s - ref.max()) < 1e-5
+    # rooms by view embedding
+    room_max = [np.dot(q[0], np.stack(r.embeddings).astype(np.float32).T).max() for r in g.rooms]
+    order = sorted(range(len(g.rooms)), key=lambda r: room_max[r], reverse=True)
+    assert g.query_hmsg_room("kitchen", query_feats=q) == order[:5]
+    assert g.query_room("kitchen", query_feats=q) == order[:3]
+    # floor by name
+    fl = rs.randn(3, 512).astype(np.float32)
+    assert g.query_floor("x", fl, query_feats=q) == int(np.argsort(np.dot(q, fl.T)[0])[::-1][0])

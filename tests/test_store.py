@@ -19,7 +19,7 @@ def _write_graph(root, d=128):
     for r in range(2):
         md = {"room_id": f"0_{r}", "name": f"room{r}", "floor_id": "0", "objects": [f"0_{r}_{i}" for i in range(7) if i % 2 == r], "views": [],
               "vertices": rs.rand(8, 3).tolist(), "room_height": 2.5, "room_zero_level": 0.0, "embeddings": rs.randn(3, d).tolist(),
-              "represent_images": [], "sample_images": [], "clip_embeddings": rs.randn(5, d).tolist()}
+              "represent_images": [], "sample_images": [100 * r + i for i in range(5)], "clip_embeddings": rs.randn(5, d).tolist()}
         json.dump(md, open(os.path.join(root, "rooms", md["room_id"] + ".json"), "w"))
     json.dump({"floor_id": "0", "name": "floor_0", "rooms": ["0_0", "0_1"], "vertices": [], "floor_height": 3.0, "floor_zero_level": 0.0},
               open(os.path.join(root, "floors", "0.json"), "w"))
