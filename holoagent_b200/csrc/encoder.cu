@@ -988,7 +988,7 @@ __global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __h
 // NBUF = 1 trades the prefetch for twice as many resident warps.
 template <int ATT3_GROUPS, int NBUF>
 __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
-                                                                       int W, float scale) {
+                                                                       int W, float scale, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   // two warps share one (image, head) tile: 8 warps per SM (2 per scheduler) hide ldmatrix / HMMA latency,
   // and each warp handles every other 16-row query tile
@@ -1020,7 +1020,7 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
   }
   int cur = 0;
   const int g = lane >> 2, t = lane & 3;
-  const int m_tiles = (T + 15) / 16;
+  const int m_tiles = min((T + 15) / 16, q_tiles);   // q_tiles = 1: class-token query only (last layer)
   for (long long pair = gw; pair < npairs; pair += tw) {
     if (NBUF == 2) {
       if (pair + tw < npairs) issue(pair + tw, cur ^ 1);
@@ -1124,7 +1124,7 @@ constexpr int ATTF_WARPS = 6;
 static inline int attf_smem_bytes(int Tp) { return (2 * Tp + ATTF_WARPS * 16) * ATT_LD * 2; }
 
 __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
-                                                                    int W, float scale, int Tp) {
+                                                                    int W, float scale, int Tp, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   __half* sK = reinterpret_cast<__half*>(att_smem);
   __half* sV = sK + (size_t)Tp * ATT_LD;
@@ -1150,7 +1150,7 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __hal
   cp_async_wait<0>();
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;
-  const int m_tiles = (T + 15) / 16;
+  const int m_tiles = min((T + 15) / 16, q_tiles);
   for (int mi = warp; mi < m_tiles; mi += ATTF_WARPS) {
     // stage this warp's 16 query rows
     __syncwarp();
@@ -1323,6 +1323,7 @@ struct VitState {
   bool attn_v2 = false;
   bool attn_v3_db = false;   // v3 with 4 double-buffered tiles per SM instead of 8 single-buffered ones
   bool attn_flash = false;   // force the any-T kernel (always used when T > 64)
+  bool last_cls_only = true; // last layer: only the class-token row feeds ln_post/proj, so only that row is computed past K/V
   int flash_smem_set = 0;
   bool smem_attr_set = false;
 };
@@ -1387,6 +1388,11 @@ static int32_t launch_gemm2_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtens
 static int g_gemm_2sm = -1;
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
+  if (!strcmp(key, "last_layer_cls_only")) {
+    if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(last_layer_cls_only): load the encoder first");
+    ctx->vit->last_cls_only = value != 0;
+    return HMSG_OK;
+  }
   if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2, 4: v3 double buffered, 5: any-T online-softmax kernel
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
     ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->attn_flash = value == 5; ctx->vit->smem_attr_set = false;
@@ -1397,13 +1403,13 @@ int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
 
 // C = A[M,K] * Wt[N,K]^T with epilogue
 static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const __half* Wt, int M, int N, int K, const float* bias, void* out,
-                    int ldo) {
+                    int ldo, long long lda = 0) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
   CUtensorMap ta, tb, to;
   int32_t rc;
   if (g_gemm_2sm < 0) { const char* e = getenv("HMSG_GEMM_2SM"); g_gemm_2sm = e ? atoi(e) : 1; }   // default: 2-CTA pairs
   const bool two_sm = g_gemm_2sm != 0 && M > 128;
-  if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM))) return rc;
+  if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM, 2, (uint64_t)lda))) return rc;
   if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, two_sm ? 128 : BN))) return rc;
   const bool f16out = (epi == EPI_F16_BIAS || epi == EPI_F16_BIAS_GELU);
   if ((rc = make_tmap(ctx, vs, &to, out, (uint64_t)M, (uint64_t)N, BM, f16out ? 2 : 4, (uint64_t)ldo))) return rc;
@@ -1571,7 +1577,17 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln1_g, L.ln1_b, vs->h, R, 1);
     ctx->prof_end(PROF_ELTWISE, (double)R * W * 6);
     HMSG_LAUNCH_CHECK();
-    if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
+    // The tower's output is ln_post(x[:, 0]) @ proj: in the last block only the class-token row of every image is
+    // consumed.  K and V are still needed for all tokens; Q, attention, out-proj, ln_2 and the MLP run on that row
+    // alone (strided TMA views pick row b*T of h / x in place).  Same values as the full computation.
+    const bool cls_only = vs->last_cls_only && l == d.layers - 1 && T > 1 && !vs->attn_simple && !vs->attn_v1 && !vs->attn_v2;
+    const int q_tiles = cls_only ? 1 : (1 << 30);
+    if (!cls_only) {
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
+    } else {
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv + (size_t)W * W, (int)R, 2 * W, W, L.bqkv + W, vs->qkv + W, 3 * W))) return rc;
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, B, W, W, L.bqkv, vs->qkv, T * 3 * W, (long long)T * W))) return rc;
+    }
     ctx->prof_begin(PROF_ATTN);
     if (T > 64 || vs->attn_flash) {
       const int Tp = (T + 15) / 16 * 16;
@@ -1580,7 +1596,7 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_flash, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         vs->flash_smem_set = sm;
       }
-      k_attention_flash<<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp);
+      k_attention_flash<<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp, q_tiles);
     } else if (vs->attn_simple) {
       k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     } else if (vs->attn_v1) {
@@ -1609,14 +1625,24 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
       long long pairs = (long long)B * d.heads;
       if (vs->attn_v3_db) {
         int grid = (int)std::min<long long>((pairs + 3) / 4, ctx->sm_count);
-        k_attention_mma3<4, 2><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+        k_attention_mma3<4, 2><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       } else {
         int grid = (int)std::min<long long>((pairs + 7) / 8, ctx->sm_count);
-        k_attention_mma3<8, 1><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
+        k_attention_mma3<8, 1><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       }
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();
+    if (cls_only) {
+      if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->h, L.wo, B, W, W, L.bo, vs->x, T * W, (long long)T * W))) return rc;
+      ctx->prof_begin(PROF_ELTWISE);
+      k_layernorm_f16<NV><<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln2_g, L.ln2_b, vs->pooled, B, T);
+      ctx->prof_end(PROF_ELTWISE, (double)B * W * 6);
+      HMSG_LAUNCH_CHECK();
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS_GELU, vs->pooled, L.wfc, B, d.mlp, W, L.bfc, vs->gbuf, d.mlp))) return rc;
+      if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->gbuf, L.wproj, B, W, d.mlp, L.bproj, vs->x, T * W))) return rc;
+      continue;
+    }
     if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->h, L.wo, (int)R, W, W, L.bo, vs->x, W))) return rc;
     ctx->prof_begin(PROF_ELTWISE);
     k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln2_g, L.ln2_b, vs->h, R, 1);

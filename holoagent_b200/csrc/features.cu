@@ -455,6 +455,21 @@ static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfe
   return HMSG_OK;
 }
 
+// winner tags are (epoch << 32 | pixel): the buffer is cleared only when it is (re)allocated - cudaMalloc hands back
+// recycled memory whose stale bits would otherwise beat or alias the live epoch - and when the epoch wraps.
+static int32_t win_next_epoch(hmsg_ctx* ctx, int64_t n) {
+  const unsigned long long* before = ctx->win;
+  const size_t before_bytes = ctx->win_bytes;
+  int32_t rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)n * std::max<int64_t>(ctx->n_nodes, 1) * 8);
+  if (rc) return rc;
+  if (ctx->win != before || ctx->win_bytes != before_bytes || ctx->epoch == 0 || ctx->epoch == 0xFFFFFFFFu) {
+    HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream));
+    if (ctx->epoch == 0xFFFFFFFFu) ctx->epoch = 0;
+  }
+  ctx->epoch++;
+  return HMSG_OK;
+}
+
 extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const float* feats, float maskedd_weight,
                                      float* F_p_out, int32_t on_device) {
   if (!ctx) return HMSG_ERR_ARG;
@@ -464,12 +479,7 @@ extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t
   if (!feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_fuse_scatter: null feats");
   int d = ctx->d;
   int32_t rc;
-  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
-  if (ctx->epoch == 0 || ctx->epoch == 0xFFFFFFFFu) {   // first use / wrap: clear tags
-    HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream));
-    ctx->epoch = 0;
-  }
-  ctx->epoch++;
+  if ((rc = win_next_epoch(ctx, n))) return rc;
   if ((rc = ctx->reserve(&ctx->Fp, &ctx->Fp_bytes, (size_t)n * M * d * 4))) return rc;
   const float* dfeats = feats;
   size_t fbytes = (size_t)n * (2 * M + 1) * d * 4;
@@ -551,9 +561,7 @@ int32_t features_ensure_pix_idx(hmsg_ctx* ctx) {
   if (ctx->batch_begin < 0) return ctx->fail(HMSG_ERR_STATE, "no mask batch (hmsg_masks_*)");
   if (ctx->pix_idx_for == ctx->batch_begin) return HMSG_OK;
   int32_t rc;
-  if ((rc = ctx->reserve(&ctx->win, &ctx->win_bytes, (size_t)ctx->batch_n * std::max<int64_t>(ctx->n_nodes, 1) * 8))) return rc;
-  if (ctx->epoch == 0 || ctx->epoch == 0xFFFFFFFFu) { HMSG_CUDA(cudaMemsetAsync(ctx->win, 0, ctx->win_bytes, ctx->stream)); ctx->epoch = 0; }
-  ctx->epoch++;
+  if ((rc = win_next_epoch(ctx, ctx->batch_n))) return rc;
   if ((rc = geometry_nn_winner(ctx, ctx->batch_begin, ctx->batch_n))) return rc;
   ctx->pix_idx_for = ctx->batch_begin;
   return HMSG_OK;

@@ -71,3 +71,19 @@ def test_encoder_load_rejects_unsupported_shapes(engine):
         engine.encoder_load(sd, image=224, patch=32, width=256, layers=1, heads=8, mlp=1024, out_dim=256)
     with pytest.raises(RuntimeError):      # image not a multiple of the patch
         engine.encoder_load(sd, image=230, patch=32, width=256, layers=1, heads=4, mlp=1024, out_dim=256)
+
+
+@pytest.mark.parametrize("shape,B", [(synth.VitB32Shape(), 70), (synth.VitB32Shape(), 300),
+                                     (synth.VitB32Shape(image=224, patch=14, width=256, layers=2, heads=4, mlp=1024, out_dim=256), 9)])
+def test_last_layer_class_token_pruning_is_exact(engine, shape, B):
+    """The last block computes Q / attention / out-proj / MLP for the class-token row only (the only row
+    ln_post + proj consume).  Switching the pruning off must give the same embeddings bit for bit."""
+    _load(engine, shape)
+    x = torch.randn(B, 3, 224, 224, generator=torch.Generator().manual_seed(21))
+    pruned = engine.encode_images(x.numpy())
+    engine.set_option("last_layer_cls_only", 0)
+    try:
+        full = engine.encode_images(x.numpy())
+    finally:
+        engine.set_option("last_layer_cls_only", 1)
+    assert np.array_equal(pruned, full)
