@@ -96,11 +96,13 @@ extern "C" int32_t hmsg_prof_read(hmsg_ctx* ctx, int32_t cls, double* ms, int64_
 
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value);
 int32_t knn_set_option(hmsg_ctx* ctx, const char* key, int value);
+int32_t crops_set_option(hmsg_ctx* ctx, const char* key, int value);
 
 extern "C" int32_t hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value) {
   if (!ctx || !key) return HMSG_ERR_ARG;
   int32_t rc = vit_set_option(ctx, key, value);
   if (rc == -1) rc = knn_set_option(ctx, key, value);
+  if (rc == -1) rc = crops_set_option(ctx, key, value);
   if (rc == -1) return ctx->fail(HMSG_ERR_ARG, std::string("hmsg_set_option: unknown key ") + key);
   return rc;
 }

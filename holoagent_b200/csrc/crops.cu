@@ -15,6 +15,7 @@
 // crops (bbox + margin), the full frame (extractor.py:147-158 order).
 #include "common.cuh"
 #include <cmath>
+#include <cstring>
 #include <map>
 #include <vector>
 
@@ -27,8 +28,21 @@ struct ResampleTable {
   int* kk = nullptr;       // [out][ksize]
 };
 
+// Banded PIL pass as int8 tensor-core MMAs (m16n8k32, s32 accumulate - exact).  Eight consecutive outputs
+// of the 512 -> 224 antialiased bicubic pass read a window of <= 31 consecutive inputs, so one k=32 MMA covers a
+// tile of 8 outputs; the 22-bit fixed-point coefficients are split into three 8-bit digit planes
+// (k = d2*65536 + d1*256 + d0, d0/d1 unsigned, d2 signed) and recombined by shifting the accumulator
+// between the planes (wrap-around int32 arithmetic is exact because the true sum fits).
+struct MmaTable {
+  uint32_t* frag = nullptr;   // [28 tiles][3 planes (d2, d1, d0)][32 lanes][2] B fragments
+  int* x0 = nullptr;          // [28] window start (multiple of 4)
+};
+
 struct CropState {
   std::map<std::pair<int, int>, ResampleTable> tables;
+  MmaTable mma;
+  uint8_t* t1p = nullptr; size_t t1p_bytes = 0;      // [crops, 3, 224, 512] planar, transposed (dy fastest)
+  __half* lut_h = nullptr; float* lut_f = nullptr;   // [3][256] ToTensor + Normalize of a uint8 value
   uint32_t* t1 = nullptr; size_t t1_bytes = 0;       // [crops, rows, 224] packed rgb
   float* out = nullptr;  size_t out_bytes = 0;       // [crops, 3, 224, 224]
   int32_t* boxes = nullptr; size_t boxes_bytes = 0;
@@ -297,15 +311,266 @@ __global__ void __launch_bounds__(256) k_crop_cols_patches(const uint32_t* __res
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// tensor-core path (default): same arithmetic, the two PIL passes of the 2M mask crops as IMMA
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void imma_u8s8(int* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void imma_u8u8(int* c, const uint32_t* a, const uint32_t* b) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+// acc[i] = sum_k A[.][k] * coef[k][.] for the three digit planes b[0..5] = (d2, d1, d0) fragments
+__device__ __forceinline__ void imma_banded(int* acc, const uint32_t* a, const uint32_t* b) {
+  acc[0] = acc[1] = acc[2] = acc[3] = 0;
+  imma_u8s8(acc, a, b);
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc[i] <<= 8;
+  imma_u8u8(acc, a, b + 2);
+#pragma unroll
+  for (int i = 0; i < 4; i++) acc[i] <<= 8;
+  imma_u8u8(acc, a, b + 4);
+}
+__device__ __forceinline__ int pil_clip8(int acc) { return min(max((acc + (1 << 21)) >> 22, 0), 255); }
+
+#define PL_LD 560   // 512 + 32 zero pad (+16: row stride of 140 words keeps the 8-row A-fragment loads bank-conflict free): the last tile's 32-wide window may run past column 511 (zero coefficients there)
+
+// pass 1: cv2 bilinear to 512x512 (16 rows per block) into planar uint8 rows in shared memory, then the PIL
+// horizontal pass as banded IMMA; output T1P[crop][c][ox][dy] (dy fastest: the vertical pass reads K-contiguous bytes).
+__global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ maskbits, long long frame0,
+                                                       int H, int W, int M, int MW, const int32_t* __restrict__ boxes, int margin,
+                                                       const uint32_t* __restrict__ frag, const int* __restrict__ wx0, uint8_t* __restrict__ t1p) {
+  __shared__ short s_xofs[CROP_MID];
+  __shared__ short s_a[CROP_MID][2];
+  __shared__ __align__(16) int s_h[2][CROP_MID * 3];          // horizontally interpolated source rows (>> 4); reused as the output transpose stage
+  __shared__ __align__(16) uint8_t s_pl[3][ROWS_PER_BLOCK][PL_LD];
+  __shared__ int s_ry[ROWS_PER_BLOCK][3];
+  const int fb = blockIdx.z, ci = blockIdx.y;
+  const bool masked = ci < M;
+  const int m = masked ? ci : ci - M;
+  const int32_t* b = boxes + ((long long)fb * M + m) * 4;
+  int x = b[0], y = b[1], w = b[2], h = b[3];
+  if (!masked) {   // increase_bbox_by_margin (sam_utils.py:58-81)
+    x -= margin; y -= margin; w += 2 * margin; h += 2 * margin;
+    if (x < 0) { w += x; x = 0; }
+    if (y < 0) { h += y; y = 0; }
+  }
+  int x1 = min(x + w, W), y1 = min(y + h, H);
+  x = min(max(x, 0), W); y = min(max(y, 0), H);
+  const int cw = x1 - x, ch = y1 - y;
+  const long long crop_id = (long long)fb * (2 * M + 1) + ci;
+  uint8_t* dst = t1p + crop_id * (long long)(3 * 224 * CROP_MID);
+  const int dy0 = blockIdx.x * ROWS_PER_BLOCK;
+  if (cw <= 0 || ch <= 0) {   // empty crop: zeros (the reference's cv2.resize would raise)
+    for (int i = threadIdx.x; i < 3 * 224; i += blockDim.x) *reinterpret_cast<uint4*>(dst + (long long)i * CROP_MID + dy0) = make_uint4(0, 0, 0, 0);
+    return;
+  }
+  const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)cw));
+  const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)ch));
+  for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+    int s, a0, a1;
+    cv_coef(d, scale_x, cw, true, s, a0, a1);
+    s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
+  }
+  for (int i = threadIdx.x; i < 3 * ROWS_PER_BLOCK * 8; i += blockDim.x)   // zero the 32-byte pad of every planar row
+    *reinterpret_cast<uint32_t*>(&s_pl[0][0][0] + (i >> 3) * PL_LD + CROP_MID + (i & 7) * 4) = 0u;
+  if (threadIdx.x < ROWS_PER_BLOCK) {
+    int sy, b0, b1;
+    cv_coef(dy0 + threadIdx.x, scale_y, ch, false, sy, b0, b1);
+    s_ry[threadIdx.x][0] = sy; s_ry[threadIdx.x][1] = b0; s_ry[threadIdx.x][2] = b1;
+  }
+  __syncthreads();
+  const uint8_t* img = rgb + (frame0 + fb) * (long long)H * W * 3;
+  const uint32_t* mb = maskbits + (long long)fb * H * W * MW;
+  int tag0 = -1, tag1 = -1;   // source rows currently held in s_h[sl0], s_h[sl0^1]
+  int sl0 = 0;
+  for (int r = 0; r < ROWS_PER_BLOCK; r++) {
+    const int sy = s_ry[r][0];
+    const unsigned b0s = (unsigned)s_ry[r][1] << 16, b1s = (unsigned)s_ry[r][2] << 16;   // (b*h)>>16 == umulhi(b<<16, h)
+    const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
+    int need0 = 1, need1 = 1;
+    if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
+    else if (tag1 == r0) { sl0 ^= 1; tag0 = tag1; tag1 = -1; need0 = 0; }
+    if (need0 | need1) __syncthreads();   // the previous row's blend has finished reading the slot(s) about to be refilled
+    for (int which = 0; which < 2; which++) {
+      if (which == 0 ? !need0 : !need1) continue;
+      const int sr = which == 0 ? r0 : r1;
+      int* hb = s_h[which == 0 ? sl0 : (sl0 ^ 1)];
+      const uint8_t* srow = img + ((long long)(y + sr) * W + x) * 3;
+      const uint32_t* mrow = mb + ((long long)(y + sr) * W + x) * MW;
+      for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+        int s0 = s_xofs[d], s1 = min(s0 + 1, cw - 1);
+        int a0 = s_a[d][0], a1 = s_a[d][1];
+        if (masked) {   // crop_image: image * segmentation (sam_utils.py:159)
+          a0 *= (mrow[(long long)s0 * MW + (m >> 5)] >> (m & 31)) & 1;
+          a1 *= (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) hb[d * 3 + c] = ((int)srow[s0 * 3 + c] * a0 + (int)srow[s1 * 3 + c] * a1) >> 4;
+      }
+    }
+    tag0 = r0; tag1 = r1;
+    if (need0 | need1) __syncthreads();
+    const int* h0 = s_h[sl0];
+    const int* h1 = s_h[sl0 ^ 1];
+    for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        int v = (int)(__umulhi(b0s, (unsigned)h0[d * 3 + c]) + __umulhi(b1s, (unsigned)h1[d * 3 + c]) + 2u) >> 2;
+        s_pl[c][r][d] = (uint8_t)v;
+      }
+    }
+  }
+  __syncthreads();
+  // PIL horizontal pass 512 -> 224: 28 tiles of 8 outputs x 3 channels; A = 16 rows x 32 window bytes, B = coefficient digit planes
+  uint8_t* s_out = reinterpret_cast<uint8_t*>(&s_h[0][0]);    // [3][224][16]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  for (int item = warp; item < 28 * 3; item += 8) {
+    const int j = item / 3, c = item - j * 3;
+    const int x0 = __ldg(&wx0[j]);
+    uint32_t bf[6];
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(frag) + (j * 3 + q) * 32 + lane);
+      bf[2 * q] = v.x; bf[2 * q + 1] = v.y;
+    }
+    uint32_t a[4];
+    const uint8_t* p0 = &s_pl[c][g][x0 + 4 * t];
+    const uint8_t* p1 = &s_pl[c][g + 8][x0 + 4 * t];
+    a[0] = *reinterpret_cast<const uint32_t*>(p0);      a[1] = *reinterpret_cast<const uint32_t*>(p1);
+    a[2] = *reinterpret_cast<const uint32_t*>(p0 + 16); a[3] = *reinterpret_cast<const uint32_t*>(p1 + 16);
+    int acc[4];
+    imma_banded(acc, a, bf);
+    const int ox = j * 8 + 2 * t;
+    uint8_t* o = s_out + (c * 224 + ox) * 16;
+    o[g] = (uint8_t)pil_clip8(acc[0]);      o[16 + g] = (uint8_t)pil_clip8(acc[1]);
+    o[g + 8] = (uint8_t)pil_clip8(acc[2]);  o[16 + g + 8] = (uint8_t)pil_clip8(acc[3]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 3 * 224; i += blockDim.x)
+    *reinterpret_cast<uint4*>(dst + (long long)i * CROP_MID + dy0) = *reinterpret_cast<const uint4*>(s_out + i * 16);
+}
+
+// pass 2: PIL vertical pass 512 -> 224 as banded IMMA + ToTensor + Normalize (256-entry table per channel).
+// grid = (7 row bands of 32 output rows, 2M crops, n frames); a warp owns one 8-row output group of the band and half
+// of the 14 column tiles.  PATCHES: emit the encoder's fp16 patch matrix (P = 32, G = 7), else fp32 NCHW.
+template <bool PATCHES>
+__global__ void __launch_bounds__(256) k_crop_cols_mma(const uint8_t* __restrict__ t1p, const uint32_t* __restrict__ frag, const int* __restrict__ wy0,
+                                                       const __half* __restrict__ lut_h, const float* __restrict__ lut_f, int crops_per_frame,
+                                                       int Kpad, __half* __restrict__ a0, float* __restrict__ out) {
+  __shared__ __half s_lh[3][256];
+  __shared__ float s_lf[3][256];
+  for (int i = threadIdx.x; i < 768; i += blockDim.x) {
+    if (PATCHES) (&s_lh[0][0])[i] = lut_h[i]; else (&s_lf[0][0])[i] = lut_f[i];
+  }
+  __syncthreads();
+  const long long crop = (long long)blockIdx.z * crops_per_frame + blockIdx.y;
+  const uint8_t* src = t1p + crop * (long long)(3 * 224 * CROP_MID);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int band = blockIdx.x;                 // output rows [32*band, 32*band + 32)
+  const int grp = band * 4 + (warp & 3);       // 8-row output group (0..27)
+  const int y0 = __ldg(&wy0[grp]);
+  uint32_t bf[6];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    const uint2 v = __ldg(reinterpret_cast<const uint2*>(frag) + (grp * 3 + q) * 32 + lane);
+    bf[2 * q] = v.x; bf[2 * q + 1] = v.y;
+  }
+  const int oy = grp * 8 + 2 * t;              // this thread's output rows: oy, oy + 1
+  for (int mt = (warp >> 2) * 7; mt < (warp >> 2) * 7 + 7; mt++) {
+    const int ox = mt * 16 + g;                // this thread's output columns: ox, ox + 8
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint8_t* p0 = src + ((long long)(c * 224 + ox)) * CROP_MID + y0 + 4 * t;
+      const uint8_t* p1 = p0 + 8 * CROP_MID;
+      uint32_t a[4];
+      a[0] = __ldg(reinterpret_cast<const uint32_t*>(p0));      a[1] = __ldg(reinterpret_cast<const uint32_t*>(p1));
+      a[2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 16)); a[3] = __ldg(reinterpret_cast<const uint32_t*>(p1 + 16));
+      int acc[4];
+      imma_banded(acc, a, bf);
+      // acc[0]: (ox, oy)  acc[1]: (ox, oy+1)  acc[2]: (ox+8, oy)  acc[3]: (ox+8, oy+1)
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const int v = pil_clip8(acc[e]);
+        const int xx = ox + (e >> 1) * 8, yy = oy + (e & 1);
+        if (PATCHES) {
+          const int py = yy >> 5, iy = yy & 31, pxx = xx >> 5, ix = xx & 31;
+          a0[(crop * 49 + py * 7 + pxx) * (long long)Kpad + c * 1024 + iy * 32 + ix] = s_lh[c][v];
+        } else {
+          out[(crop * 3 + c) * (long long)(224 * 224) + yy * 224 + xx] = s_lf[c][v];
+        }
+      }
+    }
+  }
+}
+
 int32_t crops_destroy(hmsg_ctx* ctx) {
   auto it = g_crop_states.find(ctx);
   if (it == g_crop_states.end()) return HMSG_OK;
   CropState* cs = it->second;
   for (auto& kv : cs->tables) { cudaFree(kv.second.bounds); cudaFree(kv.second.kk); }
-  free_dev(cs->t1); free_dev(cs->out); free_dev(cs->boxes);
+  free_dev(cs->t1); free_dev(cs->out); free_dev(cs->boxes); free_dev(cs->t1p); free_dev(cs->lut_h); free_dev(cs->lut_f);
+  free_dev(cs->mma.frag); free_dev(cs->mma.x0);
   delete cs;
   g_crop_states.erase(it);
   return HMSG_OK;
+}
+
+// B fragments of the banded 512 -> 224 PIL pass (both directions of a mask crop use this table)
+static int32_t get_mma_table(hmsg_ctx* ctx, CropState* cs) {
+  if (cs->mma.frag) return HMSG_OK;
+  std::vector<int> bounds, kk; int ksize = 0;
+  pil_coeffs(CROP_MID, 224, bounds, kk, ksize);
+  std::vector<uint32_t> frag((size_t)28 * 3 * 32 * 2, 0u);
+  std::vector<int> x0s(28);
+  for (int j = 0; j < 28; j++) {
+    const int x0 = bounds[(8 * j) * 2] & ~3;
+    x0s[j] = x0;
+    for (int n = 0; n < 8; n++) {
+      const int ox = 8 * j + n, xmin = bounds[ox * 2], cnt = bounds[ox * 2 + 1];
+      if (xmin < x0 || xmin + cnt > x0 + 32) return ctx->fail(HMSG_ERR_STATE, "crops: PIL window of an 8-output tile exceeds 32 inputs");
+      for (int k = 0; k < 32; k++) {
+        const int idx = x0 + k - xmin;
+        const int coef = (idx >= 0 && idx < cnt) ? kk[(size_t)ox * ksize + idx] : 0;
+        if (coef >= (1 << 23) || coef < -(1 << 23)) return ctx->fail(HMSG_ERR_STATE, "crops: PIL coefficient does not fit three 8-bit digits");
+        const uint32_t dig[3] = {(uint32_t)((coef >> 16) & 255), (uint32_t)((coef >> 8) & 255), (uint32_t)(coef & 255)};   // d2 (signed), d1, d0
+        // B fragment (32x8, "col"): lane = n*4 + t holds k = 4t..4t+3 in reg 0 and k = 16+4t..16+4t+3 in reg 1
+        const int t = (k & 15) >> 2, reg = k >> 4, byte = k & 3;
+        for (int q = 0; q < 3; q++) frag[(((size_t)j * 3 + q) * 32 + (n * 4 + t)) * 2 + reg] |= dig[q] << (8 * byte);
+      }
+    }
+  }
+  // ToTensor + Normalize of every uint8 value, in the same individually rounded float32 operations as torchvision
+  const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
+  const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};
+  std::vector<float> lf(768); std::vector<__half> lh(768);
+  for (int c = 0; c < 3; c++)
+    for (int v = 0; v < 256; v++) {
+      volatile float f = (float)v / 255.0f;
+      volatile float d = f - mean[c];
+      volatile float r = d / stdv[c];
+      lf[c * 256 + v] = r; lh[c * 256 + v] = __float2half_rn(r);
+    }
+  HMSG_CUDA(cudaMalloc((void**)&cs->mma.frag, frag.size() * 4));
+  HMSG_CUDA(cudaMalloc((void**)&cs->mma.x0, 28 * 4));
+  HMSG_CUDA(cudaMalloc((void**)&cs->lut_f, 768 * 4));
+  HMSG_CUDA(cudaMalloc((void**)&cs->lut_h, 768 * 2));
+  HMSG_CUDA(cudaMemcpy(cs->mma.frag, frag.data(), frag.size() * 4, cudaMemcpyHostToDevice));
+  HMSG_CUDA(cudaMemcpy(cs->mma.x0, x0s.data(), 28 * 4, cudaMemcpyHostToDevice));
+  HMSG_CUDA(cudaMemcpy(cs->lut_f, lf.data(), 768 * 4, cudaMemcpyHostToDevice));
+  HMSG_CUDA(cudaMemcpy(cs->lut_h, lh.data(), 768 * 2, cudaMemcpyHostToDevice));
+  return HMSG_OK;
+}
+
+static int g_crops_mma = 1;   // hmsg_set_option("crops_mma", 0) selects the scalar kernels (same results)
+int32_t crops_set_option(hmsg_ctx* ctx, const char* key, int value) {
+  (void)ctx;
+  if (!strcmp(key, "crops_mma")) { g_crops_mma = value; return HMSG_OK; }
+  return -1;
 }
 
 // a0 != nullptr: emit the fp16 patch matrix (P, G, Kpad describe it) instead of fp32 NCHW crops
@@ -337,21 +602,37 @@ int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, cons
     HMSG_CUDA(cudaMemcpyAsync(cs->boxes, xywh, (size_t)n * M * 16, cudaMemcpyHostToDevice, ctx->stream));
     dbox = cs->boxes;
   }
+  // tensor-core path for the 2M mask crops (the patch-matrix form needs the ViT-B/32 geometry P = 32, G = 7)
+  const bool use_mma = g_crops_mma != 0 && (!a0 || (P == 32 && G == 7));
+  if (use_mma) {
+    if ((rc = get_mma_table(ctx, cs))) return rc;
+    if ((rc = ctx->reserve(&cs->t1p, &cs->t1p_bytes, (size_t)ncrops * 3 * 224 * CROP_MID + 64))) return rc;
+  }
   ctx->prof_begin(PROF_CROPS);
   if (tc->ksize != 11) return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: unexpected PIL kernel size for 512->224");
-  k_crop_rows<11><<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
-                                                                                       bbox_margin, tc->bounds, tc->kk, cs->t1);
+  if (use_mma)
+    k_crop_rows_mma<<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
+                                                                                         bbox_margin, cs->mma.frag, cs->mma.x0, cs->t1p);
+  else
+    k_crop_rows<11><<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
+                                                                                         bbox_margin, tc->bounds, tc->kk, cs->t1);
   HMSG_LAUNCH_CHECK();
   k_frame_rows<<<dim3(H, n), 256, 0, ctx->stream>>>(ctx->rgb, frame_begin, H, W, M, left, tw->bounds, tw->kk, tw->ksize, rows_alloc, cs->t1);
   HMSG_LAUNCH_CHECK();
   const int pb = (224 * 224 + 255) / 256;
   if (a0) {
-    k_crop_cols_patches<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, P, G, Kpad, a0);
+    if (use_mma)
+      k_crop_cols_mma<true><<<dim3(7, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1p, cs->mma.frag, cs->mma.x0, cs->lut_h, cs->lut_f, 2 * M + 1, Kpad, a0, nullptr);
+    else
+      k_crop_cols_patches<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, P, G, Kpad, a0);
     HMSG_LAUNCH_CHECK();
     k_crop_cols_patches<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, P, G, Kpad, a0);
     HMSG_LAUNCH_CHECK();
   } else {
-    k_crop_cols<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, cs->out);
+    if (use_mma)
+      k_crop_cols_mma<false><<<dim3(7, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1p, cs->mma.frag, cs->mma.x0, cs->lut_h, cs->lut_f, 2 * M + 1, 0, nullptr, cs->out);
+    else
+      k_crop_cols<<<dim3(pb, 2 * M, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, 0, tc->bounds, tc->kk, tc->ksize, 0, 2 * M + 1, cs->out);
     HMSG_LAUNCH_CHECK();
     k_crop_cols<<<dim3(pb, 1, n), 256, 0, ctx->stream>>>(cs->t1, rows_alloc, top, th->bounds, th->kk, th->ksize, 2 * M, 2 * M + 1, cs->out);
     HMSG_LAUNCH_CHECK();

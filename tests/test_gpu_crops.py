@@ -9,8 +9,16 @@ from tests.scenes import scene, load_scene
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 0], ids=["imma", "scalar"])
+def crops_mma(engine, request):
+    """both resampling back ends: int8 tensor-core banded PIL passes (default) and the scalar kernels"""
+    engine.set_option("crops_mma", request.param)
+    yield request.param
+    engine.set_option("crops_mma", 1)
+
+
 @pytest.mark.parametrize("H,W", [(240, 320), (480, 640)])
-def test_crops_bit_exact(engine, H, W):
+def test_crops_bit_exact(engine, crops_mma, H, W):
     sc = scene(n_frames=3, H=H, W=W)
     load_scene(engine, sc)
     engine.voxel_build()
@@ -38,7 +46,7 @@ def test_crops_bit_exact(engine, H, W):
         assert np.array_equal(got[f], ref), np.abs(got[f] - ref).max()
 
 
-def test_fused_crops_encoder_equals_unfused(engine):
+def test_fused_crops_encoder_equals_unfused(engine, crops_mma):
     """hmsg_encode_crops (crops -> fp16 patch matrix -> encoder) == make_crops + encode_images, bit for bit"""
     import torch
     H, W, M, n = 240, 320, 5, 3
@@ -53,5 +61,29 @@ def test_fused_crops_encoder_equals_unfused(engine):
     engine.encode_crops(0, n, M, boxes, 50, a)
     ptr = engine.make_crops(0, n, M, boxes, 50)
     engine.encode_images_ptr(ptr, B, b)
+    engine.sync()
+    assert torch.equal(a, b)
+
+
+def test_imma_and_scalar_patch_matrices_agree(engine):
+    """fused path (crops -> fp16 patch matrix -> encoder): both resampling back ends give identical embeddings"""
+    import torch
+    H, W, M, n = 480, 640, 9, 4
+    sc = scene(n_frames=4, H=H, W=W)
+    load_scene(engine, sc)
+    engine.voxel_build(); engine.radius_filter(50, 0.5)
+    engine.encoder_load(synth.make_vit_weights())
+    boxes = np.stack([synth.make_mask_boxes(int(sc["ids"][f]) + 11, H, W, M) for f in range(n)])
+    boxes[0, 0] = (0, 0, W, H)                         # whole frame as a mask (down-sampling in both directions)
+    boxes[1, 1] = (W - 3, H - 2, 3, 2)                 # tiny crop at the corner (up-sampling x170)
+    engine.masks_boxes(0, boxes)
+    B = n * (2 * M + 1)
+    a = torch.empty((B, 512), dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    engine.encode_crops(0, n, M, boxes, 50, a)
+    engine.set_option("crops_mma", 0)
+    try:
+        engine.encode_crops(0, n, M, boxes, 50, b)
+    finally:
+        engine.set_option("crops_mma", 1)
     engine.sync()
     assert torch.equal(a, b)
