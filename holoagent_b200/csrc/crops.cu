@@ -341,13 +341,15 @@ __device__ __forceinline__ int pil_clip8(int acc) { return min(max((acc + (1 << 
 
 // pass 1: cv2 bilinear to 512x512 (16 rows per block) into planar uint8 rows in shared memory, then the PIL
 // horizontal pass as banded IMMA; output T1P[crop][c][ox][dy] (dy fastest: the vertical pass reads K-contiguous bytes).
+// Bilinear stage: a thread owns two of the 512 columns - its source offsets and 11-bit x coefficients live in
+// registers, and so do the horizontally interpolated values of the two source rows the current destination row
+// blends (they are reused while the destination rows keep mapping to the same source rows, i.e. whenever the crop
+// is magnified).  No shared-memory round trip and no barrier inside the row loop.
 __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ maskbits, long long frame0,
                                                        int H, int W, int M, int MW, const int32_t* __restrict__ boxes, int margin,
                                                        const uint32_t* __restrict__ frag, const int* __restrict__ wx0, uint8_t* __restrict__ t1p) {
-  __shared__ short s_xofs[CROP_MID];
-  __shared__ short s_a[CROP_MID][2];
-  __shared__ __align__(16) int s_h[2][CROP_MID * 3];          // horizontally interpolated source rows (>> 4); reused as the output transpose stage
   __shared__ __align__(16) uint8_t s_pl[3][ROWS_PER_BLOCK][PL_LD];
+  __shared__ __align__(16) uint8_t s_out[3 * 224 * 16];
   __shared__ int s_ry[ROWS_PER_BLOCK][3];
   const int fb = blockIdx.z, ci = blockIdx.y;
   const bool masked = ci < M;
@@ -371,10 +373,13 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
   }
   const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)cw));
   const double scale_y = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)ch));
-  for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
-    int s, a0, a1;
-    cv_coef(d, scale_x, cw, true, s, a0, a1);
-    s_xofs[d] = (short)s; s_a[d][0] = (short)a0; s_a[d][1] = (short)a1;
+  int cs0[2], cs1[2], cm0[2], cm1[2], ca0[2], ca1[2];   // byte offsets (3 per pixel), mask word offsets, 11-bit coefficients
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    int sx, a0, a1;
+    cv_coef(threadIdx.x + 256 * q, scale_x, cw, true, sx, a0, a1);
+    const int sx1 = min(sx + 1, cw - 1);
+    cs0[q] = sx * 3; cs1[q] = sx1 * 3; cm0[q] = sx * MW; cm1[q] = sx1 * MW; ca0[q] = a0; ca1[q] = a1;
   }
   for (int i = threadIdx.x; i < 3 * ROWS_PER_BLOCK * 8; i += blockDim.x)   // zero the 32-byte pad of every planar row
     *reinterpret_cast<uint32_t*>(&s_pl[0][0][0] + (i >> 3) * PL_LD + CROP_MID + (i & 7) * 4) = 0u;
@@ -384,50 +389,52 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
     s_ry[threadIdx.x][0] = sy; s_ry[threadIdx.x][1] = b0; s_ry[threadIdx.x][2] = b1;
   }
   __syncthreads();
-  const uint8_t* img = rgb + (frame0 + fb) * (long long)H * W * 3;
-  const uint32_t* mb = maskbits + (long long)fb * H * W * MW;
-  int tag0 = -1, tag1 = -1;   // source rows currently held in s_h[sl0], s_h[sl0^1]
-  int sl0 = 0;
+  const uint8_t* img = rgb + ((frame0 + fb) * (long long)H * W + (long long)y * W + x) * 3;
+  const uint32_t* mb = maskbits + ((long long)fb * H * W + (long long)y * W + x) * MW + (m >> 5);
+  const int mbit = m & 31;
+  int hp[2][3], hc[2][3];     // interpolated source rows tagp (upper) / tagc (lower), already >> 4
+  int tagp = -1, tagc = -1;
+  auto load_row = [&](int sr, int (&hh)[2][3]) {
+    const uint8_t* srow = img + (long long)sr * W * 3;
+    const uint32_t* mrow = mb + (long long)sr * W * MW;
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+      int a0 = ca0[q], a1 = ca1[q];
+      if (masked) {   // crop_image: image * segmentation (sam_utils.py:159)
+        a0 *= (__ldg(mrow + cm0[q]) >> mbit) & 1;
+        a1 *= (__ldg(mrow + cm1[q]) >> mbit) & 1;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) hh[q][c] = ((int)__ldg(srow + cs0[q] + c) * a0 + (int)__ldg(srow + cs1[q] + c) * a1) >> 4;
+    }
+  };
+#pragma unroll 1
   for (int r = 0; r < ROWS_PER_BLOCK; r++) {
     const int sy = s_ry[r][0];
     const unsigned b0s = (unsigned)s_ry[r][1] << 16, b1s = (unsigned)s_ry[r][2] << 16;   // (b*h)>>16 == umulhi(b<<16, h)
     const int r0 = min(max(sy, 0), ch - 1), r1 = min(max(sy + 1, 0), ch - 1);
-    int need0 = 1, need1 = 1;
-    if (tag0 == r0 && tag1 == r1) { need0 = need1 = 0; }
-    else if (tag1 == r0) { sl0 ^= 1; tag0 = tag1; tag1 = -1; need0 = 0; }
-    if (need0 | need1) __syncthreads();   // the previous row's blend has finished reading the slot(s) about to be refilled
-    for (int which = 0; which < 2; which++) {
-      if (which == 0 ? !need0 : !need1) continue;
-      const int sr = which == 0 ? r0 : r1;
-      int* hb = s_h[which == 0 ? sl0 : (sl0 ^ 1)];
-      const uint8_t* srow = img + ((long long)(y + sr) * W + x) * 3;
-      const uint32_t* mrow = mb + ((long long)(y + sr) * W + x) * MW;
-      for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
-        int s0 = s_xofs[d], s1 = min(s0 + 1, cw - 1);
-        int a0 = s_a[d][0], a1 = s_a[d][1];
-        if (masked) {   // crop_image: image * segmentation (sam_utils.py:159)
-          a0 *= (mrow[(long long)s0 * MW + (m >> 5)] >> (m & 31)) & 1;
-          a1 *= (mrow[(long long)s1 * MW + (m >> 5)] >> (m & 31)) & 1;
-        }
+    if (tagp != r0) {
+      if (tagc == r0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) hb[d * 3 + c] = ((int)srow[s0 * 3 + c] * a0 + (int)srow[s1 * 3 + c] * a1) >> 4;
+        for (int q = 0; q < 2; q++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) hp[q][c] = hc[q][c];
+      } else {
+        load_row(r0, hp);
       }
+      tagp = r0;
     }
-    tag0 = r0; tag1 = r1;
-    if (need0 | need1) __syncthreads();
-    const int* h0 = s_h[sl0];
-    const int* h1 = s_h[sl0 ^ 1];
-    for (int d = threadIdx.x; d < CROP_MID; d += blockDim.x) {
+    if (tagc != r1) { load_row(r1, hc); tagc = r1; }
+#pragma unroll
+    for (int q = 0; q < 2; q++)
 #pragma unroll
       for (int c = 0; c < 3; c++) {
-        int v = (int)(__umulhi(b0s, (unsigned)h0[d * 3 + c]) + __umulhi(b1s, (unsigned)h1[d * 3 + c]) + 2u) >> 2;
-        s_pl[c][r][d] = (uint8_t)v;
+        const int v = (int)(__umulhi(b0s, (unsigned)hp[q][c]) + __umulhi(b1s, (unsigned)hc[q][c]) + 2u) >> 2;
+        s_pl[c][r][threadIdx.x + 256 * q] = (uint8_t)v;
       }
-    }
   }
   __syncthreads();
   // PIL horizontal pass 512 -> 224: 28 tiles of 8 outputs x 3 channels; A = 16 rows x 32 window bytes, B = coefficient digit planes
-  uint8_t* s_out = reinterpret_cast<uint8_t*>(&s_h[0][0]);    // [3][224][16]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   for (int item = warp; item < 28 * 3; item += 8) {
     const int j = item / 3, c = item - j * 3;
