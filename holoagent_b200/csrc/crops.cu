@@ -324,18 +324,19 @@ __device__ __forceinline__ void imma_u8u8(int* c, const uint32_t* a, const uint3
                : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
-// acc[i] = sum_k A[.][k] * coef[k][.] for the three digit planes b[0..5] = (d2, d1, d0) fragments
+// acc[i] = 2^21 + sum_k A[.][k] * coef[k][.] for the three digit planes b[0..5] = (d2, d1, d0) fragments
+// (the PIL rounding constant rides along in the second shift: (acc << 8) + 2^21 is one IMAD)
 __device__ __forceinline__ void imma_banded(int* acc, const uint32_t* a, const uint32_t* b) {
   acc[0] = acc[1] = acc[2] = acc[3] = 0;
   imma_u8s8(acc, a, b);
 #pragma unroll
-  for (int i = 0; i < 4; i++) acc[i] <<= 8;
+  for (int i = 0; i < 4; i++) acc[i] = (int)((unsigned)acc[i] << 8);
   imma_u8u8(acc, a, b + 2);
 #pragma unroll
-  for (int i = 0; i < 4; i++) acc[i] <<= 8;
+  for (int i = 0; i < 4; i++) acc[i] = (int)((unsigned)acc[i] * 256u + (1u << 21));
   imma_u8u8(acc, a, b + 4);
 }
-__device__ __forceinline__ int pil_clip8(int acc) { return min(max((acc + (1 << 21)) >> 22, 0), 255); }
+__device__ __forceinline__ int pil_clip8(int acc) { return min(max(acc >> 22, 0), 255); }
 
 #define PL_LD 560   // 512 + 32 zero pad (+16: row stride of 140 words keeps the 8-row A-fragment loads bank-conflict free): the last tile's 32-wide window may run past column 511 (zero coefficients there)
 
@@ -436,8 +437,9 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
   __syncthreads();
   // PIL horizontal pass 512 -> 224: 28 tiles of 8 outputs x 3 channels; A = 16 rows x 32 window bytes, B = coefficient digit planes
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  for (int item = warp; item < 28 * 3; item += 8) {
-    const int j = item / 3, c = item - j * 3;
+  // tile j -> warp (j + c) & 7 would balance 84 items as 11/10; simpler and nearly as even: each warp takes whole tiles
+  // (B fragments loaded once per tile, reused by the three channels): 28 tiles over 8 warps = 4,4,4,4,3,3,3,3
+  for (int j = warp; j < 28; j += 8) {
     const int x0 = __ldg(&wx0[j]);
     uint32_t bf[6];
 #pragma unroll
@@ -445,17 +447,19 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
       const uint2 v = __ldg(reinterpret_cast<const uint2*>(frag) + (j * 3 + q) * 32 + lane);
       bf[2 * q] = v.x; bf[2 * q + 1] = v.y;
     }
-    uint32_t a[4];
-    const uint8_t* p0 = &s_pl[c][g][x0 + 4 * t];
-    const uint8_t* p1 = &s_pl[c][g + 8][x0 + 4 * t];
-    a[0] = *reinterpret_cast<const uint32_t*>(p0);      a[1] = *reinterpret_cast<const uint32_t*>(p1);
-    a[2] = *reinterpret_cast<const uint32_t*>(p0 + 16); a[3] = *reinterpret_cast<const uint32_t*>(p1 + 16);
-    int acc[4];
-    imma_banded(acc, a, bf);
     const int ox = j * 8 + 2 * t;
-    uint8_t* o = s_out + (c * 224 + ox) * 16;
-    o[g] = (uint8_t)pil_clip8(acc[0]);      o[16 + g] = (uint8_t)pil_clip8(acc[1]);
-    o[g + 8] = (uint8_t)pil_clip8(acc[2]);  o[16 + g + 8] = (uint8_t)pil_clip8(acc[3]);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      uint32_t a[4];
+      const uint8_t* p0 = &s_pl[c][g][x0 + 4 * t];
+      a[0] = *reinterpret_cast<const uint32_t*>(p0);      a[1] = *reinterpret_cast<const uint32_t*>(p0 + 8 * PL_LD);
+      a[2] = *reinterpret_cast<const uint32_t*>(p0 + 16); a[3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * PL_LD + 16);
+      int acc[4];
+      imma_banded(acc, a, bf);
+      uint8_t* o = s_out + (c * 224 + ox) * 16 + g;
+      o[0] = (uint8_t)pil_clip8(acc[0]);  o[16] = (uint8_t)pil_clip8(acc[1]);
+      o[8] = (uint8_t)pil_clip8(acc[2]);  o[24] = (uint8_t)pil_clip8(acc[3]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 3 * 224; i += blockDim.x)
@@ -488,17 +492,28 @@ __global__ void __launch_bounds__(256) k_crop_cols_mma(const uint8_t* __restrict
     bf[2 * q] = v.x; bf[2 * q + 1] = v.y;
   }
   const int oy = grp * 8 + 2 * t;              // this thread's output rows: oy, oy + 1
-  for (int mt = (warp >> 2) * 7; mt < (warp >> 2) * 7 + 7; mt++) {
+  const int mt0 = (warp >> 2) * 7;
+  // A fragments of the next column tile are fetched while the current one is multiplied (the kernel is bound by the
+  // latency of these 4-byte gathers: 8 rows x 16 contiguous bytes per request)
+  auto load_a = [&](int mt, uint32_t (&a)[3][4]) {
+    const uint8_t* p = src + ((long long)(mt * 16 + g)) * CROP_MID + y0 + 4 * t;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      const uint8_t* p0 = p + (long long)c * 224 * CROP_MID;
+      a[c][0] = __ldg(reinterpret_cast<const uint32_t*>(p0));      a[c][1] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8 * CROP_MID));
+      a[c][2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 16)); a[c][3] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8 * CROP_MID + 16));
+    }
+  };
+  uint32_t acur[3][4], anext[3][4];
+  load_a(mt0, acur);
+#pragma unroll 1
+  for (int mt = mt0; mt < mt0 + 7; mt++) {
+    if (mt + 1 < mt0 + 7) load_a(mt + 1, anext);
     const int ox = mt * 16 + g;                // this thread's output columns: ox, ox + 8
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const uint8_t* p0 = src + ((long long)(c * 224 + ox)) * CROP_MID + y0 + 4 * t;
-      const uint8_t* p1 = p0 + 8 * CROP_MID;
-      uint32_t a[4];
-      a[0] = __ldg(reinterpret_cast<const uint32_t*>(p0));      a[1] = __ldg(reinterpret_cast<const uint32_t*>(p1));
-      a[2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 16)); a[3] = __ldg(reinterpret_cast<const uint32_t*>(p1 + 16));
       int acc[4];
-      imma_banded(acc, a, bf);
+      imma_banded(acc, acur[c], bf);
       // acc[0]: (ox, oy)  acc[1]: (ox, oy+1)  acc[2]: (ox+8, oy)  acc[3]: (ox+8, oy+1)
 #pragma unroll
       for (int e = 0; e < 4; e++) {
@@ -512,6 +527,10 @@ __global__ void __launch_bounds__(256) k_crop_cols_mma(const uint8_t* __restrict
         }
       }
     }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int e = 0; e < 4; e++) acur[c][e] = anext[c][e];
   }
 }
 

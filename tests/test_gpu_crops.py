@@ -17,7 +17,7 @@ def crops_mma(engine, request):
     engine.set_option("crops_mma", 1)
 
 
-@pytest.mark.parametrize("H,W", [(240, 320), (480, 640)])
+@pytest.mark.parametrize("H,W", [(240, 320), (480, 640), (720, 1280)])
 def test_crops_bit_exact(engine, crops_mma, H, W):
     sc = scene(n_frames=3, H=H, W=W)
     load_scene(engine, sc)
