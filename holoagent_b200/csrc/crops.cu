@@ -121,7 +121,7 @@ __device__ __forceinline__ void cv_coef(int d, double scale, int src, bool clamp
 template <int KS>
 __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ rgb, const uint32_t* __restrict__ maskbits, long long frame0,
                                                    int H, int W, int M, int MW, const int32_t* __restrict__ boxes, int margin,
-                                                   const int* __restrict__ bounds, const int* __restrict__ kk, uint32_t* __restrict__ t1) {
+                                                   const int* __restrict__ bounds, const int* __restrict__ kk, int rows_alloc, uint32_t* __restrict__ t1) {
   __shared__ short s_xofs[CROP_MID];
   __shared__ short s_a[CROP_MID][2];
   __shared__ int s_h[2][CROP_MID * 3];      // horizontally interpolated source rows, already >> 4
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_crop_rows(const uint8_t* __restrict__ r
   x = min(max(x, 0), W); y = min(max(y, 0), H);
   const int cw = x1 - x, ch = y1 - y;
   const long long crop_id = (long long)fb * (2 * M + 1) + ci;
-  uint32_t* dst = t1 + crop_id * (long long)CROP_MID * 224;
+  uint32_t* dst = t1 + crop_id * (long long)rows_alloc * 224;   // the vertical pass strides crops by rows_alloc = max(512, H)
   const int dy0 = blockIdx.x * ROWS_PER_BLOCK;
   if (cw <= 0 || ch <= 0) {   // empty crop: cv2.resize would raise in the reference; emit zeros
     for (int i = threadIdx.x; i < ROWS_PER_BLOCK * 224; i += blockDim.x) dst[(long long)dy0 * 224 + i] = 0;
@@ -341,7 +341,8 @@ __device__ __forceinline__ int pil_clip8(int acc) { return min(max(acc >> 22, 0)
 #define PL_LD 560   // 512 + 32 zero pad (+16: row stride of 140 words keeps the 8-row A-fragment loads bank-conflict free): the last tile's 32-wide window may run past column 511 (zero coefficients there)
 
 // pass 1: cv2 bilinear to 512x512 (16 rows per block) into planar uint8 rows in shared memory, then the PIL
-// horizontal pass as banded IMMA; output T1P[crop][c][ox][dy] (dy fastest: the vertical pass reads K-contiguous bytes).
+// horizontal pass as banded IMMA; output T1P[crop][c][ox / 16][dy / 4][ox % 16][dy % 4]: the vertical pass reads its A
+// fragments (4 consecutive dy of one column) as 4-byte words, 8 columns of a tile side by side in one 32-byte sector.
 // Bilinear stage: a thread owns two of the 512 columns - its source offsets and 11-bit x coefficients live in
 // registers, and so do the horizontally interpolated values of the two source rows the current destination row
 // blends (they are reused while the destination rows keep mapping to the same source rows, i.e. whenever the crop
@@ -369,7 +370,8 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
   uint8_t* dst = t1p + crop_id * (long long)(3 * 224 * CROP_MID);
   const int dy0 = blockIdx.x * ROWS_PER_BLOCK;
   if (cw <= 0 || ch <= 0) {   // empty crop: zeros (the reference's cv2.resize would raise)
-    for (int i = threadIdx.x; i < 3 * 224; i += blockDim.x) *reinterpret_cast<uint4*>(dst + (long long)i * CROP_MID + dy0) = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 3 * 14 * 16; i += blockDim.x)
+      *reinterpret_cast<uint4*>(dst + ((long long)(i >> 4) * 128 + (dy0 >> 2)) * 64 + (i & 15) * 16) = make_uint4(0, 0, 0, 0);
     return;
   }
   const double scale_x = __ddiv_rn(1.0, __ddiv_rn((double)CROP_MID, (double)cw));
@@ -456,14 +458,16 @@ __global__ void __launch_bounds__(256) k_crop_rows_mma(const uint8_t* __restrict
       a[2] = *reinterpret_cast<const uint32_t*>(p0 + 16); a[3] = *reinterpret_cast<const uint32_t*>(p0 + 8 * PL_LD + 16);
       int acc[4];
       imma_banded(acc, a, bf);
-      uint8_t* o = s_out + (c * 224 + ox) * 16 + g;
-      o[0] = (uint8_t)pil_clip8(acc[0]);  o[16] = (uint8_t)pil_clip8(acc[1]);
-      o[8] = (uint8_t)pil_clip8(acc[2]);  o[24] = (uint8_t)pil_clip8(acc[3]);
+      // stage in the T1P tile order: [c][ox / 16][row quad][ox % 16][row % 4]
+      uint8_t* o = s_out + ((c * 14 + (ox >> 4)) * 4 + (g >> 2)) * 64 + (ox & 15) * 4 + (g & 3);
+      o[0] = (uint8_t)pil_clip8(acc[0]);    o[4] = (uint8_t)pil_clip8(acc[1]);      // (row g, ox), (row g, ox + 1)
+      o[128] = (uint8_t)pil_clip8(acc[2]);  o[132] = (uint8_t)pil_clip8(acc[3]);    // rows g + 8: two row quads further
     }
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * 224; i += blockDim.x)
-    *reinterpret_cast<uint4*>(dst + (long long)i * CROP_MID + dy0) = *reinterpret_cast<const uint4*>(s_out + i * 16);
+  // 256 contiguous bytes per (channel, 16-column tile): this block's four row quads
+  for (int i = threadIdx.x; i < 3 * 14 * 16; i += blockDim.x)
+    *reinterpret_cast<uint4*>(dst + ((long long)(i >> 4) * 128 + (dy0 >> 2)) * 64 + (i & 15) * 16) = *reinterpret_cast<const uint4*>(s_out + i * 16);
 }
 
 // pass 2: PIL vertical pass 512 -> 224 as banded IMMA + ToTensor + Normalize (256-entry table per channel).
@@ -493,15 +497,14 @@ __global__ void __launch_bounds__(256) k_crop_cols_mma(const uint8_t* __restrict
   }
   const int oy = grp * 8 + 2 * t;              // this thread's output rows: oy, oy + 1
   const int mt0 = (warp >> 2) * 7;
-  // A fragments of the next column tile are fetched while the current one is multiplied (the kernel is bound by the
-  // latency of these 4-byte gathers: 8 rows x 16 contiguous bytes per request)
+  // A fragments of the next column tile are fetched while the current one is multiplied
   auto load_a = [&](int mt, uint32_t (&a)[3][4]) {
-    const uint8_t* p = src + ((long long)(mt * 16 + g)) * CROP_MID + y0 + 4 * t;
+    const uint8_t* p = src + ((long long)mt * 128 + (y0 >> 2) + t) * 64 + g * 4;
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      const uint8_t* p0 = p + (long long)c * 224 * CROP_MID;
-      a[c][0] = __ldg(reinterpret_cast<const uint32_t*>(p0));      a[c][1] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8 * CROP_MID));
-      a[c][2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 16)); a[c][3] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 8 * CROP_MID + 16));
+      const uint8_t* p0 = p + (long long)c * 14 * 128 * 64;
+      a[c][0] = __ldg(reinterpret_cast<const uint32_t*>(p0));            a[c][1] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 32));        // columns g, g + 8
+      a[c][2] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 4 * 64));   a[c][3] = __ldg(reinterpret_cast<const uint32_t*>(p0 + 4 * 64 + 32)); // dy + 16
     }
   };
   uint32_t acur[3][4], anext[3][4];
@@ -514,16 +517,19 @@ __global__ void __launch_bounds__(256) k_crop_cols_mma(const uint8_t* __restrict
     for (int c = 0; c < 3; c++) {
       int acc[4];
       imma_banded(acc, acur[c], bf);
-      // acc[0]: (ox, oy)  acc[1]: (ox, oy+1)  acc[2]: (ox+8, oy)  acc[3]: (ox+8, oy+1)
+      // acc[0]: (ox, oy)  acc[1]: (ox, oy+1)  acc[2]: (ox+8, oy)  acc[3]: (ox+8, oy+1).  Lanes g and g^1 (lane ^ 4) hold
+      // neighbouring columns: the even one ends up with the pair of row oy, the odd one with the pair of row oy+1.
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        const int v = pil_clip8(acc[e]);
-        const int xx = ox + (e >> 1) * 8, yy = oy + (e & 1);
+      for (int hx = 0; hx < 2; hx++) {
+        const int v0 = pil_clip8(acc[2 * hx]), v1 = pil_clip8(acc[2 * hx + 1]);
+        const int got = __shfl_xor_sync(0xffffffffu, (g & 1) ? v0 : v1, 4);
+        const int lo = (g & 1) ? got : v0, hi = (g & 1) ? v1 : got;      // values of columns (xx, xx + 1), xx even
+        const int xx = (ox & ~1) + hx * 8, yy = oy + (g & 1);
         if (PATCHES) {
           const int py = yy >> 5, iy = yy & 31, pxx = xx >> 5, ix = xx & 31;
-          a0[(crop * 49 + py * 7 + pxx) * (long long)Kpad + c * 1024 + iy * 32 + ix] = s_lh[c][v];
+          *reinterpret_cast<__half2*>(a0 + (crop * 49 + py * 7 + pxx) * (long long)Kpad + c * 1024 + iy * 32 + ix) = __halves2half2(s_lh[c][lo], s_lh[c][hi]);
         } else {
-          out[(crop * 3 + c) * (long long)(224 * 224) + yy * 224 + xx] = s_lf[c][v];
+          *reinterpret_cast<float2*>(out + (crop * 3 + c) * (long long)(224 * 224) + yy * 224 + xx) = make_float2(s_lf[c][lo], s_lf[c][hi]);
         }
       }
     }
@@ -632,7 +638,7 @@ int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, cons
   const bool use_mma = g_crops_mma != 0 && (!a0 || (P == 32 && G == 7));
   if (use_mma) {
     if ((rc = get_mma_table(ctx, cs))) return rc;
-    if ((rc = ctx->reserve(&cs->t1p, &cs->t1p_bytes, (size_t)ncrops * 3 * 224 * CROP_MID + 64))) return rc;
+    if ((rc = ctx->reserve(&cs->t1p, &cs->t1p_bytes, (size_t)ncrops * 3 * 224 * CROP_MID + 1024))) return rc;
   }
   ctx->prof_begin(PROF_CROPS);
   if (tc->ksize != 11) return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: unexpected PIL kernel size for 512->224");
@@ -641,7 +647,7 @@ int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, cons
                                                                                          bbox_margin, cs->mma.frag, cs->mma.x0, cs->t1p);
   else
     k_crop_rows<11><<<dim3(CROP_MID / ROWS_PER_BLOCK, 2 * M, n), 256, 0, ctx->stream>>>(ctx->rgb, ctx->maskbits, frame_begin, H, W, M, ctx->batch_MW, dbox,
-                                                                                         bbox_margin, tc->bounds, tc->kk, cs->t1);
+                                                                                         bbox_margin, tc->bounds, tc->kk, rows_alloc, cs->t1);
   HMSG_LAUNCH_CHECK();
   k_frame_rows<<<dim3(H, n), 256, 0, ctx->stream>>>(ctx->rgb, frame_begin, H, W, M, left, tw->bounds, tw->kk, tw->ksize, rows_alloc, cs->t1);
   HMSG_LAUNCH_CHECK();
