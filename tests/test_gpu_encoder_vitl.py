@@ -87,3 +87,27 @@ def test_last_layer_class_token_pruning_is_exact(engine, shape, B):
     finally:
         engine.set_option("last_layer_cls_only", 1)
     assert np.array_equal(pruned, full)
+
+
+def test_encode_crops_with_patch14_tower(engine):
+    """hmsg_encode_crops with a patch-14 tower (ViT-L/14 geometry: K = 588 padded to 640, 257 tokens) takes the
+    crops -> fp32 NCHW -> generic im2col route; it must equal make_crops + encode_images on the same crops."""
+    from tests.scenes import scene, load_scene
+    H, W, M, n = 240, 320, 5, 3
+    sc = scene(n_frames=3, H=H, W=W)
+    load_scene(engine, sc)
+    engine.voxel_build(); engine.radius_filter(50, 0.5)
+    shape = synth.VitB32Shape(image=224, patch=14, width=256, layers=2, heads=4, mlp=1024, out_dim=256)
+    sd = _load(engine, shape, seed=14)
+    boxes = np.stack([synth.make_mask_boxes(int(sc["ids"][f]) + 5, H, W, M) for f in range(n)])
+    engine.masks_boxes(0, boxes)
+    B = n * (2 * M + 1)
+    a = torch.empty((B, 256), dtype=torch.float32, device="cuda"); b = torch.empty_like(a)
+    engine.encode_crops(0, n, M, boxes, 50, a)
+    ptr = engine.make_crops(0, n, M, boxes, 50)
+    engine.encode_images_ptr(ptr, B, b)
+    engine.sync()
+    assert torch.equal(a, b)
+    crops = engine.crops_read(B)
+    ref = O.get_img_feats_batch_tensor(sd, torch.from_numpy(crops[:4]), heads=shape.heads)
+    _check(a[:4].cpu().numpy(), ref)
