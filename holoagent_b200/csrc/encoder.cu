@@ -986,7 +986,9 @@ __global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __h
 
 // GROUPS (image, head) tiles per block, 2 warps each; NBUF = 2 double-buffers the tile (prefetch while computing),
 // NBUF = 1 trades the prefetch for twice as many resident warps.
-template <int ATT3_GROUPS, int NBUF>
+// KT = number of 8-key tiles that hold valid keys (7 for the 50 tokens of ViT-B/32): score MMAs, softmax terms and
+// P fragments of the all-padding tile are not computed at all.
+template <int ATT3_GROUPS, int NBUF, int KT>
 __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
                                                                        int W, float scale, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
@@ -1046,32 +1048,38 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
         ldsm_x4(a, sQ + (mi * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
         for (int np = 0; np < 4; np++) {     // two key tiles per ldmatrix.x4
-          uint32_t bb[4];
-          ldsm_x4(bb, sK + ((np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
-          mma_16816(s[np * 2], a, bb);
-          mma_16816(s[np * 2 + 1], a, bb + 2);
+          if (np * 2 < KT) {
+            uint32_t bb[4];
+            ldsm_x4(bb, sK + ((np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+            mma_16816(s[np * 2], a, bb);
+            if (np * 2 + 1 < KT) mma_16816(s[np * 2 + 1], a, bb + 2);
+          }
         }
       }
+      // softmax over the raw scores: exp((s - max) * scale) = exp2(s * c - max * c), c = scale * log2(e); only the last
+      // valid tile can hold padding keys
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) {
+      for (int ni = 0; ni < KT; ni++) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          int col = ni * 8 + 2 * t + e;
-          float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
-          float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
-          s[ni][e] = v0; s[ni][2 + e] = v1;
-          mx0 = fmaxf(mx0, v0); mx1 = fmaxf(mx1, v1);
+          if (ni == KT - 1) {
+            const int col = ni * 8 + 2 * t + e;
+            if (col >= T) { s[ni][e] = -INFINITY; s[ni][2 + e] = -INFINITY; }
+          }
+          mx0 = fmaxf(mx0, s[ni][e]); mx1 = fmaxf(mx1, s[ni][2 + e]);
         }
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float cexp = scale * 1.4426950408889634f;
+      const float nm0 = -mx0 * cexp, nm1 = -mx1 * cexp;
       float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) {
+      for (int ni = 0; ni < KT; ni++) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          float p0 = __expf(s[ni][e] - mx0), p1 = __expf(s[ni][2 + e] - mx1);
+          float p0 = ex2_approx(fmaf(s[ni][e], cexp, nm0)), p1 = ex2_approx(fmaf(s[ni][2 + e], cexp, nm1));
           s[ni][e] = p0; s[ni][2 + e] = p1;
           sum0 += p0; sum1 += p1;
         }
@@ -1083,14 +1091,18 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
 #pragma unroll
       for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
 #pragma unroll
-      for (int kk = 0; kk < 4; kk++) {
+      for (int kk = 0; kk < (KT + 1) / 2; kk++) {
         uint32_t a[4];
         __half2 h0 = __floats2half2_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
         __half2 h1 = __floats2half2_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-        __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-        __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
         a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
-        a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+        if (2 * kk + 1 < KT) {
+          __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
+          __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
+          a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
+        } else {
+          a[2] = 0u; a[3] = 0u;     // the all-padding tile: P = 0
+        }
 #pragma unroll
         for (int np = 0; np < 4; np++) {     // two d-column tiles per ldmatrix.x4.trans
           uint32_t bb[4];
@@ -1618,17 +1630,21 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     } else {
       constexpr int SM3 = 4 * 2 * 3 * ATT2_TILE * 2;   // == 8 * 1 * 3 * ATT2_TILE * 2
       if (!vs->smem_attr_set) {
-        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
-        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<4, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
         vs->smem_attr_set = true;
       }
       long long pairs = (long long)B * d.heads;
       if (vs->attn_v3_db) {
         int grid = (int)std::min<long long>((pairs + 3) / 4, ctx->sm_count);
-        k_attention_mma3<4, 2><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
+        k_attention_mma3<4, 2, 8><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       } else {
         int grid = (int)std::min<long long>((pairs + 7) / 8, ctx->sm_count);
-        k_attention_mma3<8, 1><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
+        if (T > 48 && T <= 56)   // ViT-B/32: 50 tokens = 7 key tiles
+          k_attention_mma3<8, 1, 7><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
+        else
+          k_attention_mma3<8, 1, 8><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       }
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
