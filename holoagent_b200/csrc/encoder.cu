@@ -1057,13 +1057,13 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
         }
       }
       // softmax over the raw scores: exp((s - max) * scale) = exp2(s * c - max * c), c = scale * log2(e); only the last
-      // valid tile can hold padding keys
+      // valid tile can hold padding keys when KT == ceil(T / 8)
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
       for (int ni = 0; ni < KT; ni++) {
 #pragma unroll
         for (int e = 0; e < 2; e++) {
-          if (ni == KT - 1) {
+          if (KT == 8 || ni == KT - 1) {   // KT < 8 is chosen only when T > 8 (KT - 1); the generic KT = 8 checks every tile
             const int col = ni * 8 + 2 * t + e;
             if (col >= T) { s[ni][e] = -INFINITY; s[ni][2 + e] = -INFINITY; }
           }

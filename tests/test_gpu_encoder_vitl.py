@@ -43,6 +43,15 @@ def test_flash_attention_agrees_on_vit_b32(engine):
     _check(alt[:4], O.get_img_feats_batch_tensor(sd, x[:4]))
 
 
+def test_short_sequence_vit(engine):
+    """17 and 37 tokens: the T <= 64 kernel's generic path with several all-padding key tiles."""
+    for image, patch in ((128, 32), (192, 32)):
+        shape = synth.VitB32Shape(image=image, patch=patch, width=256, layers=2, heads=4, mlp=1024, out_dim=256)
+        sd = _load(engine, shape, seed=image)
+        x = torch.randn(6, 3, image, image, generator=torch.Generator().manual_seed(image)) * 1.2
+        _check(engine.encode_images(x.numpy()), O.get_img_feats_batch_tensor(sd, x, heads=shape.heads))
+
+
 @pytest.mark.parametrize("patch,B", [(14, 3), (14, 37), (16, 5), (28, 4)])
 def test_small_long_sequence_vit(engine, patch, B):
     """2-layer towers with 257 / 197 / 65 tokens (ragged last key block, ragged last query tile)."""
