@@ -65,6 +65,7 @@ SIGNATURES = {
     "hmsg_make_crops": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, C.POINTER(_vp)]),
     "hmsg_encode_crops": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _i32, _vp]),
     "hmsg_crops_read": (_i32, [_vp, _i64, _vp]),
+    "hmsg_debug_pil_mma_table": (_i32, [_vp, _vp]),
     "hmsg_scene_reset_frames": (_i32, [_vp]),
     "hmsg_node_feats_pack": (_i32, [_vp, _vp, _vp, _i64]),
     "hmsg_node_feats_merge": (_i32, [_vp, _vp, _i32, _i64]),

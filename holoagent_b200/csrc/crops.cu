@@ -552,23 +552,24 @@ int32_t crops_destroy(hmsg_ctx* ctx) {
   return HMSG_OK;
 }
 
-// B fragments of the banded 512 -> 224 PIL pass (both directions of a mask crop use this table)
-static int32_t get_mma_table(hmsg_ctx* ctx, CropState* cs) {
-  if (cs->mma.frag) return HMSG_OK;
+// B fragments of the banded 512 -> 224 PIL pass (both directions of a mask crop use this table).
+// frag [28 tiles][3 planes (d2, d1, d0)][32 lanes][2 regs], x0 [28] window starts.  Returns 0, or 1 / 2 when a tile's
+// window exceeds 32 inputs / a coefficient does not fit three 8-bit digits (never for 512 -> 224).
+static int build_mma_table(std::vector<uint32_t>& frag, std::vector<int>& x0s) {
   std::vector<int> bounds, kk; int ksize = 0;
   pil_coeffs(CROP_MID, 224, bounds, kk, ksize);
-  std::vector<uint32_t> frag((size_t)28 * 3 * 32 * 2, 0u);
-  std::vector<int> x0s(28);
+  frag.assign((size_t)28 * 3 * 32 * 2, 0u);
+  x0s.assign(28, 0);
   for (int j = 0; j < 28; j++) {
     const int x0 = bounds[(8 * j) * 2] & ~3;
     x0s[j] = x0;
     for (int n = 0; n < 8; n++) {
       const int ox = 8 * j + n, xmin = bounds[ox * 2], cnt = bounds[ox * 2 + 1];
-      if (xmin < x0 || xmin + cnt > x0 + 32) return ctx->fail(HMSG_ERR_STATE, "crops: PIL window of an 8-output tile exceeds 32 inputs");
+      if (xmin < x0 || xmin + cnt > x0 + 32) return 1;
       for (int k = 0; k < 32; k++) {
         const int idx = x0 + k - xmin;
         const int coef = (idx >= 0 && idx < cnt) ? kk[(size_t)ox * ksize + idx] : 0;
-        if (coef >= (1 << 23) || coef < -(1 << 23)) return ctx->fail(HMSG_ERR_STATE, "crops: PIL coefficient does not fit three 8-bit digits");
+        if (coef >= (1 << 23) || coef < -(1 << 23)) return 2;
         const uint32_t dig[3] = {(uint32_t)((coef >> 16) & 255), (uint32_t)((coef >> 8) & 255), (uint32_t)(coef & 255)};   // d2 (signed), d1, d0
         // B fragment (32x8, "col"): lane = n*4 + t holds k = 4t..4t+3 in reg 0 and k = 16+4t..16+4t+3 in reg 1
         const int t = (k & 15) >> 2, reg = k >> 4, byte = k & 3;
@@ -576,6 +577,25 @@ static int32_t get_mma_table(hmsg_ctx* ctx, CropState* cs) {
       }
     }
   }
+  return 0;
+}
+
+// host-only (no ctx, no GPU): the table above, for the CPU test that replays the banded MMA against real PIL
+extern "C" int32_t hmsg_debug_pil_mma_table(uint32_t* frag_out, int32_t* x0_out) {
+  if (!frag_out || !x0_out) return HMSG_ERR_ARG;
+  std::vector<uint32_t> frag; std::vector<int> x0s;
+  if (build_mma_table(frag, x0s)) return HMSG_ERR_STATE;
+  memcpy(frag_out, frag.data(), frag.size() * 4);
+  for (int j = 0; j < 28; j++) x0_out[j] = x0s[j];
+  return HMSG_OK;
+}
+
+static int32_t get_mma_table(hmsg_ctx* ctx, CropState* cs) {
+  if (cs->mma.frag) return HMSG_OK;
+  std::vector<uint32_t> frag; std::vector<int> x0s;
+  const int bad = build_mma_table(frag, x0s);
+  if (bad == 1) return ctx->fail(HMSG_ERR_STATE, "crops: PIL window of an 8-output tile exceeds 32 inputs");
+  if (bad == 2) return ctx->fail(HMSG_ERR_STATE, "crops: PIL coefficient does not fit three 8-bit digits");
   // ToTensor + Normalize of every uint8 value, in the same individually rounded float32 operations as torchvision
   const float mean[3] = {0.48145466f, 0.4578275f, 0.40821073f};
   const float stdv[3] = {0.26862954f, 0.26130258f, 0.27577711f};

@@ -197,6 +197,11 @@ int32_t hmsg_encode_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, 
                           float* feats_out);
 /* copy the first n_crops [3,224,224] float32 crops of the last hmsg_make_crops to host (tests) */
 int32_t hmsg_crops_read(hmsg_ctx* ctx, int64_t n_crops, float* host_out);
+/* host-only debug export (no ctx, no GPU): the int8 MMA coefficient fragments of PIL's antialiased
+ * bicubic 512 -> 224 pass (Resample.c precompute_coeffs / normalize_coeffs_8bpc as called by the
+ * open_clip preprocess, utils/clip_utils.py:88-89).  frag_out [28][3][32][2] uint32 = per 8-output
+ * tile the (d2, d1, d0) digit planes in m16n8k32 B-fragment order, x0_out [28] = window starts. */
+int32_t hmsg_debug_pil_mma_table(uint32_t* frag_out, int32_t* x0_out);
 
 /* ---- A11 retrieval -------------------------------------------------------------------- */
 /* object_embs = np.array([obj.embedding ...]) (graph.py:3126): E [N,d] float32, copied into
