@@ -165,21 +165,111 @@ class Graph:
 
     load_graph = load_hmsg_graph
 
-    def load_full_pcd_feats(self, path):
-        """graph.py:3832-3871: full_feats.pt -> self.full_feats_array"""
-        from holoagent_b200.memory.hmsg.graph.store import load_feats_pt
+    # ------------------------------------------------------------------ artefacts on disk (graph.py:3769-3990)
+    def save_full_pcd(self, path):
+        """graph.py:3769-3780: <path>/full_pcd.ply"""
         import os
-        self.full_feats_array = load_feats_pt(os.path.join(path, "full_feats.pt"))
-        return self.full_feats_array
+        from holoagent_b200.runtime import write_point_cloud
+        os.makedirs(path, exist_ok=True)
+        write_point_cloud(os.path.join(path, "full_pcd.ply"), self.full_pcd)
+        print("full pcd saved to disk in {}".format(path))
+        return None
+
+    def load_full_pcd(self, path):
+        """graph.py:3782-3795"""
+        import os
+        from holoagent_b200.runtime import read_point_cloud
+        if not os.path.exists(path):
+            print("full pcd not found in {}".format(path))
+            return None
+        self.full_pcd = read_point_cloud(os.path.join(path, "full_pcd.ply"))
+        print("full pcd loaded from disk with shape {}".format(np.asarray(self.full_pcd.points).shape))
+        return self.full_pcd
 
     def save_full_pcd_feats(self, path):
-        """graph.py:3797-3830: torch.save of the node feature array (and the per-mask features)"""
+        """graph.py:3797-3830: drops objects with empty clouds, then torch.save of the per-object features
+        (mask_feats.pt) and of the node feature array (full_feats.pt)."""
         import os
         import torch
         os.makedirs(path, exist_ok=True)
-        torch.save(torch.from_numpy(np.asarray(self.full_feats_array)), os.path.join(path, "full_feats.pt"))
-        if self.frames_feats:
-            torch.save([f.numpy() if hasattr(f, "numpy") else f for f in self.frames_feats], os.path.join(path, "mask_feats.pt"))
+        keep = [(pc, ft) for pc, ft in zip(self.mask_pcds, self.mask_feats) if len(pc.points) > 0]
+        self.mask_pcds = [pc for pc, _ in keep]
+        self.mask_feats = [ft for _, ft in keep]
+        if len(self.mask_feats) != 0:
+            self.mask_feats = np.array(self.mask_feats)
+            torch.save(torch.from_numpy(self.mask_feats), os.path.join(path, "mask_feats.pt"))
+        if self.full_feats_array is not None and len(self.full_feats_array) != 0:
+            torch.save(torch.from_numpy(np.asarray(self.full_feats_array)), os.path.join(path, "full_feats.pt"))
+        print("full pcd feats saved to disk in {}".format(path))
+        return None
+
+    def load_full_pcd_feats(self, path, full_feats=False, normalize=True):
+        """graph.py:3832-3871: full_feats.pt -> self.full_feats_array (full_feats=True) or mask_feats.pt ->
+        self.mask_feats, L2-normalised rows unless normalize=False."""
+        import os
+        import torch
+        if not os.path.exists(path):
+            print("full pcd feats not found in {}".format(path))
+            return None
+        name = "full_feats.pt" if full_feats else "mask_feats.pt"
+        a = torch.load(os.path.join(path, name), map_location="cpu", weights_only=False)
+        a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).float()
+        if normalize:
+            a = torch.nn.functional.normalize(a, p=2, dim=-1)
+        a = a.cpu().numpy()
+        print("full pcd feats loaded from disk with shape {}".format(a.shape))
+        if full_feats:
+            self.full_feats_array = a
+        else:
+            self.mask_feats = a
+        return a
+
+    def save_masked_pcds(self, path, state="both"):
+        """graph.py:3880-3942: remove objects with < 10 points, write objects/pcd_<i>.ply and / or the union cloud
+        masked_pcd.ply (every object painted a random colour, as the reference does - in place)."""
+        import os
+        from holoagent_b200.runtime import PointCloud, paint_uniform_color, write_point_cloud
+        self.mask_feats = list(self.mask_feats)
+        for i, pcd in reversed(list(enumerate(self.mask_pcds))):
+            if len(pcd.points) < 10:
+                self.mask_pcds.pop(i); self.mask_feats.pop(i)
+        os.makedirs(path, exist_ok=True)
+        objects_path = os.path.join(path, "objects")
+        if state in ("both", "objects"):
+            os.makedirs(objects_path, exist_ok=True)      # the reference's "objects" branch forgets to define this path
+            for i, pcd in enumerate(self.mask_pcds):
+                write_point_cloud(os.path.join(objects_path, "pcd_{}.ply".format(i)), pcd)
+        if state in ("both", "full"):
+            masked = PointCloud()
+            for pcd in self.mask_pcds:
+                paint_uniform_color(pcd, np.random.rand(3))
+                masked += PointCloud(np.asarray(pcd.points), np.asarray(pcd.colors))
+            write_point_cloud(os.path.join(path, "masked_pcd.ply"), masked)
+        print("masked pcds saved to disk in {}".format(path))
+
+    def load_masked_pcds_new(self, path):
+        """graph.py:3944-3990: objects/pcd_<i>.ply -> self.mask_pcds; features of missing files are dropped."""
+        import os
+        from holoagent_b200.runtime import read_point_cloud
+        if len(self.mask_feats) == 0:
+            print("load full pcd feats first")
+            return None
+        objects_path = os.path.join(path, "objects")
+        if not os.path.exists(objects_path):
+            print("masked pcds for objects not found in {}".format(path))
+            return None
+        self.mask_pcds, not_found = [], []
+        for i in range(len(os.listdir(objects_path))):
+            fn = os.path.join(objects_path, "pcd_{}.ply".format(i))
+            if os.path.exists(fn):
+                self.mask_pcds.append(read_point_cloud(fn))
+            else:
+                print("masked pcd {} not found in {}".format(i, path))
+                not_found.append(i)
+        not_found = [i for i in not_found if i < len(self.mask_feats)]
+        self.mask_feats = np.delete(np.asarray(self.mask_feats), not_found, axis=0)
+        print("number of masked pcds loaded from disk {}".format(len(self.mask_pcds)))
+        return self.mask_pcds
 
     # ------------------------------------------------------------------ retrieval plumbing
     def _text(self, queries: List[str], query_feats=None):
