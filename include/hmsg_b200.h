@@ -45,8 +45,13 @@ void*       hmsg_stream(hmsg_ctx* ctx);
 /* number of kernels this ctx has launched since creation (bench.py "gpu_launches") */
 int64_t     hmsg_launch_count(const hmsg_ctx* ctx);
 int32_t     hmsg_version(void);
-/* tuning / A-B switches: "gemm_2sm" (0|1: cta_group::2 GEMM), "attn_variant" (0 v2, 1 v1, 2 fp32
- * reference kernel), "knn_bq" (queries per pass, 0 = auto) */
+/* tuning / A-B switches (every setting computes the same results; tests compare them):
+ *   "gemm_2sm"            0|1  cta_group::2 GEMM (default 1)
+ *   "attn_variant"        0 two warps per (image, head) tile (default), 1 / 3 earlier kernels, 2 fp32 reference
+ *                         kernel, 4 double-buffered tiles, 5 any-T online-softmax kernel (always used for T > 64)
+ *   "last_layer_cls_only" 0|1  last transformer block computes only the class-token row past K/V (default 1)
+ *   "crops_mma"           0|1  PIL passes of the mask crops as int8 tensor-core MMAs (default 1) or scalar kernels
+ *   "knn_bq"              queries per pass, 0 = auto */
 int32_t     hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value);
 /* Per-kernel-class device timing with CUDA events on the ctx stream (bench.py roofline).
  * class: 0 gemm (work = flops), 1 attention, 2 elementwise/LN, 3 knn pass (work = bytes of E
@@ -156,6 +161,9 @@ int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t*
                         double* xyz, double* rgb, int32_t* ijk);
 
 /* ---- A9 encoder: open_clip ViT visual tower ------------------------------------------ */
+/* Supported: head dim 64 (width / heads), width / mlp / out_dim multiples of 256, image a multiple of patch,
+ * up to 4096 tokens: ViT-B-32 (graph.py:112-119, clip_feat_dim 512; values in the comments below), ViT-B-16 and the
+ * config default ViT-L/14 (graph.py:98-104: image 224, patch 14, width 1024, 24 layers, 16 heads, mlp 4096, out 768). */
 typedef struct hmsg_vit_desc {
   int32_t image;      /* 224 */
   int32_t patch;      /* 32  */
@@ -188,8 +196,9 @@ int32_t hmsg_gemm_f16_debug(hmsg_ctx* ctx, const void* A, const void* W, float* 
 int32_t hmsg_make_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
                         const int32_t* xywh, int32_t bbox_margin, int32_t on_device,
                         float** crops_dev_out);
-/* hmsg_make_crops + hmsg_encode_images fused for the ingest path: the crops are resampled straight
- * into the encoder's fp16 patch matrix (no fp32 crop tensor, no im2col pass).  feats_out is a
+/* hmsg_make_crops + hmsg_encode_images fused for the ingest path: with a patch-32 tower (ViT-B-32) the crops
+ * are resampled straight into the encoder's fp16 patch matrix (no fp32 crop tensor, no im2col pass); other
+ * towers go through the fp32 crops internally.  feats_out is a
  * DEVICE pointer [n*(2M+1), out_dim] float32 unit rows in (masked, plain, full) order per frame;
  * xywh is host or device per on_device. */
 int32_t hmsg_encode_crops(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
