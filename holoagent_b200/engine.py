@@ -487,6 +487,7 @@ class HmsgEngine:
         if not dev:
             E = np.ascontiguousarray(E, dtype=np.float32)
         self._E_keepalive = E if borrow else None
+        self._graph_index_tag = None          # whatever a Graph mirror cached in this engine is gone now
         self.index_N, self.index_d = E.shape
         if dev:
             self.wait_torch()

@@ -59,7 +59,7 @@ class Graph:
         self.objects = []
         self.rooms = []
         self.floors = []
-        self._index_key = None
+        self._index_epoch = 0
         self.frame_batch = 16
         self.keep_frames_pcd = True      # per-frame 3-D masks as host point clouds (the reference's local `frames_pcd`)
 
@@ -160,7 +160,7 @@ class Graph:
         from holoagent_b200.memory.hmsg.graph.store import load_graph_nodes
         self.floors, self.rooms, self.objects = load_graph_nodes(path)
         self.objects = [o for o in self.objects if o.embedding is not None]
-        self._index_key = None
+        self.invalidate_index()
         return self
 
     load_graph = load_hmsg_graph
@@ -278,15 +278,25 @@ class Graph:
         return np.float32(get_text_feats_multiple_templates(queries, self.clip_model, self.clip_feat_dim))
 
     def _set_index(self, key, rows):
-        """object_embs = np.array([obj.embedding ...]) (graph.py:3126) -> one HBM matrix, cached."""
-        if self._index_key != key:
+        """object_embs = np.array([obj.embedding ...]) (graph.py:3126) -> one HBM matrix, cached.  The matrix lives in the
+        engine, so the tag of what it currently holds is kept ON the engine: another Graph (or a direct index_set) using
+        the same engine invalidates it.  Call invalidate_index() after editing embeddings in place."""
+        tag = (id(self), self._index_epoch, key)
+        if getattr(self.engine, "_graph_index_tag", None) != tag:
             E = np.ascontiguousarray(np.asarray(rows, dtype=np.float32))
             d = E.shape[1]
             if d % 128:
                 raise ValueError("embedding dimension must be a multiple of 128")
             self.engine.index_set(E)
-            self._index_key = key
+            try:
+                self.engine._graph_index_tag = tag
+            except AttributeError:
+                pass
         return self.engine
+
+    def invalidate_index(self):
+        """Forget the cached device matrix (objects / rooms were edited in place)."""
+        self._index_epoch += 1
 
     # graph.py:1441-1454
     def identify_object(self, object_feat, text_feats, classes):
@@ -425,6 +435,8 @@ class Graph:
 
     # graph.py:3277-3359 (view-embedding branch: per-room max, top 3)
     def query_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
-        if query_method == "label":
+        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
+        if query_method == "label" and is_room_text_valid:      # same label branch as query_hmsg_room (:3300-3334)
             return self.query_hmsg_room(query, floor_id, "label", query_feats, room_name_feats)
-        return self.query_hmsg_room(query, floor_id, "view_embedding", query_feats)[:3]
+        # view-embedding branch, also taken for an "unknown" room text: three highest-ranking rooms (:3345-3359)
+        return self.query_hmsg_room("unknown", floor_id, "view_embedding", self._text([query], query_feats))[:3]

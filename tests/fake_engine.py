@@ -15,6 +15,7 @@ class OracleRetrievalEngine:
 
     def index_set(self, E, borrow=False):
         self.E = np.ascontiguousarray(np.asarray(E, dtype=np.float32))
+        self._graph_index_tag = None
         self.index_N, self.index_d = self.E.shape
         self.index_sets += 1
 

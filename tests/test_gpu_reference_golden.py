@@ -97,3 +97,10 @@ def test_query_object_matches_reference_run(engine):
         assert ids == [int(v) for v in z["q%d_ids" % ci]], ci
         assert rids == [int(v) for v in z["q%d_rooms" % ci]], ci
         assert np.allclose(sc, z["q%d_scores" % ci], rtol=0, atol=1e-5), ci
+
+
+def test_room_and_object_retrieval_match_reference_run(engine):
+    """query_hmsg_room / query_room / query_object / identify_object on libhmsg_b200.so == the unmodified reference's
+    outputs (tests/golden/ref_retrieval.npz)."""
+    from tests.retrieval_golden_cases import check_retrieval_against_reference_run
+    assert check_retrieval_against_reference_run(engine) >= 20

@@ -91,3 +91,31 @@ def test_room_view_floor_variants(tmp_path):
     fl = rs.randn(3, 128).astype(np.float32)
     assert g.query_floor("x", fl, query_feats=q) == int(np.argsort(np.dot(q, fl.T)[0])[::-1][0])
     assert g.query_floor("x", fl, query_feats=q, zero_level_order_ids=[7, 8, 9]) in (7, 8, 9)
+
+
+def test_room_and_object_retrieval_match_reference_run():
+    from tests.retrieval_golden_cases import check_retrieval_against_reference_run
+    assert check_retrieval_against_reference_run(OracleRetrievalEngine()) >= 20
+
+
+def test_two_graphs_sharing_one_engine_do_not_see_each_others_index():
+    rs = np.random.RandomState(5)
+    eng = OracleRetrievalEngine()
+    graphs = []
+    for n in (9, 9):                                    # same sizes: only the engine-side tag tells them apart
+        emb = rs.randn(n, 128)
+        g = Graph({"pipeline": {}}, engine=eng, clip_feat_dim=128)
+        g.objects = [NS(embedding=emb[i], object_id="o%d" % i, room_id="r0") for i in range(n)]
+        g.rooms = [NS(room_id="r0", objects=g.objects)]
+        graphs.append((g, emb))
+    q = rs.randn(1, 128).astype(np.float32)
+    for _ in range(2):
+        for g, emb in graphs:
+            ids, _, sc = g.query_hmsg_object("x", top_k=1, query_feats=q)
+            assert ids == [int(np.argmax(emb.astype(np.float32) @ q[0]))]
+    # in-place edits need an explicit invalidation
+    g, emb = graphs[0]
+    g.query_hmsg_object("x", top_k=1, query_feats=q)
+    g.objects[3].embedding = q[0] * 10.0
+    g.invalidate_index()
+    assert g.query_hmsg_object("x", top_k=1, query_feats=q)[0] == [3]
