@@ -73,3 +73,16 @@ def test_synth_is_deterministic_and_well_formed():
     m = synth.make_masks(5, d1[0], 4)
     assert all(set(x) >= {"segmentation", "bbox", "predicted_iou"} for x in m)
     assert not (m[0]["segmentation"] & (d1[0] == 0)).any()
+
+
+def test_sass_carries_the_blackwell_instructions_the_design_claims():
+    """cuobjdump -sass of the shipped library: tcgen05 MMAs (UTCHMMA, also the cta_group::2 form), TMA loads / stores /
+    reduce-add (UTMALDG / UTMASTG / UTMAREDG), TMEM loads (LDTM), the int8 IMMA of the crop resampler and the packed
+    FFMA2 of the GELU epilogue.  (PTX names never appear in SASS: /opt/skills/guides/B200_PROFILING.md.)"""
+    import collections
+    import subprocess
+    out = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    ops = collections.Counter(re.findall(r"\b(UTCHMMA(?:\.2CTA)?|UTMALDG\.2D(?:\.2CTA)?|UTMASTG\.2D|UTMAREDG\.2D\.ADD|LDTM|IMMA\.16832\.U8\.[US]8|FFMA2|HMMA\.16816\.F32)", out))
+    for need in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "UTMALDG.2D.2CTA", "UTMASTG.2D", "UTMAREDG.2D.ADD", "LDTM",
+                 "IMMA.16832.U8.S8", "IMMA.16832.U8.U8", "FFMA2", "HMMA.16816.F32"):
+        assert ops[need] > 0, (need, dict(ops))
