@@ -45,6 +45,32 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
 
 
+def usable_cores():
+    """Host threads this process may really use: the scheduler affinity mask capped by the cgroup CPU quota
+    (os.cpu_count() reports the machine; oversubscribing a quota-limited container with one thread per machine
+    core slows the CPU baseline down by an order of magnitude and would flatter the GPU/CPU ratio)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, int(float(txt[0]) / float(txt[1]) + 0.5)))
+            else:
+                q = int(txt[0])
+                if q > 0:
+                    period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                    n = min(n, max(1, int(q / period + 0.5)))
+            break
+        except (OSError, ValueError, IndexError):
+            continue
+    return max(1, n)
+
+
 class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -101,7 +127,7 @@ def cpu_reference_sample(n_frames=2, enc_images=16, knn_rows=200_000, knn_querie
     from holoagent_b200 import synth
     from oracle import hmsg_oracle as O
 
-    cores = os.cpu_count() or 1
+    cores = usable_cores()
     torch.set_num_threads(cores)
     ids = np.arange(n_frames) * 4
     depth, rgb, T, K = synth.make_frames_np(ids, H, W)
@@ -119,7 +145,7 @@ def cpu_reference_sample(n_frames=2, enc_images=16, knn_rows=200_000, knn_querie
     t0 = time.perf_counter()
     from scipy.spatial import cKDTree
     tr = cKDTree(vx)
-    cnt = tr.query_ball_point(vx, 1.0, return_length=True, workers=-1)
+    cnt = tr.query_ball_point(vx, 1.0, return_length=True, workers=cores)
     t["radius_filter"] = (time.perf_counter() - t0) / n_frames
     nodes = vx[cnt > min(1000, int(np.median(cnt)))]
     if len(nodes) < 10:
@@ -186,7 +212,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": vals[-1]["cores"], "kind": "port", "sample": vals[-1]["sample"]},
             "knn": {"queries_per_s": float(np.mean([v["knn_qps"] for v in vals]))},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit_json_line(line)
 
 
 def workload_config(args, n_gpus):
@@ -199,7 +225,28 @@ def workload_config(args, n_gpus):
 
 
 # ------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on
+    stdout at any NCCL_DEBUG level from VERSION up; a driver may run with NCCL_DEBUG=INFO to see NVLS): keep the
+    real stdout for the result line and point fd 1 at stderr for everything else."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit_json_line(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=2)
@@ -215,7 +262,6 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    os.environ["NCCL_DEBUG"] = "WARN"     # keep NCCL's version banner off stdout: rank 0 prints exactly one JSON line
     import torch
     import torch.distributed as dist
     from holoagent_b200 import synth
@@ -366,7 +412,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                 "roofline": roof, "cpu_baseline": cpu, "knn": knn}
-        print(json.dumps(line))
+        emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
