@@ -7,11 +7,15 @@ One JSON line on rank 0.  A "step" is ONE whole HMSG build of the named workload
 (BASELINE.json configs[1]: F x 640x480 RGB-D frames, M=32 masks/frame, ViT-B/32 crop encoder):
   geometry (bounds, voxel index, accumulate, radius filter) over all F frames, then per frame
   batch: masks -> 2M+1 crops -> encoder -> mask-feature fusion -> pixel->node NN + winner ->
-  node feature scatter, then finalize.  `value` = F / step time with frames resident in HBM;
-  `e2e` = the same job through the host-buffer C-ABI calls (pinned host frames -> H2D inside the
-  timed region, node features D2H).  Strong scaling for N>1: the F frames are sharded by frame
-  batch across ranks for both phases (SURVEY 8e option A: the sharded geometry pass is merged by three tiny
-  collectives), one NCCL all-gather merges the per-rank node-feature partials and mask embeddings.
+  node feature scatter -> per-mask 3-D node sets (A7, create_3d_masks: graph.py:391-402), then finalize.
+  `value` = F / step time with frames resident in HBM (`a7.without_a7_value`: the same step without A7, the
+  round-1 workload); `e2e` = the same job through the host-buffer C-ABI calls (pinned host frames -> H2D inside
+  the timed region, node features D2H).  Strong scaling for N>1: every rank owns a contiguous block of F / N
+  frames for both phases (SURVEY 8e option A: the sharded geometry pass is merged by three tiny collectives),
+  hmsg_allgather_nodes (NCCL inside libhmsg_b200.so) merges the per-rank node-feature partials.
+--config c2 (default) | c4 (1280x720, 50 k frames, BASELINE configs[3]) | c5 (20 k-frame build -> 3-D mask
+merging -> per-object features -> 1 k query_hmsg_object requests, configs[4]); --api graph drives the drop-in
+Graph.create_feature_map mirror with dense host masks instead of the IngestJob.
 """
 from __future__ import annotations
 
@@ -28,7 +32,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, M, D = 480, 640, 32, 512
+H, W, M, D = 480, 640, 32, 512      # c2 / c5; c4 switches to 1280x720 in main()
 GFLOP_PER_IMAGE = 8.82          # ViT-B/32 forward, 2 x 4.41 GMAC (every token through every block)
 # executed: in the last block only K/V are needed for all 50 tokens; Q, attention, out-proj and the MLP run on the
 # class-token row alone (the only row ln_post + proj read) - bit-identical embeddings, 0.585 GFLOP/image less
@@ -194,8 +198,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    if args.batch <= 0:
-        args.batch = 64 if args.gpus == 1 else 32
+    apply_config(args, max(1, args.gpus))
     if args.crops == "auto":
         args.crops = "device"
     vals = []
@@ -215,12 +218,36 @@ def run_reference(args):
     emit_json_line(line)
 
 
+CONFIGS = {
+    "c2": {"H": 480, "W": 640, "frames": 10000, "name": "BASELINE configs[1]"},
+    "c4": {"H": 720, "W": 1280, "frames": 50000, "name": "BASELINE configs[3]"},
+    "c5": {"H": 480, "W": 640, "frames": 20000, "name": "BASELINE configs[4]"},
+}
+
+
+def apply_config(args, world):
+    """resolve --config into the module-level frame shape and the job size"""
+    global H, W
+    c = CONFIGS[args.config]
+    H, W = c["H"], c["W"]
+    if args.frames <= 0:
+        args.frames = c["frames"]
+        # the resident frame store must fit: 5 B/pixel/frame, keep it under ~110 GB per GPU
+        cap = int(110e9 // (H * W * 5)) * world
+        if args.frames > cap:
+            args.frames = cap
+    if args.batch <= 0:
+        args.batch = 64
+
+
 def workload_config(args, n_gpus):
-    return {"workload": f"{args.frames}-frame 640x480 RGB-D HMSG build + crop encoder (BASELINE configs[1]); M={M} masks/frame, "
-                        f"{2 * M + 1} crops/frame through ViT-B/32 (d=512), voxel 0.05 m",
-            "frames": args.frames, "frame_batch": args.batch, "masks_per_frame": M, "encoder": "ViT-B/32 fp16 operands / fp32 accumulate",
-            "crops": args.crops, "l2_policy": "inputs (15 GB of frames, 2 GB kNN table) are larger than the 126 MB L2",
-            "parallelism": f"frame-batch shard x{n_gpus} (geometry + features), 3 tiny geometry collectives + 1 NCCL all-gather of node embeddings / feature partials" if n_gpus > 1 else "single GPU",
+    return {"workload": f"{args.frames}-frame {W}x{H} RGB-D HMSG build + crop encoder ({CONFIGS[args.config]['name']}); M={M} masks/frame, "
+                        f"{2 * M + 1} crops/frame through ViT-B/32 (d=512), voxel 0.05 m; step = A1-A9 incl. A7 (create_3d_masks per frame)",
+            "config": args.config, "frames": args.frames, "frame_batch": args.batch, "masks_per_frame": M,
+            "encoder": "ViT-B/32 fp16 operands / fp32 accumulate", "crops": args.crops, "api": args.api,
+            "l2_policy": "inputs (GBs of frames, 2 GB kNN table) are larger than the 126 MB L2",
+            "parallelism": (f"contiguous frame block per rank x{n_gpus} (geometry + features), 3 tiny geometry collectives + hmsg_allgather_nodes "
+                            f"(all-to-all of row slices, rank-order sum, all-gather; NCCL inside the C-ABI library)") if n_gpus > 1 else "single GPU",
             "knn": f"N={KNN_N} d={D} Q={KNN_Q} top-{KNN_K}"}
 
 
@@ -245,6 +272,34 @@ def emit_json_line(line):
     os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
 
 
+class SynthMaskGenerator:
+    """SAM stand-in for --api graph: the seeded rectangles of synth.make_masks as dense bool masks in host memory
+    (what SamAutomaticMaskGenerator.generate returns: "segmentation" [H,W] bool, "bbox" XYWH)."""
+
+    def __init__(self, depths, ids, M):
+        self.depths, self.ids, self.M, self.k = depths, ids, M, 0
+
+    def generate(self, image):
+        from holoagent_b200 import synth
+        i = self.k
+        self.k += 1
+        return synth.make_masks(int(self.ids[i]), self.depths[i], self.M)
+
+
+class ListDataset:
+    """RGBDDataset-like (generic.py:19-58): dataset[i] -> (rgb, depth, pose, rgb_intrinsics, depth_intrinsics)"""
+
+    def __init__(self, depth, rgb, poses, K, scale=1000.0):
+        self.depth, self.rgb, self.poses = depth, rgb, poses
+        self.depth_intrinsics, self.scale = K, scale
+
+    def __len__(self):
+        return len(self.depth)
+
+    def __getitem__(self, i):
+        return self.rgb[i], self.depth[i], self.poses[i], self.depth_intrinsics, self.depth_intrinsics
+
+
 def main():
     claim_stdout()
     ap = argparse.ArgumentParser()
@@ -252,12 +307,18 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--frames", type=int, default=10000)
-    ap.add_argument("--batch", type=int, default=0, help="frames per batch (0 = auto: 64 on one GPU, 32 when sharded)")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--api", default="ingest", choices=["ingest", "graph"], help="graph: drive the drop-in Graph.create_feature_map mirror")
+    ap.add_argument("--frames", type=int, default=0, help="0 = the config's frame count")
+    ap.add_argument("--batch", type=int, default=0, help="frames per batch (0 = 64)")
     ap.add_argument("--crops", default="auto", choices=["auto", "device", "synthetic"])
+    ap.add_argument("--collective", default="c", choices=["c", "torch"])
+    ap.add_argument("--queries", type=int, default=1000, help="c5: query_hmsg_object requests")
+    ap.add_argument("--merge-frames", type=int, default=0, help="c5: frames per rank fed to the 3-D mask merge (0 = all)")
     ap.add_argument("--no-knn", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-a7-ablation", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -265,12 +326,11 @@ def main():
     import torch
     import torch.distributed as dist
     from holoagent_b200 import synth
-    from holoagent_b200.engine import HmsgEngine, HmsgError
+    from holoagent_b200.engine import HmsgEngine
     from holoagent_b200 import ingest
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.batch <= 0:
-        args.batch = 64 if world == 1 else 32
+    apply_config(args, world)
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -280,39 +340,34 @@ def main():
     eng = HmsgEngine(local)
     peaks = load_peaks()
     F, FB = args.frames, args.batch
+    if args.api == "graph":
+        return run_graph_api(args, eng, dev, torch)
 
-    # ---------------- synthetic workload, generated straight into HBM ----------------
+    # ---------------- synthetic workload: this rank's contiguous frame block, generated straight into HBM ----------------
     K = synth.intrinsics(H, W)
-    eng.scene_begin(H, W, K, 1000.0, 0.05, F)
-    host_depth = host_rgb = None
+    g0, n_local = ingest.frame_block(F, world, rank)
+    eng.scene_begin(H, W, K, 1000.0, 0.05, max(n_local, 1))
     want_e2e = not args.no_e2e
-    _, my_batches = ingest.shard_batches(F, FB, world, rank)
-    n_local = sum(n for _, n in my_batches)
-    mine = np.zeros(F, dtype=bool)
-    for (b0, n) in my_batches:
-        mine[b0:b0 + n] = True
-    local_of = np.cumsum(mine) - 1          # frame id -> slot in this rank's pinned host buffers (my_batches order)
+    host_depth = host_rgb = None
     if want_e2e:
         host_depth = torch.empty((max(n_local, 1), H, W), dtype=torch.int16).pin_memory()
         host_rgb = torch.empty((max(n_local, 1), H, W, 3), dtype=torch.uint8).pin_memory()
-    poses_all = synth.poses(np.arange(F)).reshape(F, 16)
-    for f0 in range(0, F, 256):
-        ids = np.arange(f0, min(F, f0 + 256))
+    gids = np.arange(g0, g0 + n_local)
+    poses_local = synth.poses(gids).reshape(n_local, 16)
+    for f0 in range(0, n_local, 256):
+        ids = gids[f0:f0 + 256]
         d, c, T, _ = synth.make_frames(ids, H, W, device=dev)
         d16 = d.view(torch.int16)
         eng.add_frames(d16, c, torch.from_numpy(T.reshape(-1, 16)).to(dev))
         if want_e2e:
-            sel = np.nonzero(mine[ids])[0]
-            if len(sel):
-                st = torch.from_numpy(sel).to(dev)
-                slots = torch.from_numpy(local_of[ids[sel]])
-                host_depth[slots] = d16[st].cpu()
-                host_rgb[slots] = c[st].cpu()
+            host_depth[f0:f0 + len(ids)] = d16.cpu()
+            host_rgb[f0:f0 + len(ids)] = c.cpu()
         eng.sync(); torch.cuda.synchronize()
-    boxes_np = np.stack([synth.make_mask_boxes(i, H, W, M) for i in range(F)])
+    boxes_np = np.stack([synth.make_mask_boxes(int(i), H, W, M) for i in gids]) if n_local else np.zeros((0, M, 4), np.int32)
     boxes_dev = torch.from_numpy(boxes_np).to(dev)
     eng.encoder_load(synth.make_vit_weights())
-    job = ingest.IngestJob(eng, F, FB, M, D, boxes_dev, rank=rank, world=world, crops=args.crops, maskedd_weight=0.4418, bbox_margin=50)
+    job = ingest.IngestJob(eng, n_local, FB, M, D, boxes_dev, rank=rank, world=world, crops=args.crops, maskedd_weight=0.4418, bbox_margin=50,
+                           a7=True, collective=args.collective, total_frames=F)
     args.crops = job.crops_mode
 
     def barrier():
@@ -322,6 +377,7 @@ def main():
             torch.cuda.synchronize()
 
     ts = eng.torch_stream()
+    ALL = ("gemm", "attn", "eltwise", "nn", "scatter", "geom", "crops", "mask3d", "comm")
 
     def timed(fn, steps, warmup, prof=None):
         for _ in range(warmup):
@@ -349,39 +405,66 @@ def main():
         eng.prof_enable()
         return ms / steps, clocks, eng.launches - l0, pr
 
-    # ---------------- headline: frames resident in HBM ----------------
-    ms_step, clocks, launches, pr = timed(job.step_device, args.steps, args.warmup, prof=("gemm", "attn", "eltwise", "nn", "scatter", "geom", "crops"))
+    # ---------------- headline: frames resident in HBM, A1-A9 incl. A7 ----------------
+    ms_step, clocks, launches, pr = timed(job.step_device, args.steps, args.warmup, prof=ALL)
     fps = F / ms_step * 1e3
     g = pr["gemm"]
     gemm_tf = g["work"] / max(g["ms"], 1e-9) / 1e9
     traffic = {}
-    tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(tp):
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
     if os.path.exists(tp):
         traffic = json.load(open(tp))
-    roof = {"bound": "tensor", "kernel": "k_gemm_f16_2sm (tcgen05.mma cta_group::2 kind::f16 M256 N256 K16, TMA 128B-swizzle operand ring, TMEM accumulators, TMA store / reduce-add epilogue)",
+    roof = {"bound": "tensor", "kernel": "k_gemm_f16_2sm (tcgen05.mma cta_group::2 kind::f16 M256 N256 K16, TMA 128B-swizzle operand ring, TMEM accumulators, fused LayerNorm / residual / GELU epilogues)",
             "achieved": gemm_tf, "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": gemm_tf / peaks["tf_sustained"],
             "peak_source": peaks["src"] + " bf16 cuBLAS sustained (kernel timed inside a long step)",
             "traffic": traffic.get("gemm", {}).get("traffic_bytes_per_launch"), "traffic_note": traffic.get("gemm", {}).get("kernel"),
             "launches": g["launches"], "avg_launch_ms": g["ms"] / max(g["launches"], 1),
             "flops_per_launch": g["work"] / max(g["launches"], 1),
             "gemm_share_of_step": g["ms"] / (ms_step * args.steps),
-            "model_tflops_whole_step": F / world * (2 * M + 1) * GFLOP_PER_IMAGE_EXECUTED / ms_step,
+            "model_tflops_whole_step": n_local * (2 * M + 1) * GFLOP_PER_IMAGE_EXECUTED / ms_step,
+            "whole_step_frac_of_peak": n_local * (2 * M + 1) * GFLOP_PER_IMAGE_EXECUTED / ms_step / peaks["tf_sustained"],
             "gflop_per_image": {"nominal": GFLOP_PER_IMAGE, "executed": GFLOP_PER_IMAGE_EXECUTED,
                                 "note": "last block: class-token row only past K/V (dead rows not computed; embeddings bit-identical)"},
             "other_kernels_ms_per_step": {k: pr[k]["ms"] / args.steps for k in pr if k != "gemm"}}
+    a7 = {"in_step": True, "ms_per_step": pr["mask3d"]["ms"] / args.steps, "reference": "generic.py:140-190 via graph.py:391-402",
+          "store": dict(zip(("frames", "masks", "points"), eng.mask_store_count()))}
+    comm = None
+    if world > 1:
+        cm = pr["comm"]
+        _, _, last_bytes = eng.comm_info()
+        comm = {"ms_per_step": cm["ms"] / args.steps, "bytes_per_step_this_rank": cm["work"] / args.steps,
+                "achieved_GBps_this_rank": cm["work"] / max(cm["ms"], 1e-9) / 1e6, "node_merge_bytes_this_rank": last_bytes,
+                "what": "all NCCL exchanges of a step on rank 0 (bounds, occupancy bitmap, voxel accumulators, radius counts, node-embedding merge); bytes sent + received"}
+    if not args.no_a7_ablation:
+        job.a7 = False
+        ms_na, _, _, _ = timed(job.step_device, 1, 1)
+        job.a7 = True
+        a7["without_a7_value"] = F / ms_na * 1e3
+        a7["without_a7_ms_per_step"] = ms_na
 
     # ---------------- e2e: host buffers through the C-ABI ----------------
     e2e = None
     if want_e2e:
-        job.bind_host(host_depth, host_rgb, poses_all, boxes_np)
+        job.bind_host(host_depth, host_rgb, poses_local, boxes_np)
         ms_e2e, _, _, _ = timed(job.step_host, max(1, args.steps), 1)
-        e2e = {"value": F / ms_e2e * 1e3, "unit": "frames/s", "h2d_bytes_per_step": job.h2d_bytes, "d2h_bytes_per_step": job.d2h_bytes,
-               "ms_per_step": ms_e2e}
+        h2d, d2h = job.h2d_bytes, job.d2h_bytes
+        if world > 1:
+            t = torch.tensor([float(h2d), float(d2h)], device=dev, dtype=torch.float64)
+            dist.all_reduce(t)
+            h2d, d2h = int(t[0].item()), int(t[1].item())
+        e2e = {"value": F / ms_e2e * 1e3, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e,
+               "overlap": "frames cross PCIe on a copy stream (one event per batch); crops + encoder of a batch wait for that batch only"}
+
+    c5 = None
+    if args.config == "c5":
+        c5 = run_c5(args, eng, job, dev, torch, dist, world, rank, barrier)
     job.release()
 
     # ---------------- kNN: 1M x 512, 10k queries ----------------
     knn = None
-    if not args.no_knn and rank == 0 or (not args.no_knn and world > 1):
+    if not args.no_knn:
         E, Q = synth.make_knn_tables(KNN_N, KNN_Q, D, device=dev)
         torch.cuda.synchronize()
         eng.index_set(E, borrow=True)
@@ -411,11 +494,91 @@ def main():
         line = {"metric": "hmsg_rgbd_frames_per_s_ingested", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16",
                 "data": "synthetic", "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
-                "roofline": roof, "cpu_baseline": cpu, "knn": knn}
+                "roofline": roof, "cpu_baseline": cpu, "knn": knn, "a7": a7, "comm": comm}
+        if c5 is not None:
+            line["c5"] = c5
         emit_json_line(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier):
+    """BASELINE configs[4]: after the build, the FSR fast path end to end - 3-D mask merging (N1: every rank merges the
+    frames it owns sequentially, graph_utils.py:1015-1038; the per-rank object lists are then merged once more on every
+    rank, the `hierarchical` idea of graph_utils.py:989-1012 across ranks), per-object features (N2, graph.py:451-488),
+    object table -> 1 k query_hmsg_object requests with one negative prompt (graph.py:3126-3151).  Wall clock, host side."""
+    out = {}
+    nf = job.F if args.merge_frames <= 0 else min(job.F, args.merge_frames)
+    barrier(); t0 = time.perf_counter()
+    job.step_device()
+    barrier(); out["build_s"] = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    eng.objects_begin(0.75, 0.05, 0.05)
+    eng.objects_merge_stored(0, nf)
+    if world == 1:
+        n_obj, n_pts = eng.objects_finish(10)
+    else:
+        eng.objects_finish(0)                      # this rank's merged list, nothing dropped yet
+        off, xyz, rgb = eng.objects_read()
+        lists = [None] * world
+        dist.all_gather_object(lists, (off, xyz, rgb))
+        eng.objects_begin(0.75, 0.05, 0.05)
+        for (o, x, c) in lists:                    # rank order; the first list is taken as is, every further one is a merge step
+            eng.objects_add_masks(o, x, c)
+        n_obj, n_pts = eng.objects_finish(10)
+    barrier(); out["merge_s"] = time.perf_counter() - t0
+    out["merged_frames_per_rank"] = nf
+    out["objects"], out["object_points"] = int(n_obj), int(n_pts)
+    t0 = time.perf_counter()
+    full = eng.node_feats_finalize()
+    feats = eng.object_feats(full, 0.05, 0.8, 0.01, 100) if n_obj else np.zeros((0, D), np.float32)
+    barrier(); out["object_feats_s"] = time.perf_counter() - t0
+    if n_obj:
+        E = feats / np.maximum(np.linalg.norm(feats, axis=1, keepdims=True), 1e-6)
+        eng.index_set(E.astype(np.float32))
+        rs = np.random.RandomState(5)
+        Q = rs.randn(args.queries, 2, D).astype(np.float32)
+        Q /= np.linalg.norm(Q, axis=-1, keepdims=True)
+        t0 = time.perf_counter()
+        k = min(5, n_obj)
+        for i in range(0, args.queries, 1):        # one request per call, like the robot (goal_pose_publisher.py:220)
+            eng.query_object(Q[i:i + 1], 0, k)
+        out["query_s"] = time.perf_counter() - t0
+        out["queries_per_s"] = args.queries / out["query_s"] * world
+    out["total_s"] = out["build_s"] + out["merge_s"] + out["object_feats_s"] + out.get("query_s", 0.0)
+    out["build_frames_per_s"] = job.total / out["build_s"]
+    return out
+
+
+def run_graph_api(args, eng, dev, torch):
+    """--api graph: frames/s through the drop-in Graph.create_feature_map mirror - host frames, dense arbitrary-shape
+    host masks (what SAM returns), everything a user of the reference class calls (single GPU)."""
+    from holoagent_b200 import synth
+    from holoagent_b200.memory.hmsg.graph.graph import Graph
+    F = args.frames if args.frames <= 2000 else 512      # dense host masks: 9.8 MB per frame at M = 32
+    ids = np.arange(F)
+    depth, rgb, T, K = synth.make_frames_np(ids, H, W)
+    eng.encoder_load(synth.make_vit_weights())
+    cfg = {"pipeline": {"voxel_size": 0.05, "skip_frames": 1, "clip_bbox_margin": 50, "clip_masked_weight": 0.4418, "max_mask_distance": 10000.0,
+                        "merge_type": "sequential", "init_overlap_thresh": 0.75, "iou_thresh": 0.05}}
+    res = []
+    for it in range(args.warmup + args.steps):
+        g = Graph(cfg, dataset=ListDataset(depth, rgb, T, K), mask_generator=SynthMaskGenerator(depth, ids, M), engine=eng, clip_feat_dim=D)
+        g.merge_objects = False                      # the timed call is the ingest (graph.py:339-415); N1/N2 are measured by --config c5
+        eng.sync(); t0 = time.perf_counter()
+        g.create_feature_map()
+        eng.sync(); dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            res.append(dt)
+    dt = float(np.mean(res))
+    line = {"metric": "hmsg_rgbd_frames_per_s_ingested", "value": F / dt, "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+            "config": dict(workload_config(args, 1), frames=F, note="Graph.create_feature_map mirror: host frames + dense host masks [M,H,W] bool per frame "
+                           "(bit-packed on the host, 1 bit per mask pixel over PCIe), SAM stand-in generating masks inside the timed region is excluded "
+                           "from nothing: wall clock of the whole call"),
+            "e2e": {"value": F / dt, "unit": "frames/s", "h2d_bytes_per_step": None, "d2h_bytes_per_step": None}, "gpu_launches": eng.launches}
+    emit_json_line(line)
 
 
 if __name__ == "__main__":

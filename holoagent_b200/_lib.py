@@ -82,6 +82,19 @@ SIGNATURES = {
     "hmsg_objects_count": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
     "hmsg_object_feats": (_i32, [_vp, _vp, _i32, C.c_double, C.c_double, C.c_float, _i32, _vp, _i32]),
     "hmsg_node_feats_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
+    "hmsg_masks_counts": (_i32, [_vp, _i64, _i32, _vp]),
+    "hmsg_mask_nodes_batch": (_i32, [_vp, _i64, _i32, C.c_double, C.c_double, _i32]),
+    "hmsg_mask_store_reset": (_i32, [_vp]),
+    "hmsg_mask_store_count": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "hmsg_mask_store_read": (_i32, [_vp, _i64, C.POINTER(_i32), _vp, _vp, _vp, _vp]),
+    "hmsg_objects_merge_stored": (_i32, [_vp, _i64, _i64]),
+    "hmsg_comm_unique_id": (_i32, [_vp]),
+    "hmsg_comm_init": (_i32, [_vp, _vp, _i32, _i32]),
+    "hmsg_comm_attach": (_i32, [_vp, _vp]),
+    "hmsg_comm_info": (_i32, [_vp, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_f64)]),
+    "hmsg_voxel_build_sharded": (_i32, [_vp, _vp, _vp, _i32, C.POINTER(_i64), _vp]),
+    "hmsg_radius_filter_sharded": (_i32, [_vp, _vp, _i32, _f64, C.POINTER(_i64)]),
+    "hmsg_allgather_nodes": (_i32, [_vp, _vp, _vp, _i64, _vp, _i64]),
 }
 
 _lib = None

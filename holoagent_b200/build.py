@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libhmsg_b200.so")
-SOURCES = ["api.cu", "geometry.cu", "features.cu", "knn.cu", "encoder.cu", "crops.cu", "objects.cu"]
+SOURCES = ["api.cu", "geometry.cu", "features.cu", "knn.cu", "encoder.cu", "crops.cu", "objects.cu", "masks3d.cu", "comm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "--expt-relaxed-constexpr",
@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -3,7 +3,7 @@
 
 static std::string g_create_error;
 
-extern "C" int32_t hmsg_version(void) { return 100; }
+extern "C" int32_t hmsg_version(void) { return 200; }
 
 extern "C" int32_t hmsg_ctx_create(int32_t device, hmsg_ctx** out) {
   if (!out) return HMSG_ERR_ARG;
@@ -33,6 +33,9 @@ extern "C" int32_t hmsg_ctx_create(int32_t device, hmsg_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return HMSG_ERR_CUDA; }
+  e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->sync_event, cudaEventDisableTiming);
+  if (e != cudaSuccess) { g_create_error = cudaGetErrorString(e); delete ctx; return HMSG_ERR_CUDA; }
   *out = ctx;
   return HMSG_OK;
 }
@@ -40,19 +43,25 @@ extern "C" int32_t hmsg_ctx_create(int32_t device, hmsg_ctx** out) {
 extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   if (!ctx) return HMSG_OK;
   cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->copy_stream);
   cudaStreamSynchronize(ctx->stream);
   vit_destroy(ctx);
   knn_destroy(ctx);
   objects_destroy(ctx);
+  masks3d_destroy(ctx);
+  comm_destroy(ctx);
   crops_destroy(ctx);
   free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->d_bounds);
   free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt);
   free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt); free_dev(ctx->nbitmap); free_dev(ctx->nprefix); free_dev(ctx->node_xyz);
   free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox); free_dev(ctx->sum_feats); free_dev(ctx->counter);
   free_dev(ctx->maskbits); free_dev(ctx->pix_idx); free_dev(ctx->win); free_dev(ctx->Fp); free_dev(ctx->feats_stage);
-  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage); free_dev(ctx->cbitmap); free_dev(ctx->far_list); free_dev(ctx->far_count);
+  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage); free_dev(ctx->cbitmap); free_dev(ctx->far_list); free_dev(ctx->far_count); free_dev(ctx->mask_cnt);
   if (ctx->scratch) cudaFree(ctx->scratch);
   for (auto& pc : ctx->prof) for (auto e : pc.ev) cudaEventDestroy(e);
+  for (auto e : ctx->upload_events) cudaEventDestroy(e);
+  if (ctx->sync_event) cudaEventDestroy(ctx->sync_event);
+  cudaStreamDestroy(ctx->copy_stream);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
   return HMSG_OK;
@@ -62,6 +71,7 @@ extern "C" const char* hmsg_last_error(const hmsg_ctx* ctx) { return ctx ? ctx->
 
 extern "C" int32_t hmsg_sync(hmsg_ctx* ctx) {
   if (!ctx) return HMSG_ERR_ARG;
+  HMSG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   return HMSG_OK;
 }

@@ -27,7 +27,7 @@
   } while (0)
 
 // ---- optional per-kernel-class CUDA-event profiling (bench.py roofline numbers)
-enum { PROF_GEMM = 0, PROF_ATTN, PROF_ELTWISE, PROF_KNN, PROF_NN, PROF_SCATTER, PROF_GEOM, PROF_CROPS, PROF_NCLASS };
+enum { PROF_GEMM = 0, PROF_ATTN, PROF_ELTWISE, PROF_KNN, PROF_NN, PROF_SCATTER, PROF_GEOM, PROF_CROPS, PROF_MASK3D, PROF_COMM, PROF_NCLASS };
 struct ProfClass {
   std::vector<cudaEvent_t> ev;   // pairs (begin, end)
   size_t used = 0;
@@ -37,6 +37,8 @@ struct ProfClass {
 struct VitState;   // encoder.cu
 struct KnnState;   // knn.cu
 struct ObjState;   // objects.cu
+struct M3dState;   // masks3d.cu
+struct CommState;  // comm.cu
 
 struct GridDesc {
   double vmin[3];     // min_bound - vs/2  (Open3D voxel_min_bound)
@@ -55,9 +57,26 @@ struct CamDesc {
   int H, W;
 };
 
+// host -> device frame uploads run on their own stream; consumers wait for exactly the uploads they read
+struct UploadRec {
+  int64_t f0, n;
+  cudaEvent_t ev;
+  bool waited;
+};
+
 struct hmsg_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;      // hmsg_scene_put_frames from host memory (H2D overlaps compute on `stream`)
+  std::vector<UploadRec> uploads;
+  std::vector<cudaEvent_t> upload_events;  // pool (reused across scenes)
+  size_t upload_events_used = 0;
+  cudaEvent_t sync_event = nullptr;
+  // make `stream` wait for every pending upload that overlaps frames [f0, f0 + n)
+  void wait_frames(int64_t f0, int64_t n) {
+    for (auto& u : uploads)
+      if (!u.waited && u.f0 < f0 + n && f0 < u.f0 + u.n) { cudaStreamWaitEvent(stream, u.ev, 0); u.waited = true; }
+  }
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
@@ -111,6 +130,9 @@ struct hmsg_ctx {
   int batch_M = 0, batch_MW = 0;
   int64_t batch_begin = -1;
   int batch_n = 0;
+  std::vector<int> batch_counts;   // real masks per frame of the batch (ragged SAM output; <= batch_M)
+  int32_t* mask_cnt = nullptr;     // device copy [batch_cap]
+  size_t mask_cnt_bytes = 0;
   uint32_t* maskbits = nullptr;    // [batch_cap, H*W, MW]
   size_t maskbits_bytes = 0;
   int32_t* pix_idx = nullptr;      // [batch_cap, H*W]
@@ -134,6 +156,8 @@ struct hmsg_ctx {
   VitState* vit = nullptr;
   KnnState* knn = nullptr;
   ObjState* obj = nullptr;
+  M3dState* m3d = nullptr;
+  CommState* comm = nullptr;
 
   uint32_t prof_mask = 0;
   ProfClass prof[PROF_NCLASS];
@@ -246,6 +270,11 @@ int32_t vit_destroy(hmsg_ctx* ctx);
 int32_t knn_destroy(hmsg_ctx* ctx);
 int32_t crops_destroy(hmsg_ctx* ctx);
 int32_t objects_destroy(hmsg_ctx* ctx);
+int32_t masks3d_destroy(hmsg_ctx* ctx);
+void masks3d_invalidate_scratch(hmsg_ctx* ctx);
+int32_t comm_destroy(hmsg_ctx* ctx);
 int32_t features_ensure_pix_idx(hmsg_ctx* ctx);
+int32_t geometry_radius_count(hmsg_ctx* ctx, double radius, int64_t v_begin, int64_t n);
+int32_t geometry_radius_finish(hmsg_ctx* ctx, int32_t nb_points, int64_t* n_nodes);
 int32_t geometry_points_to_node_dev(hmsg_ctx* ctx, const double* d_pts, long long n, int64_t* d_idx, double* d_dist);
 int32_t vit_encode_device(hmsg_ctx* ctx, const float* dx, int B, float* dout, int normalize);

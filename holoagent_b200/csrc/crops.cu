@@ -660,6 +660,7 @@ int32_t crops_run(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, cons
     if ((rc = get_mma_table(ctx, cs))) return rc;
     if ((rc = ctx->reserve(&cs->t1p, &cs->t1p_bytes, (size_t)ncrops * 3 * 224 * CROP_MID + 1024))) return rc;
   }
+  ctx->wait_frames(frame_begin, n);
   ctx->prof_begin(PROF_CROPS);
   if (tc->ksize != 11) return ctx->fail(HMSG_ERR_STATE, "hmsg_make_crops: unexpected PIL kernel size for 512->224");
   if (use_mma)

@@ -58,10 +58,14 @@ __global__ void __launch_bounds__(TPB) k_masks_dense(const uint8_t* seg, int HW,
 // one block per frame.  feats [n, 2M+1, d]: rows 0..M-1 masked crops, M..2M-1 plain crops,
 // row 2M the full frame (F_g).  extractor.py:159-175.
 template <int DV>   // d = 128*DV ; a lane owns DV float4
-__global__ void __launch_bounds__(TPB) k_fuse(const float* __restrict__ feats, int M, float w_masked, float w_plain, float* __restrict__ Fp) {
+__global__ void __launch_bounds__(TPB) k_fuse(const float* __restrict__ feats, int M, const int32_t* __restrict__ mask_cnt, float w_masked,
+                                              float w_plain, float* __restrict__ Fp) {
   extern __shared__ float sm[];      // phi[M]
   const int d = 128 * DV;
   int fb = blockIdx.x;
+  // SAM returns a different number of masks per frame; the batch is padded to M slots.  The softmax of
+  // extractor.py:168-172 runs over the frame's REAL masks only: padded slots take no part in it.
+  const int Mr = mask_cnt[fb];
   const float* base = feats + (long long)fb * (2 * M + 1) * d;
   float* out = Fp + (long long)fb * M * d;
   int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(TPB) k_fuse(const float* __restrict__ feats, i
   for (int o = 16; o > 0; o >>= 1) gn += __shfl_xor_sync(0xffffffffu, gn, o);
   gn = fmaxf(sqrtf(gn), 1e-6f);
   // pass 1: F_l = normalize(w*masked + (1-w)*plain) -> stored in out ; phi = cos(F_l, F_g)
-  for (int m = wid; m < M; m += nw) {
+  for (int m = wid; m < Mr; m += nw) {
     float4 v[DV];
     float nn = 0.f;
 #pragma unroll
@@ -104,11 +108,11 @@ __global__ void __launch_bounds__(TPB) k_fuse(const float* __restrict__ feats, i
   __syncthreads();
   // softmax over the masks of the frame (dim=0)
   float mx = -INFINITY;
-  for (int m = 0; m < M; m++) mx = fmaxf(mx, sm[m]);
+  for (int m = 0; m < Mr; m++) mx = fmaxf(mx, sm[m]);
   float den = 0.f;
-  for (int m = 0; m < M; m++) den += expf(sm[m] - mx);
+  for (int m = 0; m < Mr; m++) den += expf(sm[m] - mx);
   // pass 2: F_p = normalize(w_i*F_g + (1-w_i)*F_l)
-  for (int m = wid; m < M; m += nw) {
+  for (int m = wid; m < Mr; m += nw) {
     float wi = expf(sm[m] - mx) / den;
     float om = 1.0f - wi;
     float4 v[DV];
@@ -284,92 +288,47 @@ __global__ void __launch_bounds__(TPB) k_finalize_feats(const float* __restrict_
   reinterpret_cast<float4*>(out)[i] = v;
 }
 
-// ----------------------------------------------------------------------------- A7 mask nodes
-// generic.py:162-190.  Mask pixels' points are bit-identical to the frame's points, so the
-// NN index of a mask pixel is pix_idx of the frame.  Per mask: min bound over the hit node
-// positions, re-voxelisation key = floor((c - (min - vs/2)) / vs), accumulation weighted by
-// pixel multiplicity.  Implemented as: (1) per-mask min bound (atomicMin on ordered doubles),
-// (2) emit (mask, key) -> 64-bit composite per mask pixel into an open-addressing hash table in
-// HBM with f64 accumulators, (3) compaction on the host of the (small) table.
-struct MaskCell {
-  unsigned long long key;   // (mask+1) << 42 | i << 28 | j << 14 | k   (0 = empty)
-  double acc[6];
-  unsigned int cnt;
-  unsigned int pad;
-};
-
-__global__ void __launch_bounds__(TPB) k_mask_bounds(const int32_t* pix_idx, const uint32_t* maskbits, int HW, int MW, const double* nodes,
-                                                     long long* mb /*[M,3]*/) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  int n = pix_idx[p];
-  if (n < 0) return;
-  double c[3] = {nodes[(long long)n * 3], nodes[(long long)n * 3 + 1], nodes[(long long)n * 3 + 2]};
-  for (int w = 0; w < MW; w++) {
-    uint32_t bits = maskbits[(long long)p * MW + w];
-    while (bits) {
-      int m = __ffs(bits) - 1 + 32 * w;
-      bits &= bits - 1;
-      for (int k = 0; k < 3; k++) atomicMin(&mb[m * 3 + k], d2ord(c[k]));
-    }
-  }
-}
-
-__global__ void __launch_bounds__(TPB) k_mask_accum(const int32_t* pix_idx, const uint32_t* maskbits, int HW, int MW, const double* nodes,
-                                                    const double* nrgb, const long long* mb, double vs, MaskCell* table,
-                                                    unsigned long long cap_mask, int* overflow) {
-  int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= HW) return;
-  int n = pix_idx[p];
-  if (n < 0) return;
-  double c[3] = {nodes[(long long)n * 3], nodes[(long long)n * 3 + 1], nodes[(long long)n * 3 + 2]};
-  double col[3] = {nrgb[(long long)n * 3], nrgb[(long long)n * 3 + 1], nrgb[(long long)n * 3 + 2]};
-  for (int w = 0; w < MW; w++) {
-    uint32_t bits = maskbits[(long long)p * MW + w];
-    while (bits) {
-      int m = __ffs(bits) - 1 + 32 * w;
-      bits &= bits - 1;
-      unsigned long long key = (unsigned long long)(m + 1) << 42;
-      bool bad = false;
-      for (int k = 0; k < 3; k++) {
-        long long o = mb[m * 3 + k];
-        long long bb = o >= 0 ? o : (o ^ 0x7FFFFFFFFFFFFFFFLL);
-        double mn = __longlong_as_double(bb);
-        double vmin = __dsub_rn(mn, __dmul_rn(vs, 0.5));
-        long long q = (long long)floor(cell_coord(c[k], vmin, vs));
-        if (q < 0 || q >= (1 << 14)) bad = true;
-        key |= (unsigned long long)q << (14 * (2 - k));
-      }
-      if (bad) { atomicExch(overflow, 2); continue; }
-      unsigned long long h = key * 0x9E3779B97F4A7C15ULL;
-      unsigned long long slot = (h >> 20) & cap_mask;
-      for (unsigned long long probe = 0; probe <= cap_mask; probe++) {
-        unsigned long long prev = atomicCAS(&table[slot].key, 0ULL, key);
-        if (prev == 0ULL || prev == key) {
-          for (int k = 0; k < 3; k++) { atomicAdd(&table[slot].acc[k], c[k]); atomicAdd(&table[slot].acc[3 + k], col[k]); }
-          atomicAdd(&table[slot].cnt, 1u);
-          break;
-        }
-        slot = (slot + 1) & cap_mask;
-        if (probe == cap_mask) atomicExch(overflow, 1);
-      }
-    }
-  }
+__global__ void k_fill_i32(int32_t* a, int n, int32_t v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
 }
 
 // ======================================================================================
 // host side
 // ======================================================================================
 static int32_t ensure_batch(hmsg_ctx* ctx, int n_frames, int M) {
-  if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "masks/features: call hmsg_radius_filter first");
+  // masks need the frames only (crops + encoder of a batch may run before the node table exists: the host-fed
+  // path encodes early batches while later frames are still crossing PCIe); A4-A7 check for the node table themselves
+  if (!ctx->depth) return ctx->fail(HMSG_ERR_STATE, "masks: call hmsg_scene_begin / add frames first");
   if (M <= 0 || M > 1024) return ctx->fail(HMSG_ERR_ARG, "masks: M out of range");
   size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
   int MW = (M + 31) / 32;
   int32_t rc;
   if ((rc = ctx->reserve(&ctx->maskbits, &ctx->maskbits_bytes, (size_t)n_frames * hw * MW * 4))) return rc;
   if ((rc = ctx->reserve(&ctx->pix_idx, &ctx->pix_idx_bytes, (size_t)n_frames * hw * 4))) return rc;
+  if ((rc = ctx->reserve(&ctx->mask_cnt, &ctx->mask_cnt_bytes, (size_t)std::max(n_frames, 64) * 4))) return rc;
   ctx->batch_M = M; ctx->batch_MW = MW; ctx->batch_n = n_frames;
   ctx->pix_idx_for = -1;
+  masks3d_invalidate_scratch(ctx);
+  // every slot is a real mask until hmsg_masks_counts says otherwise
+  ctx->batch_counts.assign(n_frames, M);
+  k_fill_i32<<<(n_frames + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(ctx->mask_cnt, n_frames, M);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+// Ragged SAM output (extractor.py:117-124 returns as many masks as SAM finds): counts[i] <= M real masks in frame
+// frame_begin + i of the batch just set with hmsg_masks_*; slots past the count are padding that takes no part in the
+// softmax of A5, produces no 3-D mask in A7 and is not appended to the N1 merge list.
+extern "C" int32_t hmsg_masks_counts(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, const int32_t* counts) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (ctx->batch_begin != frame_begin || ctx->batch_n != n || !counts)
+    return ctx->fail(HMSG_ERR_STATE, "hmsg_masks_counts: call right after hmsg_masks_* of the same batch");
+  for (int i = 0; i < n; i++)
+    if (counts[i] < 0 || counts[i] > ctx->batch_M) return ctx->fail(HMSG_ERR_ARG, "hmsg_masks_counts: count outside [0, M]");
+  ctx->batch_counts.assign(counts, counts + n);
+  HMSG_CUDA(cudaMemcpyAsync(ctx->mask_cnt, ctx->batch_counts.data(), (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  masks3d_invalidate_scratch(ctx);
   return HMSG_OK;
 }
 
@@ -386,6 +345,7 @@ extern "C" int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t 
   }
   int HW = ctx->cam.H * ctx->cam.W;
   dim3 grid((HW + TPB - 1) / TPB, n);
+  ctx->wait_frames(frame_begin, n);
   k_masks_boxes<<<grid, TPB, M * 16, ctx->stream>>>(ctx->depth, frame_begin, ctx->cam.H, ctx->cam.W, ctx->cam.scale, M, ctx->batch_MW, dbox,
                                                     ctx->maskbits);
   HMSG_LAUNCH_CHECK();
@@ -432,7 +392,7 @@ extern "C" int32_t hmsg_features_begin(hmsg_ctx* ctx, int32_t d) {
 template <int DV>
 static int32_t launch_fuse_scatter(hmsg_ctx* ctx, int n, int M, const float* dfeats, float w_masked, float w_plain) {
   int HW = ctx->cam.H * ctx->cam.W;
-  k_fuse<DV><<<n, TPB, M * sizeof(float), ctx->stream>>>(dfeats, M, w_masked, w_plain, ctx->Fp);
+  k_fuse<DV><<<n, TPB, M * sizeof(float), ctx->stream>>>(dfeats, M, ctx->mask_cnt, w_masked, w_plain, ctx->Fp);
   HMSG_LAUNCH_CHECK();
   ctx->prof_begin(PROF_SCATTER);
   static int per_frame = -1;
@@ -473,7 +433,7 @@ static int32_t win_next_epoch(hmsg_ctx* ctx, int64_t n) {
 extern "C" int32_t hmsg_fuse_scatter(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const float* feats, float maskedd_weight,
                                      float* F_p_out, int32_t on_device) {
   if (!ctx) return HMSG_ERR_ARG;
-  if (!ctx->sum_feats || ctx->d == 0) return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: call hmsg_features_begin first");
+  if (!ctx->sum_feats || ctx->d == 0 || !ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: call hmsg_features_begin first");
   if (ctx->batch_begin != frame_begin || ctx->batch_n != n || ctx->batch_M != M)
     return ctx->fail(HMSG_ERR_STATE, "hmsg_fuse_scatter: masks of this batch were not set (hmsg_masks_*)");
   if (!feats) return ctx->fail(HMSG_ERR_ARG, "hmsg_fuse_scatter: null feats");
@@ -559,74 +519,12 @@ extern "C" int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, f
 // caller asks for 3-D masks without having scattered features for this batch)
 int32_t features_ensure_pix_idx(hmsg_ctx* ctx) {
   if (ctx->batch_begin < 0) return ctx->fail(HMSG_ERR_STATE, "no mask batch (hmsg_masks_*)");
+  if (!ctx->nodes_built) return ctx->fail(HMSG_ERR_STATE, "pixel->node map: call hmsg_radius_filter first");
   if (ctx->pix_idx_for == ctx->batch_begin) return HMSG_OK;
   int32_t rc;
   if ((rc = win_next_epoch(ctx, ctx->batch_n))) return rc;
   if ((rc = geometry_nn_winner(ctx, ctx->batch_begin, ctx->batch_n))) return rc;
   ctx->pix_idx_for = ctx->batch_begin;
-  return HMSG_OK;
-}
-
-// A7: one frame (must be inside the current mask batch).
-extern "C" int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t* offsets, double* xyz, double* rgb, int32_t* ijk) {
-  if (!ctx) return HMSG_ERR_ARG;
-  if (ctx->batch_begin < 0 || frame < ctx->batch_begin || frame >= ctx->batch_begin + ctx->batch_n)
-    return ctx->fail(HMSG_ERR_STATE, "hmsg_mask_nodes: frame is not in the current mask batch (hmsg_masks_*)");
-  if (!offsets || !(down_size > 0)) return ctx->fail(HMSG_ERR_ARG, "hmsg_mask_nodes: bad argument");
-  int M = ctx->batch_M, MW = ctx->batch_MW;
-  int HW = ctx->cam.H * ctx->cam.W;
-  int fb = (int)(frame - ctx->batch_begin);
-  int32_t rc;
-  if ((rc = features_ensure_pix_idx(ctx))) return rc;
-  // count mask pixels to size the table
-  size_t cap = 1;
-  while (cap < (size_t)HW * 2) cap <<= 1;       // >= 2x the largest possible number of distinct (mask,cell) pairs per mask pixel
-  cap = std::min(cap * (size_t)std::max(1, std::min(M, 8)), (size_t)1 << 24);
-  size_t need = cap * sizeof(MaskCell) + (size_t)M * 3 * 8 + 64;
-  if ((rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, need))) return rc;
-  MaskCell* table = (MaskCell*)ctx->scratch;
-  long long* mb = (long long*)((char*)ctx->scratch + cap * sizeof(MaskCell));
-  int* overflow = (int*)(mb + M * 3);
-  HMSG_CUDA(cudaMemsetAsync(table, 0, cap * sizeof(MaskCell), ctx->stream));
-  std::vector<long long> init(M * 3);
-  {
-    double pinf = INFINITY; long long a; memcpy(&a, &pinf, 8);
-    for (auto& v : init) v = a;
-  }
-  HMSG_CUDA(cudaMemcpyAsync(mb, init.data(), M * 3 * 8, cudaMemcpyHostToDevice, ctx->stream));
-  HMSG_CUDA(cudaMemsetAsync(overflow, 0, 4, ctx->stream));
-  const int32_t* pidx = ctx->pix_idx + (size_t)fb * HW;
-  const uint32_t* mbits = ctx->maskbits + (size_t)fb * HW * MW;
-  k_mask_bounds<<<(HW + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(pidx, mbits, HW, MW, ctx->node_xyz, mb);
-  HMSG_LAUNCH_CHECK();
-  k_mask_accum<<<(HW + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(pidx, mbits, HW, MW, ctx->node_xyz, ctx->node_rgb, mb, down_size, table,
-                                                              (unsigned long long)cap - 1, overflow);
-  HMSG_LAUNCH_CHECK();
-  std::vector<MaskCell> host(cap);
-  int ov = 0;
-  HMSG_CUDA(cudaMemcpyAsync(host.data(), table, cap * sizeof(MaskCell), cudaMemcpyDeviceToHost, ctx->stream));
-  HMSG_CUDA(cudaMemcpyAsync(&ov, overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (ov == 1) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_mask_nodes: mask cell table overflow");
-  if (ov == 2) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_mask_nodes: a mask spans more than 2^14 cells per axis");
-  // ragged compaction + canonical (mask, i, j, k) order: the composite key sorts exactly that way
-  std::vector<const MaskCell*> used;
-  used.reserve(1024);
-  for (size_t i = 0; i < cap; i++) if (host[i].key) used.push_back(&host[i]);
-  std::sort(used.begin(), used.end(), [](const MaskCell* a, const MaskCell* b) { return a->key < b->key; });
-  for (int m = 0; m <= M; m++) offsets[m] = 0;
-  for (auto* c : used) offsets[(c->key >> 42)]++;        // key>>42 = mask+1
-  for (int m = 0; m < M; m++) offsets[m + 1] += offsets[m];
-  if (xyz || rgb || ijk) {
-    int64_t r = 0;
-    for (auto* c : used) {
-      double n = (double)c->cnt;
-      if (xyz) for (int k = 0; k < 3; k++) xyz[r * 3 + k] = c->acc[k] / n;
-      if (rgb) for (int k = 0; k < 3; k++) rgb[r * 3 + k] = c->acc[3 + k] / n;
-      if (ijk) { ijk[r * 3] = (int32_t)((c->key >> 28) & 0x3FFF); ijk[r * 3 + 1] = (int32_t)((c->key >> 14) & 0x3FFF); ijk[r * 3 + 2] = (int32_t)(c->key & 0x3FFF); }
-      r++;
-    }
-  }
   return HMSG_OK;
 }
 

@@ -314,10 +314,10 @@ __global__ void __launch_bounds__(TPB) k_write_ijk(const uint32_t* bitmap, const
 // words of each column, fetch candidate centroids by rank and count d2 < R^2 in float64
 // with the accumulation order ((dx*dx+dy*dy)+dz*dz) (Open3D/nanoflann L2_Simple).
 __global__ void __launch_bounds__(TPB) k_radius_count(GridDesc g, const uint32_t* bitmap, const uint32_t* prefix, const double* acc,
-                                                      const int32_t* ijk, long long n, double R, uint32_t* out) {
-  long long v = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+                                                      const int32_t* ijk, long long v_begin, long long v_end, double R, uint32_t* out) {
+  long long v = v_begin + (((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   int lane = threadIdx.x & 31;
-  if (v >= n) return;
+  if (v >= v_end) return;
   double cx = acc[v * 6 + 0], cy = acc[v * 6 + 1], cz = acc[v * 6 + 2];
   int ci = ijk[v * 3 + 0], cj = ijk[v * 3 + 1], ck = ijk[v * 3 + 2];
   double R2 = __dmul_rn(R, R);
@@ -683,9 +683,27 @@ extern "C" int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, con
   if (frame_begin + n > ctx->cap) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_scene_put_frames: frame capacity exceeded");
   size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
   cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-  HMSG_CUDA(cudaMemcpyAsync(ctx->depth + hw * frame_begin, depth, hw * 2 * n, kind, ctx->stream));
-  HMSG_CUDA(cudaMemcpyAsync(ctx->rgb + hw * 3 * frame_begin, rgb, hw * 3 * n, kind, ctx->stream));
-  HMSG_CUDA(cudaMemcpyAsync(ctx->poses + 16 * frame_begin, poses, 16 * sizeof(double) * n, kind, ctx->stream));
+  // Host frames go over PCIe on the copy stream so that the upload of later batches overlaps the kernels of earlier
+  // ones; an event per call lets every consumer wait for exactly the frames it reads (hmsg_ctx::wait_frames).  The
+  // first upload of a scene is ordered after everything the compute stream still reads from the old frames.
+  cudaStream_t st = on_device ? ctx->stream : ctx->copy_stream;
+  if (!on_device && ctx->uploads.empty()) {
+    HMSG_CUDA(cudaEventRecord(ctx->sync_event, ctx->stream));
+    HMSG_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->sync_event, 0));
+  }
+  HMSG_CUDA(cudaMemcpyAsync(ctx->depth + hw * frame_begin, depth, hw * 2 * n, kind, st));
+  HMSG_CUDA(cudaMemcpyAsync(ctx->rgb + hw * 3 * frame_begin, rgb, hw * 3 * n, kind, st));
+  HMSG_CUDA(cudaMemcpyAsync(ctx->poses + 16 * frame_begin, poses, 16 * sizeof(double) * n, kind, st));
+  if (!on_device) {
+    if (ctx->upload_events_used == ctx->upload_events.size()) {
+      cudaEvent_t e;
+      HMSG_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->upload_events.push_back(e);
+    }
+    cudaEvent_t ev = ctx->upload_events[ctx->upload_events_used++];
+    HMSG_CUDA(cudaEventRecord(ev, ctx->copy_stream));
+    ctx->uploads.push_back(UploadRec{frame_begin, n, ev, false});
+  }
   if (frame_begin + n > ctx->nframes) ctx->nframes = frame_begin + n;
   ctx->voxels_built = false; ctx->nodes_built = false;
   return HMSG_OK;
@@ -701,6 +719,10 @@ extern "C" int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n) {
 extern "C" int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx) {
   if (!ctx) return HMSG_ERR_ARG;
   ctx->nframes = 0; ctx->voxels_built = false; ctx->nodes_built = false; ctx->batch_begin = -1;
+  // pending uploads of the old scene: nothing may still be in flight when their slots are reused
+  if (!ctx->uploads.empty()) HMSG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->uploads.clear();
+  ctx->upload_events_used = 0;
   return HMSG_OK;
 }
 
@@ -710,6 +732,7 @@ extern "C" int32_t hmsg_unproject_frame(hmsg_ctx* ctx, int64_t frame, double* xy
   if (!ctx) return HMSG_ERR_ARG;
   if (frame < 0 || frame >= ctx->nframes) return ctx->fail(HMSG_ERR_ARG, "hmsg_unproject_frame: frame out of range");
   if (!xyz || !rgb || !valid) return ctx->fail(HMSG_ERR_ARG, "hmsg_unproject_frame: null output");
+  ctx->wait_frames(frame, 1);
   size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
   size_t need = hw * (48 + 1) + 64;
   int32_t rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, need);
@@ -743,6 +766,7 @@ static int32_t run_scan(hmsg_ctx* ctx, const uint32_t* bitmap, long long nwords,
 template <typename F>
 static int32_t for_frame_chunks(hmsg_ctx* ctx, F&& launch) {
   int HW = ctx->cam.H * ctx->cam.W;
+  ctx->wait_frames(0, ctx->nframes);
   unsigned bpf = (unsigned)((HW + TPB * 4 - 1) / (TPB * 4));
   for (int64_t f0 = 0; f0 < ctx->nframes; f0 += 32768) {
     unsigned nf = (unsigned)std::min<int64_t>(32768, ctx->nframes - f0);
@@ -756,6 +780,7 @@ static int32_t for_frame_chunks(hmsg_ctx* ctx, F&& launch) {
 template <typename F>
 static int32_t for_frame_range(hmsg_ctx* ctx, int64_t f_begin, int64_t n, F&& launch) {
   int HW = ctx->cam.H * ctx->cam.W;
+  ctx->wait_frames(f_begin, n);
   unsigned bpf = (unsigned)((HW + TPB * 4 - 1) / (TPB * 4));
   for (int64_t f0 = f_begin; f0 < f_begin + n; f0 += 32768) {
     unsigned nf = (unsigned)std::min<int64_t>(32768, f_begin + n - f0);
@@ -963,19 +988,25 @@ extern "C" int32_t hmsg_voxels_read(hmsg_ctx* ctx, double* xyz, double* rgb, int
   return HMSG_OK;
 }
 
-extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double radius, int64_t* n_nodes) {
-  if (!ctx) return HMSG_ERR_ARG;
+// neighbour counts of the voxels [v_begin, v_begin + n): ranks can split the voxel table (hmsg_radius_filter_sharded)
+int32_t geometry_radius_count(hmsg_ctx* ctx, double radius, int64_t v_begin, int64_t n) {
   if (!ctx->voxels_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_radius_filter: call hmsg_voxel_build first");
-  if (nb_points < 0 || !(radius > 0)) return ctx->fail(HMSG_ERR_ARG, "hmsg_radius_filter: bad argument");
+  if (!(radius > 0) || v_begin < 0 || n < 0 || v_begin + n > ctx->n_voxels) return ctx->fail(HMSG_ERR_ARG, "hmsg_radius_filter: bad argument");
+  if (n == 0) return HMSG_OK;
+  ctx->prof_begin(PROF_GEOM);
+  long long threads = n * 32;
+  k_radius_count<<<(unsigned)((threads + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->grid, ctx->bitmap, ctx->prefix, ctx->vox_acc, ctx->vox_ijk, v_begin,
+                                                                                  v_begin + n, radius, ctx->rad_cnt);
+  ctx->prof_end(PROF_GEOM, 0.0);
+  HMSG_LAUNCH_CHECK();
+  return HMSG_OK;
+}
+
+// keep iff count > nb_points (self included, H5) -> node bitmap / prefix / coarse bitmap / compact node table
+int32_t geometry_radius_finish(hmsg_ctx* ctx, int32_t nb_points, int64_t* n_nodes) {
+  if (!ctx->voxels_built) return ctx->fail(HMSG_ERR_STATE, "hmsg_radius_filter: call hmsg_voxel_build first");
+  if (nb_points < 0) return ctx->fail(HMSG_ERR_ARG, "hmsg_radius_filter: bad argument");
   const GridDesc& g = ctx->grid;
-  int64_t n = ctx->n_voxels;
-  // pcd_denoise_dbscan(eps=0.01,min_points=100) (graph.py:352) is the identity for voxel_size >= 0.02 (SURVEY H6)
-  if (n > 0) {
-    long long threads = n * 32;
-    k_radius_count<<<(unsigned)((threads + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(g, ctx->bitmap, ctx->prefix, ctx->vox_acc, ctx->vox_ijk, n,
-                                                                                    radius, ctx->rad_cnt);
-    HMSG_LAUNCH_CHECK();
-  }
   k_node_bitmap<<<(unsigned)((g.nwords + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(ctx->bitmap, ctx->prefix, g.nwords, ctx->rad_cnt,
                                                                                  (uint32_t)nb_points, ctx->nbitmap);
   HMSG_LAUNCH_CHECK();
@@ -1003,6 +1034,14 @@ extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double r
   ctx->d = 0;   // features_begin must be called again (buffers are kept and re-zeroed there)
   if (n_nodes) *n_nodes = ctx->n_nodes;
   return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_radius_filter(hmsg_ctx* ctx, int32_t nb_points, double radius, int64_t* n_nodes) {
+  if (!ctx) return HMSG_ERR_ARG;
+  // pcd_denoise_dbscan(eps=0.01,min_points=100) (graph.py:352) is the identity for voxel_size >= 0.02 (SURVEY H6)
+  int32_t rc = geometry_radius_count(ctx, radius, 0, ctx->n_voxels);
+  if (rc) return rc;
+  return geometry_radius_finish(ctx, nb_points, n_nodes);
 }
 
 extern "C" int32_t hmsg_radius_counts_read(hmsg_ctx* ctx, uint32_t* counts) {
@@ -1036,6 +1075,7 @@ extern "C" int32_t hmsg_pixel_to_node(hmsg_ctx* ctx, int64_t frame, int64_t* idx
   int32_t rc = ctx->reserve((char**)&ctx->scratch, &ctx->scratch_bytes, hw * 16);
   if (rc) return rc;
   int64_t* di = (int64_t*)ctx->scratch; double* dd = (double*)(di + hw);
+  ctx->wait_frames(frame, 1);
   k_pixel_to_node<<<(unsigned)((hw + TPB - 1) / TPB), TPB, 0, ctx->stream>>>(frame_args(ctx, frame), ctx->grid, ctx->nbitmap, ctx->nprefix,
                                                                               ctx->cbitmap, ctx->node_xyz, di, dist ? dd : nullptr);
   HMSG_LAUNCH_CHECK();
@@ -1081,6 +1121,7 @@ int32_t geometry_nn_winner(hmsg_ctx* ctx, int64_t frame_begin, int n_frames) {
   int32_t rc = ctx->reserve(&ctx->far_list, &ctx->far_list_bytes, (size_t)n_frames * HW * 4);
   if (rc) return rc;
   if (!ctx->far_count) HMSG_CUDA(cudaMalloc((void**)&ctx->far_count, 4));
+  ctx->wait_frames(frame_begin, n_frames);
   HMSG_CUDA(cudaMemsetAsync(ctx->far_count, 0, 4, ctx->stream));
   ctx->prof_begin(PROF_NN);
   k_nn_winner<<<grid, TPB, 0, ctx->stream>>>(frame_args(ctx, frame_begin), ctx->grid, ctx->nbitmap, ctx->nprefix, ctx->node_xyz, ctx->pix_idx,

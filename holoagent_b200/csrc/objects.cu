@@ -1160,6 +1160,7 @@ extern "C" int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double d
   { double pinf = INFINITY; long long a; memcpy(&a, &pinf, 8); for (auto& v : init) v = a; }
   HMSG_CUDA(cudaMemsetAsync(base, 0, need, ctx->stream));
   HMSG_CUDA(cudaMemcpyAsync(mb, init.data(), (size_t)M * 24, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->wait_frames(frame, 1);
   k_fm_stats<<<blocks_for(HW), OTPB, 0, ctx->stream>>>(pidx, mbits, depth, ctx->cam.scale, HW, MW, ctx->node_xyz, cnt, dsum, mb);
   HMSG_LAUNCH_CHECK();
   std::vector<int> hcnt(M); std::vector<double> hsum(M);
@@ -1167,14 +1168,15 @@ extern "C" int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double d
   HMSG_CUDA(cudaMemcpyAsync(hsum.data(), dsum, (size_t)M * 8, cudaMemcpyDeviceToHost, ctx->stream));
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<long long> eoff(M + 1, 0); std::vector<unsigned char> keepm(M, 0);
+  const int Mr = ctx->batch_counts[fb];                                            // real masks of this frame; padded slots are not list entries
   for (int m = 0; m < M; m++) {
-    bool keep = hcnt[m] > 0 && !(hsum[m] / (double)hcnt[m] > filter_distance);     // `if Z.mean() > filter_distance: return empty`
+    bool keep = m < Mr && hcnt[m] > 0 && !(hsum[m] / (double)hcnt[m] > filter_distance);     // `if Z.mean() > filter_distance: return empty`
     keepm[m] = keep ? 1 : 0;
     eoff[m + 1] = eoff[m] + (keep ? hcnt[m] : 0);
   }
   long long E = eoff[M];
   std::vector<int64_t> voff(M + 1, 0);
-  if (E == 0) return hmsg_objects_add_masks(ctx, M, voff.data(), nullptr, nullptr, 1);
+  if (E == 0) return hmsg_objects_add_masks(ctx, Mr, voff.data(), nullptr, nullptr, 1);
   if (E >= (1LL << 31)) return ctx->fail(HMSG_ERR_CAPACITY, "hmsg_objects_add_frame: too many mask pixels");
   HMSG_CUDA(cudaMemcpyAsync(d_eoff, eoff.data(), (size_t)(M + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
   HMSG_CUDA(cudaMemcpyAsync(d_keep, keepm.data(), (size_t)M, cudaMemcpyHostToDevice, ctx->stream));
@@ -1213,7 +1215,7 @@ extern "C" int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double d
   k_fm_means<<<blocks_for(E), OTPB, 0, ctx->stream>>>(k1, v1, S.heads, S.hscan, E, ctx->node_xyz, ctx->node_rgb, st->in_xyz, st->in_rgb);
   HMSG_LAUNCH_CHECK();
   for (int m = 0; m <= M; m++) voff[m] = hv[m];
-  return hmsg_objects_add_masks(ctx, M, voff.data(), st->in_xyz, st->in_rgb, 1);
+  return hmsg_objects_add_masks(ctx, Mr, voff.data(), st->in_xyz, st->in_rgb, 1);   // slots >= Mr are empty: offsets[Mr] is the total
 }
 
 // the frame masks staged by the last hmsg_objects_add_frame are not kept; this reads the CURRENT global list instead

@@ -119,7 +119,7 @@ class HmsgEngine:
     def set_option(self, key: str, value: int):
         self._ck(self.lib.hmsg_set_option(self.h, key.encode(), int(value)))
 
-    PROF = {"gemm": 0, "attn": 1, "eltwise": 2, "knn": 3, "nn": 4, "scatter": 5, "geom": 6, "crops": 7}
+    PROF = {"gemm": 0, "attn": 1, "eltwise": 2, "knn": 3, "nn": 4, "scatter": 5, "geom": 6, "crops": 7, "mask3d": 8, "comm": 9}
 
     def prof_enable(self, *classes):
         mask = 0
@@ -298,6 +298,11 @@ class HmsgEngine:
         if dev:
             self.torch_wait()
 
+    def masks_counts(self, frame_begin, counts):
+        """ragged SAM output: counts[i] real masks in frame frame_begin + i of the batch just set (slots past it are padding)"""
+        counts = np.ascontiguousarray(counts, dtype=np.int32)
+        self._ck(self.lib.hmsg_masks_counts(self.h, int(frame_begin), int(len(counts)), ptr(counts)))
+
     def fuse_scatter(self, frame_begin, n, M, feats, maskedd_weight, Fp_out=None):
         dev = _is_dev(feats)
         if not dev:
@@ -342,6 +347,34 @@ class HmsgEngine:
         if tot:
             self._ck(self.lib.hmsg_mask_nodes(self.h, int(frame), float(down_size), ptr(off), ptr(xyz), ptr(rgb), ptr(ijk)))
         return off, xyz, rgb, ijk
+
+    def mask_nodes_batch(self, frame_begin, n_frames, down_size, filter_distance=float("inf"), keep=True):
+        """A7 for frames of the current mask batch, results stay in HBM (keep: appended to the mask store)"""
+        self._ck(self.lib.hmsg_mask_nodes_batch(self.h, int(frame_begin), int(n_frames), float(down_size), float(filter_distance), 1 if keep else 0))
+
+    def mask_store_reset(self):
+        self._ck(self.lib.hmsg_mask_store_reset(self.h))
+
+    def mask_store_count(self):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        self._ck(self.lib.hmsg_mask_store_count(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def mask_store_read(self, frame, max_masks=4096):
+        """-> (offsets [n_masks+1], xyz, rgb, ijk) of one stored frame (host)"""
+        nm = C.c_int32()
+        off = np.zeros(max_masks + 1, np.int64)
+        self._ck(self.lib.hmsg_mask_store_read(self.h, int(frame), C.byref(nm), ptr(off), None, None, None))
+        off = off[:nm.value + 1].copy()
+        tot = int(off[-1])
+        xyz = np.empty((tot, 3), np.float64); rgb = np.empty((tot, 3), np.float64); ijk = np.empty((tot, 3), np.int32)
+        if tot:
+            self._ck(self.lib.hmsg_mask_store_read(self.h, int(frame), C.byref(nm), ptr(off), ptr(xyz), ptr(rgb), ptr(ijk)))
+        return off, xyz, rgb, ijk
+
+    def objects_merge_stored(self, frame_begin, n_frames):
+        """seq_merge iterations over stored frames (graph_utils.py:1015-1038), fed from HBM"""
+        self._ck(self.lib.hmsg_objects_merge_stored(self.h, int(frame_begin), int(n_frames)))
 
     # ------------------------------------------------------------------ N1 object instances
     def objects_begin(self, overlap_thresh=0.75, down_size=0.05, iou_thresh=0.05):
@@ -476,6 +509,67 @@ class HmsgEngine:
     def merge_partials(self, gathered, world, stride):
         self._ck(self.lib.hmsg_node_feats_merge(self.h, ptr(gathered), int(world), int(stride)))
         self.torch_wait()
+
+    # ------------------------------------------------------------------ multi-GPU through the C-ABI (NCCL inside the library)
+    def comm_init_torch(self):
+        """Give the ctx its own NCCL communicator; the 128-byte unique id travels over the already
+        initialised torch.distributed group (plumbing only - every data-path collective runs inside
+        libhmsg_b200.so on the ctx stream)."""
+        import torch
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        uid = np.zeros(128, np.uint8)
+        if rank == 0:
+            rc = self.lib.hmsg_comm_unique_id(ptr(uid))
+            if rc != 0:
+                raise HmsgError("hmsg_comm_unique_id failed (NCCL not loadable)")
+        t = torch.from_numpy(uid)
+        if dist.get_backend() == "nccl":
+            t = t.to(torch.device("cuda", self.device))
+        dist.broadcast(t, 0)
+        uid = t.cpu().numpy().copy()
+        self._ck(self.lib.hmsg_comm_init(self.h, ptr(uid), int(rank), int(world)))
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_init_local(self, uid=None, rank=0, world=1):
+        """communicator without torch.distributed: uid = bytes from comm_unique_id() of rank 0 (world 1: made here)"""
+        if uid is None:
+            uid = self.comm_unique_id()
+        uid = np.ascontiguousarray(np.frombuffer(bytes(uid), dtype=np.uint8))
+        self._ck(self.lib.hmsg_comm_init(self.h, ptr(uid), int(rank), int(world)))
+        self.comm_rank, self.comm_world = rank, world
+
+    def comm_unique_id(self) -> bytes:
+        uid = np.zeros(128, np.uint8)
+        if self.lib.hmsg_comm_unique_id(ptr(uid)) != 0:
+            raise HmsgError("hmsg_comm_unique_id failed (NCCL not loadable)")
+        return uid.tobytes()
+
+    def comm_info(self):
+        r, w, b = C.c_int32(), C.c_int32(), C.c_double()
+        self._ck(self.lib.hmsg_comm_info(self.h, C.byref(r), C.byref(w), C.byref(b)))
+        return r.value, w.value, b.value
+
+    def voxel_build_sharded_c(self, ranges, comm=None):
+        """hmsg_voxel_build_sharded: this rank's frame ranges [(begin, n), ...], collectives inside the library"""
+        rg = np.ascontiguousarray(np.asarray(ranges, dtype=np.int64).reshape(-1, 2))
+        nv = C.c_int64(); mb = np.zeros(3, np.float64)
+        self._ck(self.lib.hmsg_voxel_build_sharded(self.h, C.c_void_p(comm) if comm else None, ptr(rg) if len(rg) else None, int(len(rg)), C.byref(nv), ptr(mb)))
+        self.n_voxels = nv.value
+        return nv.value, mb
+
+    def radius_filter_sharded(self, nb_points=1000, radius=1.0, comm=None):
+        n = C.c_int64(0)
+        self._ck(self.lib.hmsg_radius_filter_sharded(self.h, C.c_void_p(comm) if comm else None, int(nb_points), float(radius), C.byref(n)))
+        self.n_nodes = n.value
+        return n.value
+
+    def allgather_nodes(self, Fp_local=None, fp_floats=0, Fp_all=None, fp_stride=0, comm=None):
+        if Fp_all is not None:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_allgather_nodes(self.h, C.c_void_p(comm) if comm else None, ptr(Fp_local), int(fp_floats), ptr(Fp_all), int(fp_stride)))
+        if Fp_all is not None:
+            self.torch_wait()
 
     def gemm_debug(self, A_f16, W_f16, C_f32, M, N, K):
         self.wait_torch()

@@ -34,34 +34,44 @@ def _ns(d):
     return d
 
 
-class Graph:
-    def __init__(self, cfg, dataset=None, clip_model=None, preprocess=None, mask_generator=None, engine=None, clip_feat_dim=512):
-        """cfg: the reference's hydra config (dict / OmegaConf-like) - keys read here are the ones
-        the reference reads on the hot path (SURVEY appendix B): pipeline.voxel_size,
-        pipeline.skip_frames, pipeline.clip_bbox_margin, pipeline.clip_masked_weight,
-        pipeline.max_mask_distance.  dataset: an RGBDDataset-like object yielding
-        (rgb_image, depth_image, pose, rgb_intrinsics, depth_intrinsics) with .scale and
-        .depth_intrinsics (generic.py:19-33)."""
-        self.cfg = _ns(cfg) if isinstance(cfg, dict) else cfg
-        self.dataset = dataset
-        self.clip_model = clip_model
-        self.preprocess = preprocess
-        self.mask_generator = mask_generator
-        self.clip_feat_dim = clip_feat_dim
-        self.engine = engine or (clip_model.engine if clip_model is not None else get_engine(0))
-        self.full_pcd = PointCloud()
-        self.full_feats_array = None
-        self.mask_feats = []
-        self.mask_pcds = []
-        self.frames_feats = []
-        self.frames_pcd = []
+class _LazyFramesPcd:
+    """The reference's local `frames_pcd` (graph.py:371, :401): per frame the list of 3-D mask clouds.  They live in
+    the engine's HBM mask store; a frame is copied to the host only when somebody indexes it."""
+
+    def __init__(self, eng, frames):
+        self._eng, self._frames = eng, list(frames)
+
+    def __len__(self):
+        return len(self._frames)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[k] for k in range(*i.indices(len(self)))]
+        off, xyz, rgb, _ = self._eng.mask_store_read(self._frames[i])
+        return [to_o3d(PointCloud(xyz[off[j]:off[j + 1]], rgb[off[j]:off[j + 1]])) for j in range(len(off) - 1)]
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+class B200HotPath:
+    """The hot half of the reference's Graph on libhmsg_b200.so, written as a MIXIN: every method has the reference's
+    name and signature, so `class Graph(B200HotPath, <reference Graph>)` (see `dropin_graph_class`) lets the reference's
+    own glue - query_hierarchy_protected (graph.py:3593, what nav_agent's goal_pose_publisher.py:220 calls), room / floor
+    building, LLM reasoning - reach the B200 cores through normal method resolution.  `Graph` below is the same mixin
+    stand-alone (no reference checkout needed)."""
+
+    def _b200_init(self, engine=None, clip_feat_dim=None):
+        if clip_feat_dim is not None:
+            self.clip_feat_dim = clip_feat_dim
+        clip_model = getattr(self, "clip_model", None)
+        self.engine = engine or (getattr(clip_model, "engine", None) or get_engine(0))
         self.frame_global_feats = {}     # frame id -> F_g [d] (== get_img_feats(full frame), graph.py:1125-1129)
-        self.objects = []
-        self.rooms = []
-        self.floors = []
         self._index_epoch = 0
-        self.frame_batch = 16
-        self.keep_frames_pcd = True      # per-frame 3-D masks as host point clouds (the reference's local `frames_pcd`)
+        self.frame_batch = 32
+        self.merge_objects = True        # graph.py:424-488 (N1 + N2) after the ingest
+        self.exact_mask_sums = False     # True: per-frame create_3d_masks with Open3D's ordered float64 sums (bit-identical, slower)
+        self.views = getattr(self, "views", [])
 
     # ------------------------------------------------------------------ build (graph.py:262-415)
     def create_feature_map(self, save_path=None):
@@ -70,23 +80,32 @@ class Graph:
             return
         import torch
         eng, p = self.engine, self.cfg.pipeline
+        g = lambda k, dflt: getattr(p, k, dflt) if not isinstance(p, dict) else p.get(k, dflt)
         skip = int(p.skip_frames)
         ids = list(range(0, len(self.dataset), skip))
-        # ---- pass 1 (graph.py:339-345): frames -> resident HBM store
+        nF, FB = len(ids), int(self.frame_batch)
+        # ---- pass 1 (graph.py:339-345): frames -> resident HBM store, uploaded batch-wise on the copy stream
         first = self.dataset[ids[0]]
-        depth0 = np.array(first[1])
-        H, W = depth0.shape
-        eng.scene_begin(H, W, np.asarray(self.dataset.depth_intrinsics, dtype=np.float64), float(self.dataset.scale), float(p.voxel_size), len(ids))
+        H, W = np.array(first[1]).shape
+        eng.scene_begin(H, W, np.asarray(self.dataset.depth_intrinsics, dtype=np.float64), float(self.dataset.scale), float(p.voxel_size), nF)
         rgbs = []
-        for i in ids:
-            rgb_image, depth_image, pose, _, _ = self.dataset[i]
-            rgb = np.array(rgb_image).astype(np.uint8)
-            depth = np.array(depth_image).astype(np.uint16)
-            if rgb.shape[:2] != depth.shape[:2]:
-                import cv2
-                rgb = cv2.resize(rgb, (depth.shape[1], depth.shape[0]), interpolation=cv2.INTER_AREA)   # generic.py:98-104
-            eng.add_frames(depth[None], rgb[None], np.asarray(pose, dtype=np.float64).reshape(1, 16))
-            rgbs.append(rgb)
+        for b0 in range(0, nF, FB):
+            chunk = ids[b0:b0 + FB]
+            dd = np.empty((len(chunk), H, W), np.uint16); cc = np.empty((len(chunk), H, W, 3), np.uint8); pp = np.empty((len(chunk), 16), np.float64)
+            for k, i in enumerate(chunk):
+                rgb_image, depth_image, pose, _, _ = self.dataset[i]
+                depth = np.array(depth_image).astype(np.uint16)
+                rgb = np.array(rgb_image).astype(np.uint8)
+                if rgb.shape[:2] != depth.shape[:2]:
+                    # graph.py:378-379: the feature pass uses PIL `rgb_image.resize(depth_image.size)` (bicubic); the colours of
+                    # create_pcd come from a cv2 INTER_AREA resize (generic.py:98-104).  One image per frame is stored: the
+                    # feature-pass one (crops / embeddings match the reference; node colours differ slightly for such datasets)
+                    from PIL import Image
+                    rgb = np.asarray(Image.fromarray(rgb).resize((depth.shape[1], depth.shape[0])))
+                dd[k], cc[k], pp[k] = depth, rgb, np.asarray(pose, dtype=np.float64).reshape(16)
+                rgbs.append(rgb)
+            eng.put_frames_host(b0, dd, cc, pp)
+        eng.set_num_frames(nF)
         # ---- graph.py:348-358: voxel_down_sample, dbscan (identity), remove_radius_outlier
         eng.voxel_build()
         eng.radius_filter(1000, 1.0)
@@ -100,66 +119,325 @@ class Graph:
         except AttributeError:          # open3d objects do not take attributes: keep the side table on self
             pass
         self._frame_of = frame_of
+        sp = getattr(getattr(self.cfg, "main", None), "save_path", None)
+        if sp:
+            self.save_full_pcd(path=sp)         # graph.py:359
         # ---- pass 2 (graph.py:373-411)
         d = self.clip_feat_dim
         eng.features_begin(d)
-        g = lambda k, dflt: getattr(p, k, dflt) if not isinstance(p, dict) else p.get(k, dflt)
         merge_type = g("merge_type", "sequential")
-        if merge_type != "sequential":
-            raise NotImplementedError("pipeline.merge_type=%r: only the reference's default 'sequential' merge is on the device" % (merge_type,))
+        if merge_type not in ("sequential", "hierarchical"):
+            raise ValueError("pipeline.merge_type=%r (graph.py:425-443 knows 'hierarchical' and 'sequential')" % (merge_type,))
         max_mask_distance = float(g("max_mask_distance", float("inf")))
-        eng.objects_begin(float(g("init_overlap_thresh", 0.75)), float(p.voxel_size), float(g("iou_thresh", 0.05)))   # seq_merge args, graph.py:437-442
-        self.frames_pcd, self.frames_feats, self.frame_global_feats = [], [], {}
+        vs = float(p.voxel_size)
+        exact = bool(self.exact_mask_sums) and merge_type == "sequential" and self.merge_objects
+        if exact:
+            eng.objects_begin(float(g("init_overlap_thresh", 0.75)), vs, float(g("iou_thresh", 0.05)))   # seq_merge args, graph.py:437-442
+        eng.mask_store_reset()
+        self.frames_feats, self.frame_global_feats = [], {}
         dev = f"cuda:{eng.device}"
-        for b0 in range(0, len(ids), self.frame_batch):
-            chunk = ids[b0:b0 + self.frame_batch]
-            all_masks = [self.mask_generator.generate(rgbs[b0 + k]) for k in range(len(chunk))]   # SAM: outside the hot path
-            M = max(len(m) for m in all_masks)
-            if M == 0:
-                continue
+        bufs, events = [None, None], [None, None]
+        kept = []                                 # (b0, n, M, counts, Fp device, Fg device)
+        for bi, b0 in enumerate(range(0, nF, FB)):
+            chunk = ids[b0:b0 + FB]
             n = len(chunk)
-            seg = np.zeros((n, M, H, W), np.uint8)
+            all_masks = [self.mask_generator.generate(rgbs[b0 + k]) for k in range(n)]   # SAM: outside the hot path
+            counts = np.array([len(m) for m in all_masks], np.int32)
+            M = int(counts.max()) if n else 0
+            if M == 0:
+                kept.append((b0, n, 0, counts, None, None))
+                continue
+            # dense masks -> pinned staging (double buffered: the GPU works on batch i while the host fills batch i+1)
+            slot = bi & 1
+            need = n * M * H * W
+            if bufs[slot] is None or bufs[slot].numel() < need:
+                bufs[slot] = torch.empty(need, dtype=torch.uint8).pin_memory()
+            if events[slot] is not None:
+                events[slot].synchronize()
+            seg = bufs[slot][:need].view(n, M, H, W)
+            segn = seg.numpy()
             boxes = np.zeros((n, M, 4), np.int32)
+            boxes[:, :, 2:] = 1                     # padded slots: an empty mask on a 1-pixel box
             for k, ms in enumerate(all_masks):
                 for j, m in enumerate(ms):
-                    seg[k, j] = np.asarray(m["segmentation"]).astype(np.uint8)
-                    boxes[k, j] = [int(v) for v in m["bbox"]]
-                for j in range(len(ms), M):       # pad with an empty mask on a 1-pixel box (never wins a pixel)
-                    boxes[k, j] = (0, 0, 1, 1)
+                    segn[k, j] = m["segmentation"]
+                    boxes[k, j] = m["bbox"]
+                if len(ms) < M:
+                    segn[k, len(ms):] = 0
             eng.masks_dense(b0, seg)
+            events[slot] = torch.cuda.Event()
+            events[slot].record(eng.torch_stream())
+            eng.masks_counts(b0, counts)            # ragged SAM output: the softmax of extractor.py:168-172 runs over the frame's own masks
             feats = torch.empty((n * (2 * M + 1), d), dtype=torch.float32, device=dev)
             eng.encode_crops(b0, n, M, boxes, int(p.clip_bbox_margin), feats)     # crops + preprocess + encoder, fused
             Fp = eng.fuse_scatter(b0, n, M, feats.view(n, 2 * M + 1, d), float(p.clip_masked_weight),
                                   Fp_out=torch.empty((n, M, d), dtype=torch.float32, device=dev))
-            eng.torch_wait()
-            Fp = Fp.cpu()
-            Fg = feats.view(n, 2 * M + 1, d)[:, 2 * M].cpu().numpy()
-            for k, ms in enumerate(all_masks):
-                self.frame_global_feats[chunk[k]] = Fg[k]
-                self.frames_feats.append(Fp[k, :len(ms)])
-                if self.keep_frames_pcd:
-                    off, mx, mc, _ = eng.mask_nodes(b0 + k, float(p.voxel_size), M)
-                    self.frames_pcd.append([to_o3d(PointCloud(mx[off[j]:off[j + 1]], mc[off[j]:off[j + 1]])) for j in range(len(ms))])
-                # create_3d_masks + one seq_merge iteration (graph.py:391-402, :437-442), on the device
-                eng.objects_add_frame(b0 + k, float(p.voxel_size), max_mask_distance)
+            kept.append((b0, n, M, counts, Fp, feats.view(n, 2 * M + 1, d)[:, 2 * M].clone()))
+            # create_3d_masks for every frame of the batch (graph.py:391-402) -> HBM mask store
+            eng.mask_nodes_batch(b0, n, vs, max_mask_distance, keep=True)
+            if exact:
+                for k in range(n):                # + one seq_merge iteration per frame with ordered sums (graph.py:437-442)
+                    eng.objects_add_frame(b0 + k, vs, max_mask_distance)
+        # one pass of device -> host copies after the loop (no per-batch sync)
+        eng.torch_wait()
+        for (b0, n, M, counts, Fp, Fg) in kept:
+            Fp_h = Fp.cpu() if Fp is not None else None
+            Fg_h = Fg.cpu().numpy() if Fg is not None else None
+            for k in range(n):
+                self.frames_feats.append(Fp_h[k, :counts[k]] if Fp_h is not None else torch.zeros((0, d)))
+                if Fg_h is not None:
+                    self.frame_global_feats[ids[b0 + k]] = Fg_h[k]
+        self.frames_pcd = _LazyFramesPcd(eng, range(nF))
         # ---- graph.py:413-415
         self.full_feats_array = eng.node_feats_finalize()
-        # ---- graph.py:424-448: final merge + removal of masks with < 10 points -> self.mask_pcds
-        eng.objects_finish(10)
+        if not self.merge_objects:
+            return self.full_feats_array
+        # ---- graph.py:424-448: merge the 3-D masks into object instances, drop those with < 10 points -> self.mask_pcds
+        if merge_type == "hierarchical":
+            self._hierarchical_merge(nF, float(g("init_overlap_thresh", 0.75)), float(g("overlap_thresh_factor", 0.025)), vs, float(g("iou_thresh", 0.05)))
+        else:
+            if not exact:
+                eng.objects_begin(float(g("init_overlap_thresh", 0.75)), vs, float(g("iou_thresh", 0.05)))
+                eng.objects_merge_stored(0, nF)
+            eng.objects_finish(10)
         off, ox, oc = eng.objects_read()
         self.mask_pcds = [to_o3d(PointCloud(ox[off[j]:off[j + 1]], oc[off[j]:off[j + 1]])) for j in range(len(off) - 1)]
         # ---- graph.py:451-488: one feature per object (cosine-DBSCAN largest-cluster mean) -> self.mask_feats
-        feats = eng.object_feats(self.full_feats_array, float(p.voxel_size), 0.8, 0.01, 100) if len(self.mask_pcds) else np.zeros((0, d), np.float32)
+        feats = eng.object_feats(self.full_feats_array, vs, 0.8, 0.01, 100) if len(self.mask_pcds) else np.zeros((0, d), np.float32)
         self.mask_feats = [feats[j] for j in range(len(self.mask_pcds))]
         return self.full_feats_array
+
+    def _hierarchical_merge(self, nF, th, th_factor, down_size, proxy_th):
+        """graph.py:425-433 -> graph_utils.py:958-1012: merge adjacent frame lists level by level with a decreasing
+        threshold, then one more merge_3d_masks at 0.75 and the < 10 points removal.  Each pair merge is one
+        hmsg_objects_begin / add_masks / add_masks on the device; the ragged lists of a level cross the host."""
+        eng = self.engine
+        lists = [eng.mask_store_read(f)[:3] for f in range(nF)]
+        while len(lists) > 1:
+            nxt = []
+            for i in range(0, len(lists), 2):
+                if i == len(lists) - 1:
+                    nxt.append(lists[i])
+                    break
+                eng.objects_begin(th, down_size, proxy_th)
+                eng.objects_add_masks(*lists[i])
+                eng.objects_add_masks(*lists[i + 1])
+                nxt.append(eng.objects_read())
+            lists = nxt
+            if len(lists) > 1:
+                th -= th_factor * (len(lists) - 2) / max(1, len(lists) - 1)
+        eng.objects_begin(0.75, down_size, proxy_th)
+        if lists:
+            eng.objects_add_masks(*lists[0])
+        eng.objects_finish(10)
+
+    # ------------------------------------------------------------------ retrieval plumbing
+    def _text(self, queries: List[str], query_feats=None):
+        if query_feats is not None:
+            return np.asarray(query_feats, dtype=np.float32).reshape(len(queries), -1)
+        fn = getattr(self, "text_feats_fn", None)       # dropin_graph_class: the reference's own get_text_feats_multiple_templates
+        if fn is not None:
+            return np.float32(fn(list(queries)))
+        return np.float32(get_text_feats_multiple_templates(queries, self.clip_model, self.clip_feat_dim))
+
+    def _set_index(self, key, rows):
+        """object_embs = np.array([obj.embedding ...]) (graph.py:3126) -> one HBM matrix, cached.  The matrix lives in the
+        engine, so the tag of what it currently holds is kept ON the engine: another Graph (or a direct index_set) using
+        the same engine invalidates it.  Call invalidate_index() after editing embeddings in place."""
+        E = np.ascontiguousarray(np.asarray(rows, dtype=np.float32))
+        # the tag carries a digest of the matrix itself: equal lengths / recycled object ids can never alias a stale
+        # device copy (hashing a few MB is far cheaper than the upload it saves)
+        import hashlib
+        tag = (id(self), self._index_epoch, key, E.shape, hashlib.blake2b(E.tobytes(), digest_size=16).digest())
+        if getattr(self.engine, "_graph_index_tag", None) != tag:
+            d = E.shape[1]
+            if d % 128:
+                raise ValueError("embedding dimension must be a multiple of 128")
+            self.engine.index_set(E)
+            try:
+                self.engine._graph_index_tag = tag
+            except AttributeError:
+                pass
+        return self.engine
+
+    def invalidate_index(self):
+        """Forget the cached device matrix (objects / rooms were edited in place)."""
+        self._index_epoch += 1
+
+    # graph.py:1441-1454
+    def identify_object(self, object_feat, text_feats, classes):
+        eng = self._set_index(("labels",), text_feats)
+        sim = eng.query_scores(np.asarray(object_feat, dtype=np.float32).reshape(1, -1))
+        return classes[int(np.argmax(sim))]
+
+    # graph.py:2189-2214 (visualisation dropped)
+    def query_graph(self, query, query_feats=None):
+        q = self._text([query], query_feats)
+        eng = self._set_index(("objects", len(self.objects)), [o.embedding for o in self.objects])
+        ids, _ = eng.query_topk(q, min(5, len(self.objects)))
+        return self.objects[int(ids[0][0])]
+
+    # graph.py:3056-3162
+    def query_hmsg_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
+                          negative_prompt: List[str] = [], query_feats=None):
+        if query in negative_prompt:
+            query_id = negative_prompt.index(query)
+        else:
+            query_id = None
+        if query_id is None:
+            query = [query, *negative_prompt]
+            query_id = 0
+        else:
+            query = negative_prompt
+        q = self._text(query, query_feats)
+        room_ids_list = []
+        for obj in self.objects:
+            for i, room in enumerate(self.rooms):
+                if obj.room_id == room.room_id:
+                    room_ids_list.append(i)
+                    break
+        objects_list = None
+        if len(room_ids) != 0:
+            objects_list, room_ids_list = [], []
+            for i in room_ids:
+                src = self.floors[floor_id].rooms[i].objects if floor_id != -1 else self.rooms[i].objects
+                objects_list.extend(src)
+                room_ids_list.extend([i] * len(src))
+        if objects_list is None:
+            # the reference leaves `objects_list` undefined here (SURVEY H9); searching all objects is
+            # what its docstring promises ("Defaults to [], which means search from all rooms")
+            objects_list = list(self.objects)
+        if query_method != "clip":
+            return NotImplementedError
+        key = ("objsel", floor_id, tuple(room_ids), len(objects_list))
+        eng = self._set_index(key, [o.embedding for o in objects_list])
+        top_k_eff = min(top_k, len(objects_list))
+        top_index = None
+        if len(negative_prompt) > 0:
+            ids, sc, nf = eng.query_object(q[None], query_id, top_k_eff)
+            if nf[0] > 0:
+                top_index, scores = ids[0][:nf[0]], sc[0][:nf[0]]
+        if top_index is None:
+            ids, sc = eng.query_topk(q[query_id:query_id + 1], top_k_eff)
+            top_index, scores = ids[0], sc[0]
+        target_object_id = [objects_list[i].object_id for i in top_index]
+        target_object_score = [float(s) for s in scores]
+        target_room_id = [room_ids_list[i] for i in top_index]
+        target_id = [[i for i, x in enumerate(self.objects) if x.object_id == ti][0] for ti in target_object_id]
+        return target_id, target_room_id, target_object_score
+
+    # graph.py:3363-3481 (same core, returns (ids, room_ids))
+    def query_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
+                     negative_prompt: List[str] = [], query_feats=None):
+        tid, trid, _ = self.query_hmsg_object(query, floor_id, room_ids, query_method, top_k, negative_prompt, query_feats)
+        return tid, trid
+
+    # graph.py:3164-3272
+    def query_hmsg_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
+        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
+        q = self._text([query], query_feats)
+        rooms_list = self.rooms if floor_id == -1 else self.floors[floor_id].rooms
+        if query_method == "label" and is_room_text_valid:
+            embs = room_name_feats if room_name_feats is not None else self._text([r.name for r in rooms_list])     # :3198-3203
+            eng = self._set_index(("roomnames", floor_id, len(rooms_list)), embs)
+            sim = eng.query_scores(q)[0]
+            top_index = np.lexsort((np.arange(len(sim)), -sim))
+            tar = sim[top_index[0]]
+            same = [int(top_index[0])] + [int(i) for i in top_index[1:] if abs(sim[i] - tar) < 1e-3]      # :3216-3221
+            target_room_ids = [rooms_list[i].room_id for i in same]
+            return [i for i, x in enumerate(rooms_list) if x.room_id in target_room_ids]
+        rows, seg = [], []
+        for ri, room in enumerate(rooms_list):
+            e = np.stack(room.embeddings)
+            rows.append(e); seg.extend([ri] * len(e))
+        eng = self._set_index(("roomviews", floor_id, len(seg)), np.concatenate(rows))
+        sim = eng.query_scores(q)[0]
+        seg = np.asarray(seg)
+        room_max = np.array([sim[seg == ri].max() for ri in range(len(rooms_list))])                      # :3250-3253
+        order = sorted(range(len(rooms_list)), key=lambda r: room_max[r], reverse=True)
+        # :3259-3272: the reference builds a dict keyed by the trailing integer of the room id, so rooms "0_1" and "1_1"
+        # (floor_id = -1 on a multi-floor graph) collapse to one key that keeps its first position
+        out = list(dict.fromkeys(int(str(rooms_list[r].room_id).split("_")[-1]) for r in order))
+        return out[:min(len(out), 5 if is_room_text_valid else 10)]
+
+    # graph.py:2864-2897 (slow path: the goal view over ALL rooms' view embeddings)
+    def query_views(self, query, rooms_list=None, top_k: int = 24, query_feats=None):
+        """-> (best_image_id, top_image_ids, top_scores): `sims = dot(query_feats[0], stack(clip_embeddings).T)`,
+        `argmax`, `argsort(sims)[-top_k:][::-1]` with `top_k = min(24, len(sims))`; image ids come from
+        `room.sample_images` (asserted to align with `room.clip_embeddings`, :2870-2871)."""
+        rooms_list = self.rooms if rooms_list is None else rooms_list
+        q = self._text([query], query_feats)
+        ids, embs = [], []
+        for room in rooms_list:
+            assert len(room.sample_images) == len(room.clip_embeddings), \
+                f"Number of images ({len(room.sample_images)}) != embeddings ({len(room.clip_embeddings)})"
+            ids.extend(room.sample_images)
+            embs.extend(room.clip_embeddings)
+        if not embs:
+            return None, [], []
+        eng = self._set_index(("views", len(embs)), np.stack(embs))
+        k = min(top_k, len(embs))
+        top, sc = eng.query_topk(q[:1], k)
+        return ids[int(top[0][0])], [ids[int(i)] for i in top[0]], [float(v) for v in sc[0]]
+
+    # graph.py:2977-2984 (slow path: best object among those visible in the chosen view)
+    def rematch_in_view(self, query, object_ids_in_view, query_feats=None):
+        """-> (object_id, score) = argmax / max of dot(query_feats[0], embeddings of the view's objects)."""
+        q = self._text([query], query_feats)
+        by_id = {o.object_id: o for o in self.objects}
+        objs = [by_id[i] for i in object_ids_in_view]
+        if not objs:
+            return None, None
+        eng = self._set_index(("inview", tuple(object_ids_in_view)), [o.embedding for o in objs])
+        top, sc = eng.query_topk(q[:1], 1)
+        return objs[int(top[0][0])].object_id, float(sc[0][0])
+
+    # graph.py:2216-2258
+    def query_floor(self, query, query_method="clip", floor_name_feats=None, query_feats=None, zero_level_order_ids=None):
+        """A number in text form selects by floor level order (:2231-2237); otherwise the clip branch matches the query
+        against the text embeddings of "floor i" (:2239-2252; pass `floor_name_feats` / `query_feats` when the text tower
+        is not attached).  Second positional argument may also be the floor-name embedding matrix (round-1 signature)."""
+        if not isinstance(query_method, str):
+            floor_name_feats, query_method = query_method, "clip"
+        n_names = len(self.floors) if floor_name_feats is None else len(floor_name_feats)
+        if zero_level_order_ids is None and self.floors and n_names == len(self.floors) and all(hasattr(f, "floor_zero_level") for f in self.floors):
+            zero_level_order_ids = np.argsort([f.floor_zero_level for f in self.floors])           # :2231-2233
+        try:
+            i = int(query) - 1
+            return zero_level_order_ids[i] if zero_level_order_ids is not None else i
+        except BaseException:
+            pass
+        if query_method != "clip":
+            raise NotImplementedError("query_floor: only the 'clip' branch runs on the device (the 'gpt' branch is an LLM call)")
+        q = self._text([query], query_feats)
+        if floor_name_feats is None:
+            floor_name_feats = self._text(["floor " + str(i) for i in range(len(self.floors))])
+        eng = self._set_index(("floors",), floor_name_feats)
+        sim = eng.query_scores(q[:1])[0]
+        i = int(np.argsort(sim)[::-1][0])             # :2251 (ties -> the higher index, like the reference's argsort()[::-1])
+        return zero_level_order_ids[i] if zero_level_order_ids is not None else i
+
+    # graph.py:3277-3359 (view-embedding branch: per-room max, top 3)
+    def query_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
+        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
+        if query_method == "label" and is_room_text_valid:      # same label branch as query_hmsg_room (:3300-3334)
+            return self.query_hmsg_room(query, floor_id, "label", query_feats, room_name_feats)
+        # view-embedding branch, also taken for an "unknown" room text: three highest-ranking rooms (:3345-3359)
+        return self.query_hmsg_room("unknown", floor_id, "view_embedding", self._text([query], query_feats))[:3]
+
+
+class B200Standalone:
+    """What the stand-alone `Graph` adds on top of the mixin: the artefact I/O (graph.py:1892-1987, :3769-3990) and the
+    fast-path glue of query_hierarchy_protected (graph.py:3484-3716) with an injectable instruction parser.  In drop-in
+    mode (`dropin_graph_class`) these stay the reference's own methods."""
 
     # ------------------------------------------------------------------ N4: graphs built by the unmodified reference
     def load_hmsg_graph(self, path):
         """graph.py:1892-1987 (metadata only): floors / rooms / objects JSON -> node lists; the object
         embeddings are packed into one device matrix on the first query."""
         from holoagent_b200.memory.hmsg.graph.store import load_graph_nodes
-        self.floors, self.rooms, self.objects = load_graph_nodes(path)
-        self.objects = [o for o in self.objects if o.embedding is not None]
+        self.floors, self.rooms, self.objects, self.views = load_graph_nodes(path)
+        self.graph_path = path
         self.invalidate_index()
         return self
 
@@ -271,172 +549,117 @@ class Graph:
         print("number of masked pcds loaded from disk {}".format(len(self.mask_pcds)))
         return self.mask_pcds
 
-    # ------------------------------------------------------------------ retrieval plumbing
-    def _text(self, queries: List[str], query_feats=None):
-        if query_feats is not None:
-            return np.asarray(query_feats, dtype=np.float32).reshape(len(queries), -1)
-        return np.float32(get_text_feats_multiple_templates(queries, self.clip_model, self.clip_feat_dim))
+    # graph.py:3593-3716 / :3484-3591 (fast path; the slow `use_gpt` branch is LLM / VLM reasoning, out of scope)
+    BACKGROUND_LABELS = ["background", "divider", "ledge", "pillar", "tape", "stairs", "door", "doors", "stair", "window", "glass", "railing",
+                         "glass doors", "whiteboard", "sliding door", "carpet", "ceiling", "curtain"]
 
-    def _set_index(self, key, rows):
-        """object_embs = np.array([obj.embedding ...]) (graph.py:3126) -> one HBM matrix, cached.  The matrix lives in the
-        engine, so the tag of what it currently holds is kept ON the engine: another Graph (or a direct index_set) using
-        the same engine invalidates it.  Call invalidate_index() after editing embeddings in place."""
-        tag = (id(self), self._index_epoch, key)
-        if getattr(self.engine, "_graph_index_tag", None) != tag:
-            E = np.ascontiguousarray(np.asarray(rows, dtype=np.float32))
-            d = E.shape[1]
-            if d % 128:
-                raise ValueError("embedding dimension must be a multiple of 128")
-            self.engine.index_set(E)
-            try:
-                self.engine._graph_index_tag = tag
-            except AttributeError:
-                pass
-        return self.engine
+    def _parse_hier(self, query_instruction, icra=False):
+        """The reference parses "object X in room Y on floor Z" with an LLM prompt (llm_utils); a callable
+        `self.hier_query_parser(instruction) -> (floor_query, room_query, object_query)` is injected here."""
+        parser = getattr(self, "hier_query_parser", None)
+        if parser is None:
+            raise RuntimeError("query_hierarchy_protected: set graph.hier_query_parser (the LLM parse of the instruction is outside the hot path)")
+        return parser(query_instruction)
 
-    def invalidate_index(self):
-        """Forget the cached device matrix (objects / rooms were edited in place)."""
-        self._index_epoch += 1
+    def _hier_result(self, floor_id, room_ids, object_ids, res_dict):
+        return (self.floors[floor_id] if floor_id != -1 else None,
+                [self.floors[floor_id].rooms[k] for k in room_ids] if floor_id != -1 else [self.rooms[k] for k in room_ids],
+                [self.objects[i] for i in object_ids], res_dict)
 
-    # graph.py:1441-1454
-    def identify_object(self, object_feat, text_feats, classes):
-        eng = self._set_index(("labels", id(text_feats)), text_feats)
-        sim = eng.query_scores(np.asarray(object_feat, dtype=np.float32).reshape(1, -1))
-        return classes[int(np.argmax(sim))]
-
-    # graph.py:2189-2214 (visualisation dropped)
-    def query_graph(self, query, query_feats=None):
-        q = self._text([query], query_feats)
-        eng = self._set_index(("objects", len(self.objects)), [o.embedding for o in self.objects])
-        ids, _ = eng.query_topk(q, min(5, len(self.objects)))
-        return self.objects[int(ids[0][0])]
-
-    # graph.py:3056-3162
-    def query_hmsg_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
-                          negative_prompt: List[str] = [], query_feats=None):
-        if query in negative_prompt:
-            query_id = negative_prompt.index(query)
+    def query_hierarchy_protected(self, query_instruction: str, top_k: int = 1, use_gpt: bool = False):
+        """-> (Floor | None, [Room], [Object], res_dict): floor by number / clip, room by label match, objects by
+        embedding kNN with the reference's negative labels (graph.py:3608-3716)."""
+        import time
+        if use_gpt:
+            raise NotImplementedError("use_gpt=True is the slow VLM reasoning path (graph.py:3665-3680), outside the B200 hot path")
+        negative_labels = self.BACKGROUND_LABELS + ["monitor", "wall", "speaker"]
+        t0 = time.time()
+        floor_query, room_query, object_query = self._parse_hier(query_instruction)
+        res_dict = {"object_query": object_query, "room_query": room_query, "negative_labels": negative_labels, "LLM_Parse_Time": time.time() - t0}
+        floor_id = self.query_floor(floor_query) if floor_query is not None else -1
+        room_ids = self.query_hmsg_room(room_query, floor_id=floor_id, query_method="label") if room_query is not None else []
+        if object_query is not None:
+            object_ids, room_ids, object_scores = self.query_hmsg_object(object_query, floor_id=floor_id, room_ids=room_ids, top_k=top_k,
+                                                                         negative_prompt=negative_labels)
         else:
-            query_id = None
-        if query_id is None:
-            query = [query, *negative_prompt]
-            query_id = 0
+            object_ids, room_ids, object_scores = [], [], []
+        res_dict["object_scores"] = object_scores
+        return self._hier_result(floor_id, room_ids, object_ids, res_dict)
+
+    def query_hierarchy_protected_icra(self, query_instruction: str, top_k: int = 1, use_gpt: bool = False):
+        """graph.py:3484-3591: same flow with negative_labels = ["background"] (["wall"] for exhibition rooms)."""
+        import time
+        if use_gpt:
+            raise NotImplementedError("use_gpt=True is the slow VLM reasoning path, outside the B200 hot path")
+        negative_labels = ["background"]
+        t0 = time.time()
+        floor_query, room_query, object_query = self._parse_hier(query_instruction, icra=True)
+        llm = time.time() - t0
+        if "Exhibition" in room_query:
+            negative_labels = ["wall"]
+        floor_id = self.query_floor(floor_query) if floor_query is not None else -1
+        room_ids = self.query_hmsg_room(room_query, floor_id=floor_id, query_method="label") if room_query is not None else []
+        if object_query is not None:
+            object_ids, room_ids, _ = self.query_hmsg_object(object_query, floor_id=floor_id, room_ids=room_ids, top_k=top_k, negative_prompt=negative_labels)
         else:
-            query = negative_prompt
-        q = self._text(query, query_feats)
-        room_ids_list = []
-        for obj in self.objects:
-            for i, room in enumerate(self.rooms):
-                if obj.room_id == room.room_id:
-                    room_ids_list.append(i)
-                    break
-        objects_list = None
-        if len(room_ids) != 0:
-            objects_list, room_ids_list = [], []
-            for i in room_ids:
-                src = self.floors[floor_id].rooms[i].objects if floor_id != -1 else self.rooms[i].objects
-                objects_list.extend(src)
-                room_ids_list.extend([i] * len(src))
-        if objects_list is None:
-            # the reference leaves `objects_list` undefined here (SURVEY H9); searching all objects is
-            # what its docstring promises ("Defaults to [], which means search from all rooms")
-            objects_list = list(self.objects)
-        if query_method != "clip":
-            return NotImplementedError
-        key = ("objsel", floor_id, tuple(room_ids), len(objects_list))
-        eng = self._set_index(key, [o.embedding for o in objects_list])
-        top_k_eff = min(top_k, len(objects_list))
-        top_index = None
-        if len(negative_prompt) > 0:
-            ids, sc, nf = eng.query_object(q[None], query_id, top_k_eff)
-            if nf[0] > 0:
-                top_index, scores = ids[0][:nf[0]], sc[0][:nf[0]]
-        if top_index is None:
-            ids, sc = eng.query_topk(q[query_id:query_id + 1], top_k_eff)
-            top_index, scores = ids[0], sc[0]
-        target_object_id = [objects_list[i].object_id for i in top_index]
-        target_object_score = [float(s) for s in scores]
-        target_room_id = [room_ids_list[i] for i in top_index]
-        target_id = [[i for i, x in enumerate(self.objects) if x.object_id == ti][0] for ti in target_object_id]
-        return target_id, target_room_id, target_object_score
+            object_ids, room_ids = [], []
+        res_dict = {"room_query": room_query, "object_query": object_query, "negative_labels": negative_labels, "LLM_Parse_Time": llm,
+                    "FastMatching": 0.0, "ObjectInImageCheck": 0.0, "VLM_Rethinking": 0.0, "Re_Matching": 0.0, "Total_Time": 0.0}
+        return self._hier_result(floor_id, room_ids, object_ids, res_dict)
 
-    # graph.py:3363-3481 (same core, returns (ids, room_ids))
-    def query_object(self, query: str, floor_id: int = -1, room_ids: List[int] = [], query_method: str = "clip", top_k: int = 1,
-                     negative_prompt: List[str] = [], query_feats=None):
-        tid, trid, _ = self.query_hmsg_object(query, floor_id, room_ids, query_method, top_k, negative_prompt, query_feats)
-        return tid, trid
 
-    # graph.py:3164-3272
-    def query_hmsg_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
-        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
-        q = self._text([query], query_feats)
-        rooms_list = self.rooms if floor_id == -1 else self.floors[floor_id].rooms
-        if query_method == "label" and is_room_text_valid:
-            embs = room_name_feats if room_name_feats is not None else get_text_feats_multiple_templates(
-                [r.name for r in rooms_list], self.clip_model, self.clip_feat_dim)
-            eng = self._set_index(("roomnames", floor_id, len(rooms_list)), embs)
-            sim = eng.query_scores(q)[0]
-            top_index = np.lexsort((np.arange(len(sim)), -sim))
-            tar = sim[top_index[0]]
-            same = [int(top_index[0])] + [int(i) for i in top_index[1:] if abs(sim[i] - tar) < 1e-3]      # :3216-3221
-            target_room_ids = [rooms_list[i].room_id for i in same]
-            return [i for i, x in enumerate(rooms_list) if x.room_id in target_room_ids]
-        rows, seg = [], []
-        for ri, room in enumerate(rooms_list):
-            e = np.stack(room.embeddings)
-            rows.append(e); seg.extend([ri] * len(e))
-        eng = self._set_index(("roomviews", floor_id, len(seg)), np.concatenate(rows))
-        sim = eng.query_scores(q)[0]
-        seg = np.asarray(seg)
-        room_max = np.array([sim[seg == ri].max() for ri in range(len(rooms_list))])                      # :3250-3253
-        order = sorted(range(len(rooms_list)), key=lambda r: room_max[r], reverse=True)
-        out = [int(str(rooms_list[r].room_id).split("_")[-1]) for r in order]                             # :3262-3267
-        return out[:min(len(out), 5 if is_room_text_valid else 10)]
+class Graph(B200HotPath, B200Standalone):
+    """Stand-alone drop-in (no reference checkout needed): same constructor keywords as the mixin needs."""
 
-    # graph.py:2864-2897 (slow path: the goal view over ALL rooms' view embeddings)
-    def query_views(self, query, rooms_list=None, top_k: int = 24, query_feats=None):
-        """-> (best_image_id, top_image_ids, top_scores): `sims = dot(query_feats[0], stack(clip_embeddings).T)`,
-        `argmax`, `argsort(sims)[-top_k:][::-1]` with `top_k = min(24, len(sims))`; image ids come from
-        `room.sample_images` (asserted to align with `room.clip_embeddings`, :2870-2871)."""
-        rooms_list = self.rooms if rooms_list is None else rooms_list
-        q = self._text([query], query_feats)
-        ids, embs = [], []
-        for room in rooms_list:
-            assert len(room.sample_images) == len(room.clip_embeddings), \
-                f"Number of images ({len(room.sample_images)}) != embeddings ({len(room.clip_embeddings)})"
-            ids.extend(room.sample_images)
-            embs.extend(room.clip_embeddings)
-        if not embs:
-            return None, [], []
-        eng = self._set_index(("views", len(embs), id(rooms_list)), np.stack(embs))
-        k = min(top_k, len(embs))
-        top, sc = eng.query_topk(q[:1], k)
-        return ids[int(top[0][0])], [ids[int(i)] for i in top[0]], [float(v) for v in sc[0]]
+    def __init__(self, cfg, dataset=None, clip_model=None, preprocess=None, mask_generator=None, engine=None, clip_feat_dim=512):
+        """cfg: the reference's hydra config (dict / OmegaConf-like) - keys read here are the ones
+        the reference reads on the hot path (SURVEY appendix B): pipeline.voxel_size,
+        pipeline.skip_frames, pipeline.clip_bbox_margin, pipeline.clip_masked_weight,
+        pipeline.max_mask_distance, pipeline.merge_type.  dataset: an RGBDDataset-like object yielding
+        (rgb_image, depth_image, pose, rgb_intrinsics, depth_intrinsics) with .scale and
+        .depth_intrinsics (generic.py:19-33)."""
+        self.cfg = _ns(cfg) if isinstance(cfg, dict) else cfg
+        self.dataset = dataset
+        self.clip_model = clip_model
+        self.preprocess = preprocess
+        self.mask_generator = mask_generator
+        self.full_pcd = PointCloud()
+        self.full_feats_array = None
+        self.mask_feats = []
+        self.mask_pcds = []
+        self.frames_feats = []
+        self.frames_pcd = []
+        self.objects = []
+        self.rooms = []
+        self.floors = []
+        self.views = []
+        self._b200_init(engine, clip_feat_dim)
 
-    # graph.py:2977-2984 (slow path: best object among those visible in the chosen view)
-    def rematch_in_view(self, query, object_ids_in_view, query_feats=None):
-        """-> (object_id, score) = argmax / max of dot(query_feats[0], embeddings of the view's objects)."""
-        q = self._text([query], query_feats)
-        by_id = {o.object_id: o for o in self.objects}
-        objs = [by_id[i] for i in object_ids_in_view]
-        if not objs:
-            return None, None
-        eng = self._set_index(("inview", tuple(object_ids_in_view)), [o.embedding for o in objs])
-        top, sc = eng.query_topk(q[:1], 1)
-        return objs[int(top[0][0])].object_id, float(sc[0][0])
 
-    # graph.py:2238-2251 (clip branch; floors are few: the text embeddings of "floor i" are injected)
-    def query_floor(self, query, floor_name_feats, query_feats=None, zero_level_order_ids=None):
-        q = self._text([query], query_feats)
-        eng = self._set_index(("floors", id(floor_name_feats)), floor_name_feats)
-        top, _ = eng.query_topk(q[:1], 1)
-        i = int(top[0][0])
-        return zero_level_order_ids[i] if zero_level_order_ids is not None else i
+def dropin_graph_class(reference_graph_cls, text_feats_fn=None):
+    """`class Graph(B200HotPath, <reference Graph>)`: the reference's constructor, graph building, LLM glue
+    and I/O stay untouched; create_feature_map and every retrieval core resolve to libhmsg_b200.so first.  Usage on the
+    reference side (nav_agent/sem_nav_ctr/goal_pose_publisher.py:39, application scripts):
 
-    # graph.py:3277-3359 (view-embedding branch: per-room max, top 3)
-    def query_room(self, query: str, floor_id: int = -1, query_method: str = "view_embedding", query_feats=None, room_name_feats=None):
-        is_room_text_valid = query is not None and query != "" and "unknown" not in query.lower()
-        if query_method == "label" and is_room_text_valid:      # same label branch as query_hmsg_room (:3300-3334)
-            return self.query_hmsg_room(query, floor_id, "label", query_feats, room_name_feats)
-        # view-embedding branch, also taken for an "unknown" room text: three highest-ranking rooms (:3345-3359)
-        return self.query_hmsg_room("unknown", floor_id, "view_embedding", self._text([query], query_feats))[:3]
+        from hmsg.graph.graph import Graph as RefGraph
+        from holoagent_b200.memory.hmsg.graph.graph import dropin_graph_class
+        Graph = dropin_graph_class(RefGraph)
+
+    text_feats_fn(texts, clip_model, clip_feat_dim) -> [n, d]: the reference's get_text_feats_multiple_templates (its CLIP
+    text tower stays where it is); defaults to the one the reference module imported."""
+
+    class Graph(B200HotPath, reference_graph_cls):
+        def __init__(self, *args, engine=None, **kwargs):
+            reference_graph_cls.__init__(self, *args, **kwargs)
+            self._b200_init(engine, None)
+            fn = text_feats_fn
+            if fn is None:
+                import sys
+                mod = sys.modules.get(reference_graph_cls.__module__)
+                fn = getattr(mod, "get_text_feats_multiple_templates", None)
+            if fn is not None:
+                self.text_feats_fn = lambda texts, _fn=fn: _fn(texts, self.clip_model, self.clip_feat_dim)
+
+    Graph.__name__ = "Graph"
+    Graph.__qualname__ = "Graph"
+    return Graph

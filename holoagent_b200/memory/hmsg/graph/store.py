@@ -7,6 +7,7 @@ Schema followed (JSON metadata; the .ply clouds are not needed for retrieval):
                              "room_zero_level","embeddings","represent_images","sample_images","clip_embeddings"}
                             (room.py:309-333, load_new :354-374)
   floors/<floor_id>.json    {"floor_id","name","rooms","vertices","floor_height","floor_zero_level"} (floor.py:33-66)
+  views/<view_id>.json      {"view_id","room_id","img_id","object_ids","img_path","text_discription"} (view.py:62-72, :95-108)
   full_feats.pt / mask_feats.pt  torch.save of the node / mask feature arrays (graph.py:3797-3830)
 """
 from __future__ import annotations
@@ -51,38 +52,77 @@ class FloorNode:
         self.name = md.get("name")
         self.room_ids = md.get("rooms", [])
         self.rooms = []
+        self.floor_height = md.get("floor_height")
+        self.floor_zero_level = md.get("floor_zero_level", 0.0)
 
 
-def _read_dir(path, cls, sort_key):
+class ViewNode:
+    """views/<view_id>.json (view.py:62-72, load :95-108): the image a room keeps plus the objects visible in it"""
+
+    def __init__(self, md, view_id=None):
+        self.view_id = md.get("view_id", view_id)
+        self.room_id = md.get("room_id")
+        self.img_id = md.get("img_id")
+        self.img_path = md.get("img_path")
+        self.object_ids = md.get("object_ids", [])
+        self.text_discription = md.get("text_discription", [])
+        self.embedding = None
+
+
+def _read_dir(path, cls):
+    """Node files in the reference loader's order: `sorted(os.listdir())` of the file names (graph.py:1897-1930), i.e. by
+    the full id STRING ("0_10" before "0_2").  The reference enumerates the .ply clouds and reads the .json next to
+    each; graphs exported without clouds are enumerated by their .json files."""
+    if not os.path.isdir(path):
+        return []
+    names = sorted(os.listdir(path))
+    stems = [n[:-4] for n in names if n.endswith(".ply")]
+    if not stems:
+        stems = [n[:-5] for n in names if n.endswith(".json")]
     out = []
-    for fn in glob.glob(os.path.join(path, "*.json")):
+    for st in stems:
+        fn = os.path.join(path, st + ".json")
+        if not os.path.exists(fn):
+            continue
         with open(fn) as f:
-            out.append(cls(json.load(f)))
-    out.sort(key=sort_key)
+            out.append((st, cls(json.load(f))))
     return out
 
 
-def _tail_int(x):
-    try:
-        return int(str(x).split("_")[-1])
-    except ValueError:
-        return str(x)
-
-
 def load_graph_nodes(graph_path):
-    """graph_<timestamp>/{floors,rooms,objects}/ -> (floors, rooms, objects) with the cross links the
-    retrieval methods use (room.objects, floor.rooms)."""
-    objects = _read_dir(os.path.join(graph_path, "objects"), ObjectNode, lambda o: _tail_int(o.object_id))
-    rooms = _read_dir(os.path.join(graph_path, "rooms"), RoomNode, lambda r: _tail_int(r.room_id))
-    floors = _read_dir(os.path.join(graph_path, "floors"), FloorNode, lambda f: _tail_int(f.floor_id)) if os.path.isdir(
-        os.path.join(graph_path, "floors")) else []
-    by_id = {o.object_id: o for o in objects}
-    for r in rooms:
-        r.objects = [by_id[i] for i in r.object_ids if i in by_id]
+    """graph_<timestamp>/{floors,rooms,objects,views}/ -> (floors, rooms, objects, views) with the cross links the
+    retrieval methods use, built the way graph.py:1892-1987 builds them: an object's room is the "<floor>_<room>" prefix of
+    its file name (:1936, :1950), `room.objects` / `floor.rooms` are appended in load order."""
+    floors = [n for _, n in _read_dir(os.path.join(graph_path, "floors"), FloorNode)]
+    rooms = []
+    for st, r in _read_dir(os.path.join(graph_path, "rooms"), RoomNode):
+        r.room_id = st
+        rooms.append(r)
     rb = {r.room_id: r for r in rooms}
     for fl in floors:
-        fl.rooms = [rb[i] for i in fl.room_ids if i in rb]
-    return floors, rooms, objects
+        fl.rooms = []
+    for r in rooms:                                             # :1924-1926: floors[int(room.floor_id)].rooms.append(room)
+        try:
+            fl = floors[int(r.floor_id)]
+        except (ValueError, IndexError, TypeError):
+            fl = next((f for f in floors if str(f.floor_id) == str(r.floor_id)), None)
+        if fl is not None:
+            fl.rooms.append(r)
+    objects = []
+    for st, o in _read_dir(os.path.join(graph_path, "objects"), ObjectNode):
+        o.object_id = st
+        o.room_id = "_".join(st.split("_")[:2])
+        if o.embedding is None:                                 # an object without an embedding cannot be ranked; it is dropped
+            continue                                            # from BOTH lists so that room-restricted queries stay aligned
+        objects.append(o)
+        if o.room_id in rb:
+            rb[o.room_id].objects.append(o)                     # :1959 parent_room.add_object(objectt)
+    views = []
+    for st, v in _read_dir(os.path.join(graph_path, "views"), ViewNode):
+        v.view_id = st
+        v.room_id = "_".join(st.split("_")[:2])
+        views.append(v)
+    return floors, rooms, objects, views
 
 
 def load_feats_pt(path):

@@ -55,7 +55,8 @@ int32_t     hmsg_version(void);
 int32_t     hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value);
 /* Per-kernel-class device timing with CUDA events on the ctx stream (bench.py roofline).
  * class: 0 gemm (work = flops), 1 attention, 2 elementwise/LN, 3 knn pass (work = bytes of E
- * streamed), 4 pixel->node + winner, 5 feature scatter, 6 geometry passes, 7 crops.
+ * streamed), 4 pixel->node + winner, 5 feature scatter, 6 geometry passes, 7 crops, 8 per-mask 3-D node
+ * sets (A7), 9 NCCL exchanges (work = bytes this rank sent + received).
  * hmsg_prof_read synchronises, returns the summed event time / launch count / algorithmic
  * work since the last read and resets the class. */
 int32_t     hmsg_prof_enable(hmsg_ctx* ctx, uint32_t class_mask);
@@ -135,6 +136,12 @@ int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, i
 int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
                          const int32_t* xywh, int32_t on_device);
 
+/* Ragged SAM output (extractor.py:117-124 returns as many masks as SAM finds): counts [n_frames] int32 HOST,
+ * counts[i] <= M real masks in frame frame_begin + i of the batch just set with hmsg_masks_*.  Slots past the count
+ * are padding: they take no part in the softmax of A5 (extractor.py:168-172 runs over the frame's own masks),
+ * produce no 3-D mask in A7 and are not appended to the N1 merge list.  Without this call every slot is real. */
+int32_t hmsg_masks_counts(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, const int32_t* counts);
+
 /* A5+A6 for the batch whose masks were just set: given the encoder outputs of the batch,
  * feats [n, 2M+1, d] float32 unit rows ordered (M masked crops, M plain crops, 1 full
  * frame) = (cropped_masked_feats, cropped_feats, F_g) of extractor.py:147-158, computes
@@ -156,9 +163,24 @@ int32_t hmsg_pixel_feature_map(hmsg_ctx* ctx, int64_t frame, uint16_t* out_half)
  * were set: per mask the node positions hit by its pixels, re-voxelised (down_size) relative
  * to the mask's own min bound with pixel multiplicity as weight.  Ragged output: offsets
  * [M+1]; xyz/rgb [offsets[M],3] float64; ijk int32.  Call once with NULL data pointers to
- * get offsets, then again with buffers. */
+ * get offsets, then again with buffers.  The whole current mask batch is processed on the device
+ * once and cached; only the requested frame's rows are copied to the host. */
 int32_t hmsg_mask_nodes(hmsg_ctx* ctx, int64_t frame, double down_size, int64_t* offsets,
                         double* xyz, double* rgb, int32_t* ijk);
+/* A7 for a range of frames inside the current mask batch, results kept in HBM (the ingest path:
+ * graph.py:391-402 calls create_3d_masks for every frame and appends to frames_pcd).  filter_distance =
+ * cfg.pipeline.max_mask_distance (generic.py:126: a mask whose mean depth exceeds it yields an empty cloud).
+ * keep = 1 appends the frames to the mask store (ascending frame order), keep = 0 leaves them in a scratch
+ * area overwritten by the next call.  Voxel keys / counts are exact; means are sums of (pixel count x node
+ * centroid) in ascending node order, within 1e-12 of Open3D's per-pixel sequential sums. */
+int32_t hmsg_mask_nodes_batch(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, double down_size,
+                              double filter_distance, int32_t keep);
+int32_t hmsg_mask_store_reset(hmsg_ctx* ctx);
+int32_t hmsg_mask_store_count(hmsg_ctx* ctx, int64_t* n_frames, int64_t* n_masks, int64_t* n_points);
+/* one stored frame -> host: n_masks (real masks of the frame), offsets [n_masks+1], xyz/rgb [offsets[n_masks],3]
+ * float64, ijk int32; any output pointer may be NULL */
+int32_t hmsg_mask_store_read(hmsg_ctx* ctx, int64_t frame, int32_t* n_masks, int64_t* offsets, double* xyz,
+                             double* rgb, int32_t* ijk);
 
 /* ---- A9 encoder: open_clip ViT visual tower ------------------------------------------ */
 /* Supported: head dim 64 (width / heads), width / mlp / out_dim multiples of 256, image a multiple of patch,
@@ -257,6 +279,9 @@ int32_t hmsg_objects_add_masks(hmsg_ctx* ctx, int32_t n_masks, const int64_t* of
  * (hmsg_masks_*) and merged without leaving HBM.  Voxel sums run over the mask's pixels in row-major
  * order (stable sort), so the point sets are bit-identical to Open3D's sequential accumulation. */
 int32_t hmsg_objects_add_frame(hmsg_ctx* ctx, int64_t frame, double down_size, double filter_distance);
+/* The same iterations fed from the mask store (hmsg_mask_nodes_batch with keep = 1): frames
+ * [frame_begin, frame_begin + n_frames) in order, nothing visits the host but ragged offsets. */
+int32_t hmsg_objects_merge_stored(hmsg_ctx* ctx, int64_t frame_begin, int64_t n_frames);
 int32_t hmsg_objects_finish(hmsg_ctx* ctx, int32_t min_points, int64_t* n_objects, int64_t* n_points);
 /* current list (after finish: the objects, self.mask_pcds): offsets [n+1], xyz / rgb [n_points,3] -> host */
 int32_t hmsg_objects_read(hmsg_ctx* ctx, int64_t* offsets, double* xyz, double* rgb);
@@ -274,15 +299,37 @@ int32_t hmsg_object_feats(hmsg_ctx* ctx, const float* full_feats, int32_t d, dou
                           double max_dist, float eps, int32_t min_points, float* out,
                           int32_t on_device);
 
-/* ---- multi-GPU ------------------------------------------------------------ */
-/* One ncclAllGather of this rank's F_p rows + partial sum_features/counter is issued by the
- * caller's communicator; see holoagent_b200/dist.py.  The library exposes the device
- * buffers so the host side can hand them to NCCL without a copy. */
+/* ---- multi-GPU: frame-batch sharding over the GPUs of one box, NCCL over NVLink ---------- */
+/* One ctx (one process or thread) per GPU.  Either the library owns the communicator -
+ * hmsg_comm_unique_id on rank 0, the 128 bytes reach the other ranks by any means, hmsg_comm_init on every
+ * rank - or the caller supplies its own: every collective entry point takes `void* nccl_comm` (an ncclComm_t;
+ * NULL = the ctx's communicator).  NCCL is resolved with dlopen at the first call (the copy already loaded in
+ * the process, else HMSG_NCCL_LIB, else libnccl.so.2); failures return HMSG_ERR_NCCL. */
+int32_t hmsg_comm_unique_id(uint8_t id_out[128]);
+int32_t hmsg_comm_init(hmsg_ctx* ctx, const uint8_t id[128], int32_t rank, int32_t world);
+int32_t hmsg_comm_attach(hmsg_ctx* ctx, void* nccl_comm);
+/* rank / world of the ctx's communicator and the bytes this rank sent + received in the last hmsg_allgather_nodes */
+int32_t hmsg_comm_info(hmsg_ctx* ctx, int32_t* rank, int32_t* world, double* last_exchange_bytes);
+/* hmsg_voxel_build where this rank only touches its own frame ranges (int64 pairs (begin, count), HOST): local
+ * bounds / occupancy / accumulation merged by all-reduce(min) of 6 doubles, all-gather + OR of the bitmap and
+ * all-reduce(sum) of the f64 accumulators; every rank ends with the identical voxel table. */
+int32_t hmsg_voxel_build_sharded(hmsg_ctx* ctx, void* nccl_comm, const int64_t* ranges, int32_t n_ranges,
+                                 int64_t* n_voxels, double* min_bound_out);
+/* hmsg_radius_filter with the neighbour counts computed for this rank's slice of the voxel table and exchanged */
+int32_t hmsg_radius_filter_sharded(hmsg_ctx* ctx, void* nccl_comm, int32_t nb_points, double radius,
+                                   int64_t* n_nodes);
+/* The node-embedding merge: after every rank has scattered its own frames, sum_features / counter
+ * hold dense partials.  Row slices are exchanged all-to-all, the owner sums the `world` partials of its slice in
+ * rank order (deterministic) and the finished slices are all-gathered: every rank ends with the full sums.
+ * Optionally the per-frame mask embeddings (frames_feats, graph.py:402) are gathered in the same group:
+ * Fp_local (device, fp_stride_floats floats of which fp_floats are used) -> Fp_all [world, fp_stride_floats]
+ * (device); pass NULLs to skip. */
+int32_t hmsg_allgather_nodes(hmsg_ctx* ctx, void* nccl_comm, const float* Fp_local, int64_t fp_floats,
+                             float* Fp_all, int64_t fp_stride_floats);
+/* Building blocks of the torch.distributed form of the same merge (holoagent_b200/ingest.py drives either):
+ * device views of the partials, pack into one all-gather send buffer, rank-order sum of gathered partials. */
 int32_t hmsg_node_feats_device(hmsg_ctx* ctx, float** sum_features, float** counter,
                                int64_t* n_nodes, int32_t* d);
-/* dst (device) <- [sum_features n*d | counter n | Fp_rows fp_floats]: the send buffer of the
- * all-gather.  hmsg_node_feats_merge sums the `world` gathered partials (each `stride_floats`
- * apart) in rank order into sum_features / counter. */
 int32_t hmsg_node_feats_pack(hmsg_ctx* ctx, float* dst, const float* Fp_rows, int64_t fp_floats);
 int32_t hmsg_node_feats_merge(hmsg_ctx* ctx, const float* gathered, int32_t world,
                               int64_t stride_floats);

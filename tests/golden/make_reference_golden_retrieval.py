@@ -4,6 +4,10 @@ harness as make_reference_golden.py.  What executes is the reference's own sourc
   * Graph.query_room        graph.py:3277-3359
   * Graph.query_object      graph.py:3363-3481
   * Graph.identify_object   graph.py:1441-1454
+  * Graph.query_hierarchy_protected / _icra   graph.py:3593-3716 / :3484-3591 (fast path, use_gpt=False; the LLM parse of the
+    instruction - llm_utils, a network call - is replaced by a lookup table, exactly like the text tower)
+  * Graph.query_floor       graph.py:2216-2252
+  * a multi-floor graph queried with floor_id=-1 (rooms "0_1" and "1_1" collapse in the view-embedding branch, :3259-3272)
 The CLIP text tower is out of scope: `get_text_feats_multiple_templates` is replaced by a seeded lookup table keyed
 by string (the same substitution as in make_reference_golden.py).  Output: tests/golden/ref_retrieval.npz
 
@@ -33,7 +37,9 @@ D = 256
 
 def main():
     rs = np.random.RandomState(2024)
-    words = ["kitchen", "bedroom", "office", "corridor", "unknown area", "chair", "mug", "plant", "background", "floor 0", "floor 1"]
+    words = ["kitchen", "bedroom", "office", "corridor", "unknown area", "chair", "mug", "plant", "background", "floor 0", "floor 1",
+             "divider", "ledge", "pillar", "tape", "stairs", "door", "doors", "stair", "window", "glass", "railing", "glass doors", "whiteboard",
+             "sliding door", "carpet", "ceiling", "curtain", "monitor", "wall", "speaker"]
     tf = rs.randn(len(words), D).astype(np.float32); tf /= np.linalg.norm(tf, axis=1, keepdims=True)
     room_names = ["kitchen", "bed room", "office", "hall", "kitchen"]          # two rooms share a name -> identical label scores (tie window)
     name_tf = {"kitchen": tf[0], "bed room": tf[1] * 0.9 + tf[0] * 0.1, "office": tf[2], "hall": tf[3]}
@@ -75,6 +81,41 @@ def main():
             fl = obj_cases[ci][1] if obj_cases[ci][1] != [] else -1
             ids, rids = g.query_object(q, floor_id=fl, room_ids=rooms, top_k=k, negative_prompt=list(neg))
             out["obj_%d_ids" % ci] = np.array(ids, np.int64); out["obj_%d_rooms" % ci] = np.array(rids, np.int64)
+        # ---- the entry point the robot calls (goal_pose_publisher.py:220): instruction -> (floor, rooms, objects, res_dict)
+        parses = {"go to the chair in the kitchen": (None, "kitchen", "chair"),
+                  "find a mug in the office on floor 1": ("1", "office", "mug"),
+                  "bring me the plant": (None, "unknown area", "plant"),
+                  "the mug in the bedroom upstairs": ("floor 1", "bedroom", "mug")}
+        ref_graph.parse_hier_query_use_prompt_insentence_parse = lambda cfg, q: parses[q]
+        ref_graph.parse_hier_query_use_prompt_insentence_parse_icra = lambda cfg, q: parses[q]
+        g.cfg = None
+        for f, lvl in zip(g.floors, (0.0, 3.1)):
+            f.floor_zero_level = lvl
+        cwd = os.getcwd(); os.chdir("/tmp")            # the reference appends to room_obj_query_log.txt in the cwd
+        hier = []
+        for hi, (ins, tk) in enumerate([("go to the chair in the kitchen", 3), ("find a mug in the office on floor 1", 2), ("bring me the plant", 4),
+                                        ("the mug in the bedroom upstairs", 1)]):
+            for fn in ("query_hierarchy_protected", "query_hierarchy_protected_icra"):
+                fl, rooms, objs, res = getattr(g, fn)(ins, top_k=tk, use_gpt=False)
+                hier.append({"fn": fn, "instruction": ins, "top_k": tk, "parse": parses[ins], "floor": None if fl is None else fl.floor_id,
+                             "rooms": [r.room_id for r in rooms], "objects": [o.object_id for o in objs], "negative_labels": res["negative_labels"]})
+        os.chdir(cwd)
+        out["hier_cases"] = np.array(json.dumps(hier))
+        # ---- multi-floor graph, floor_id = -1: duplicate trailing room numbers
+        g2 = ref_graph.Graph.__new__(ref_graph.Graph)
+        g2.clip_model, g2.clip_feat_dim = None, D
+        mf_ids = ["0_0", "0_1", "1_0", "1_1", "1_2"]
+        mf_embs = []
+        for r in range(len(mf_ids)):
+            e = rs.randn(4 + r, D).astype(np.float32); e /= np.linalg.norm(e, axis=1, keepdims=True)
+            mf_embs.append((0.7 * e + 0.3 * tf[(r + 1) % 4]).astype(np.float32))
+        g2.rooms = [NS(room_id=mf_ids[r], name="room", embeddings=list(mf_embs[r]), objects=[]) for r in range(len(mf_ids))]
+        g2.floors = [NS(floor_id="0", rooms=g2.rooms[:2]), NS(floor_id="1", rooms=g2.rooms[2:])]
+        g2.objects = []
+        out["mf_room_ids"] = np.array(json.dumps(mf_ids)); out["mf_view_counts"] = np.array([len(e) for e in mf_embs]); out["mf_embs"] = np.concatenate(mf_embs)
+        for qi, q in enumerate(["kitchen", "office", "unknown area"]):
+            out["mf_hmsg_room_%d" % qi] = np.array(g2.query_hmsg_room(q, floor_id=-1, query_method="view_embedding"), np.int64)
+            out["mf_room_%d" % qi] = np.array(g2.query_room(q, floor_id=-1, query_method="view_embedding"), np.int64)
         classes = ["chair", "mug", "plant", "background"]
         label_feats = np.stack([table[c] for c in classes])
         out["identify"] = np.array(json.dumps([g.identify_object(emb[i], label_feats, classes) for i in range(0, n_obj, 7)]))

@@ -38,6 +38,28 @@ def check_retrieval_against_reference_run(engine):
         ids, rids = g.query_object(q, floor_id=fl, room_ids=rooms, top_k=k, negative_prompt=list(neg), query_feats=qf)
         assert ids == z["obj_%d_ids" % ci].tolist() and rids == z["obj_%d_rooms" % ci].tolist(), (ci, q, fl, rooms)
         n_checked += 1
+    # ---- the robot's entry point (goal_pose_publisher.py:220 -> graph.py:3593 / :3484): instruction -> floor, rooms, objects
+    table = {w: tf[i] for i, w in enumerate(words)}
+    table.update({n: name_feats[i] for i, n in enumerate(room_names)})
+    g.text_feats_fn = lambda texts: np.stack([table[t] for t in texts])
+    for f, lvl in zip(g.floors, (0.0, 3.1)):
+        f.floor_zero_level = lvl
+    for h in json.loads(str(z["hier_cases"])):
+        g.hier_query_parser = lambda ins, _p=tuple(h["parse"]): _p
+        fl, rooms, objs, res = getattr(g, h["fn"])(h["instruction"], top_k=h["top_k"], use_gpt=False)
+        assert (None if fl is None else fl.floor_id) == h["floor"], h
+        assert [r.room_id for r in rooms] == h["rooms"] and [o.object_id for o in objs] == h["objects"], h
+        assert res["negative_labels"] == h["negative_labels"]
+        n_checked += 1
+    # ---- multi-floor graph with floor_id = -1: rooms "0_1" / "1_1" collapse to one key (graph.py:3259-3272)
+    mf_ids = json.loads(str(z["mf_room_ids"])); mo = np.concatenate([[0], np.cumsum(z["mf_view_counts"])])
+    g2 = Graph({"pipeline": {}}, engine=engine, clip_feat_dim=emb.shape[1])
+    g2.rooms = [NS(room_id=mf_ids[r], name="room", embeddings=list(z["mf_embs"][mo[r]:mo[r + 1]]), objects=[]) for r in range(len(mf_ids))]
+    g2.floors = [NS(floor_id="0", rooms=g2.rooms[:2]), NS(floor_id="1", rooms=g2.rooms[2:])]
+    for qi, q in enumerate(["kitchen", "office", "unknown area"]):
+        assert g2.query_hmsg_room(q, floor_id=-1, query_method="view_embedding", query_feats=feat(q)) == z["mf_hmsg_room_%d" % qi].tolist(), q
+        assert g2.query_room(q, floor_id=-1, query_method="view_embedding", query_feats=feat(q)) == z["mf_room_%d" % qi].tolist(), q
+        n_checked += 2
     classes = json.loads(str(z["classes"]))
     label_feats = np.stack([tf[words.index(c)] for c in classes])
     assert [g.identify_object(emb[i], label_feats, classes) for i in range(0, len(emb), 7)] == json.loads(str(z["identify"]))

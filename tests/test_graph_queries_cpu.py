@@ -72,7 +72,8 @@ def test_room_view_floor_variants(tmp_path):
     assert best == ids[int(np.argmax(sims))] and top_ids == [ids[i] for i in top_idx] and np.allclose(sc, sims[top_idx], atol=1e-6)
     # re-match inside a view (graph.py:2977-2984)
     in_view = ["0_0_2", "0_1_3", "0_0_6"]
-    ref = np.dot(q[0], np.stack([o.embedding for o in g.objects if o.object_id in in_view]).astype(np.float32).T)
+    by_id = {o.object_id: o for o in g.objects}
+    ref = np.dot(q[0], np.stack([by_id[i].embedding for i in in_view]).astype(np.float32).T)
     oid, s = g.rematch_in_view("x", in_view, query_feats=q)
     assert oid == in_view[int(np.argmax(ref))] and abs(s - ref.max()) < 1e-6
     assert g.rematch_in_view("x", [], query_feats=q) == (None, None)

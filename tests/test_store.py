@@ -9,8 +9,11 @@ from holoagent_b200.memory.hmsg.graph.store import load_feats_pt, load_graph_nod
 
 def _write_graph(root, d=128):
     rs = np.random.RandomState(0)
-    for sub in ("objects", "rooms", "floors"):
+    for sub in ("objects", "rooms", "floors", "views"):
         os.makedirs(os.path.join(root, sub))
+    for v in ("0_0_3", "0_1_10", "0_1_2"):
+        json.dump({"view_id": v, "room_id": v[:3], "img_id": 7, "object_ids": [1, 2], "img_path": "a.png", "text_discription": ["x"]},
+                  open(os.path.join(root, "views", v + ".json"), "w"))
     embs = rs.randn(7, d)
     for i in range(7):
         md = {"object_id": f"0_{i % 2}_{i}", "vertices": rs.rand(8, 3).tolist(), "room_id": f"0_{i % 2}", "name": f"obj{i}",
@@ -28,12 +31,29 @@ def _write_graph(root, d=128):
 
 def test_load_graph_nodes(tmp_path):
     embs = _write_graph(str(tmp_path))
-    floors, rooms, objects = load_graph_nodes(str(tmp_path))
-    assert [o.object_id for o in objects] == [f"0_{i % 2}_{i}" for i in range(7)]
-    assert objects[5].embedding is None and objects[3].embedding.dtype == np.float64
-    assert np.array_equal(objects[3].embedding, embs[3])
-    assert [len(r.objects) for r in rooms] == [4, 3] and len(rooms[0].embeddings) == 3 and len(rooms[1].clip_embeddings) == 5
-    assert floors[0].rooms == rooms
+    floors, rooms, objects, views = load_graph_nodes(str(tmp_path))
+    # the reference loader's order: sorted file names = full id strings (graph.py:1912-1930); the object without an embedding
+    # is dropped from self.objects AND from its room's list (room-restricted queries index both)
+    assert [o.object_id for o in objects] == sorted(f"0_{i % 2}_{i}" for i in range(7) if i != 5)
+    by = {o.object_id: o for o in objects}
+    assert by["0_1_3"].embedding.dtype == np.float64 and np.array_equal(by["0_1_3"].embedding, embs[3])
+    assert [len(r.objects) for r in rooms] == [4, 2] and len(rooms[0].embeddings) == 3 and len(rooms[1].clip_embeddings) == 5
+    assert all(o in objects for r in rooms for o in r.objects)
+    assert floors[0].rooms == rooms and floors[0].floor_zero_level == 0.0
+    assert [v.view_id for v in views] == ["0_0_3", "0_1_10", "0_1_2"] and views[1].room_id == "0_1" and views[0].object_ids == [1, 2]
+
+
+def test_string_order_matches_reference_listing(tmp_path):
+    """ "0_10" sorts before "0_2" exactly like sorted(os.listdir()) in graph.py:1912"""
+    root = str(tmp_path)
+    for sub in ("objects", "rooms", "floors"):
+        os.makedirs(os.path.join(root, sub))
+    json.dump({"floor_id": "0", "name": "f", "rooms": [], "vertices": [], "floor_height": 3.0, "floor_zero_level": 0.0}, open(os.path.join(root, "floors", "0.json"), "w"))
+    for r in ("0_2", "0_10", "0_1"):
+        json.dump({"room_id": r, "name": r, "floor_id": "0", "objects": [], "views": [], "vertices": [], "room_height": 1, "room_zero_level": 0,
+                   "embeddings": [], "represent_images": [], "sample_images": [], "clip_embeddings": []}, open(os.path.join(root, "rooms", r + ".json"), "w"))
+    _, rooms, _, _ = load_graph_nodes(root)
+    assert [r.room_id for r in rooms] == ["0_1", "0_10", "0_2"]
 
 
 def test_feats_pt_roundtrip(tmp_path):
