@@ -83,6 +83,7 @@ SIGNATURES = {
     "hmsg_object_feats": (_i32, [_vp, _vp, _i32, C.c_double, C.c_double, C.c_float, _i32, _vp, _i32]),
     "hmsg_node_feats_device": (_i32, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_i32)]),
     "hmsg_masks_counts": (_i32, [_vp, _i64, _i32, _vp]),
+    "hmsg_masks_labels": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32]),
     "hmsg_mask_nodes_batch": (_i32, [_vp, _i64, _i32, C.c_double, C.c_double, _i32]),
     "hmsg_mask_store_reset": (_i32, [_vp]),
     "hmsg_mask_store_count": (_i32, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),

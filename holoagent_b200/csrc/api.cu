@@ -56,7 +56,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt); free_dev(ctx->nbitmap); free_dev(ctx->nprefix); free_dev(ctx->node_xyz);
   free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox); free_dev(ctx->sum_feats); free_dev(ctx->counter);
   free_dev(ctx->maskbits); free_dev(ctx->pix_idx); free_dev(ctx->win); free_dev(ctx->Fp); free_dev(ctx->feats_stage);
-  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage); free_dev(ctx->cbitmap); free_dev(ctx->far_list); free_dev(ctx->far_count); free_dev(ctx->mask_cnt);
+  free_dev(ctx->boxes_stage); free_dev(ctx->seg_stage); free_dev(ctx->cbitmap); free_dev(ctx->far_list); free_dev(ctx->far_count); free_dev(ctx->mask_cnt); free_dev(ctx->mask_rect);
   if (ctx->scratch) cudaFree(ctx->scratch);
   for (auto& pc : ctx->prof) for (auto e : pc.ev) cudaEventDestroy(e);
   for (auto e : ctx->upload_events) cudaEventDestroy(e);
@@ -107,12 +107,14 @@ extern "C" int32_t hmsg_prof_read(hmsg_ctx* ctx, int32_t cls, double* ms, int64_
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value);
 int32_t knn_set_option(hmsg_ctx* ctx, const char* key, int value);
 int32_t crops_set_option(hmsg_ctx* ctx, const char* key, int value);
+int32_t masks3d_set_option(hmsg_ctx* ctx, const char* key, int value);
 
 extern "C" int32_t hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value) {
   if (!ctx || !key) return HMSG_ERR_ARG;
   int32_t rc = vit_set_option(ctx, key, value);
   if (rc == -1) rc = knn_set_option(ctx, key, value);
   if (rc == -1) rc = crops_set_option(ctx, key, value);
+  if (rc == -1) rc = masks3d_set_option(ctx, key, value);
   if (rc == -1) return ctx->fail(HMSG_ERR_ARG, std::string("hmsg_set_option: unknown key ") + key);
   return rc;
 }

@@ -133,6 +133,8 @@ struct hmsg_ctx {
   std::vector<int> batch_counts;   // real masks per frame of the batch (ragged SAM output; <= batch_M)
   int32_t* mask_cnt = nullptr;     // device copy [batch_cap]
   size_t mask_cnt_bytes = 0;
+  int32_t* mask_rect = nullptr;    // [batch_cap, M, 4] pixel bounding box (x0, y0, x1, y1) exclusive of every mask (A7 scans it)
+  size_t mask_rect_bytes = 0;
   uint32_t* maskbits = nullptr;    // [batch_cap, H*W, MW]
   size_t maskbits_bytes = 0;
   int32_t* pix_idx = nullptr;      // [batch_cap, H*W]

@@ -126,12 +126,29 @@ constexpr int OUT_STAGE_BYTES = BM * 128;    // 16 KB: 128 rows x one 128-byte s
 constexpr int GEMM_THREADS = 640;            // 4 control warps + 16 epilogue warps
 constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
-enum { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU = 1, EPI_F32_RESIDUAL = 2, EPI_F32_STORE = 3 };
+// EPI_F16_LN / EPI_F16_LN_GELU: the GEMM consumes the fp16 residual stream x directly; LayerNorm is folded in:
+//   LN(x) W^T + b = rstd_r * (x W''^T - mean_r * sres_n) + b'_n,  W''[n,k] = gamma_k W[n,k] - mean_k(gamma W[n,:])  (rows sum to ~0,
+//   so the row mean of x drops out of the product; sres_n = what is left of the row sum after fp16 rounding), b' = b + W beta.
+//   mean_r / rstd_r come from per-row (sum, sum of squares) accumulated by the epilogue that wrote x.
+// EPI_F16_RESID_STATS: x_new = fp16(x_old + acc + bias) written in place (fp16 residual stream, like the reference's
+//   precision='fp16' tower, graph.py:117) + the row statistics of the ROUNDED values for the next LayerNorm.
+enum { EPI_F16_BIAS = 0, EPI_F16_BIAS_GELU = 1, EPI_F32_RESIDUAL = 2, EPI_F32_STORE = 3, EPI_F16_LN = 4, EPI_F16_LN_GELU = 5, EPI_F16_RESID_STATS = 6 };
 
 struct GemmArgs {
   int M, N, K;
   const float* bias;     // [N] or null
   int quick_gelu;
+  // folded-LayerNorm / fp16-residual epilogues
+  const float* sres;     // [N] residual row sums of the folded weight
+  const float2* stats_in;   // [rows * stat_stride][stat_parts] partial (sum, sumsq) of the A rows, summed in part order
+  float2* stats_out;        // [rows * stat_stride][stat_parts]: every (N tile, column group) owner writes its own part - no
+                            // atomics, no zeroing, bit-reproducible; null = not needed
+  int stat_parts;           // width / 64
+  const __half* resid;      // x_old (same buffer the output tile goes to)
+  long long ldr;            // row stride of resid in elements
+  int stat_stride;          // row r of this GEMM = stats row r * stat_stride (class-token rows: T)
+  float inv_w;              // 1 / width
+  float ln_eps;
 };
 
 // erf by Abramowitz-Stegun 7.1.26 (|error| < 1.5e-7, far inside the 1e-3 embedding contract):
@@ -148,7 +165,8 @@ __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.
 __device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   // erfc(z) = 1 / (1 + a1 z + ... + a6 z^6)^16  (Abramowitz-Stegun 7.1.28, |err| < 3e-7), with z = |x|/sqrt(2)
-  // folded into the coefficients: one MUFU.RCP per element, everything else on the packed FFMA2/FMUL2 pipe
+  // folded into the coefficients: one MUFU.RCP per element, everything else on the packed FFMA2/FMUL2 pipe.
+  // Branch-free form: gelu(x) = 0.5 x (1 + erf(x/sqrt2)) = max(x, 0) - 0.5 |x| erfc(|x|/sqrt2)  (both signs of x).
   const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
   float2 p = __ffma2_rn(make_float2(5.38297490e-06f, 5.38297490e-06f), ax, make_float2(4.88906371e-05f, 4.88906371e-05f));
   p = __ffma2_rn(p, ax, make_float2(3.80035744e-05f, 3.80035744e-05f));
@@ -158,9 +176,8 @@ __device__ __forceinline__ float2 gelu_erf2(float2 x) {
   p = __ffma2_rn(p, ax, make_float2(1.f, 1.f));
   float2 r = make_float2(rcp_approx(p.x), rcp_approx(p.y));
   r = __fmul2_rn(r, r); r = __fmul2_rn(r, r); r = __fmul2_rn(r, r); r = __fmul2_rn(r, r);      // ^16 = erfc(|x|/sqrt2)
-  float2 hh = __fmul2_rn(__fmul2_rn(x, make_float2(0.5f, 0.5f)), r);                            // 0.5 x erfc(|x|/sqrt2)
-  float2 d = __fadd2_rn(x, make_float2(-hh.x, -hh.y));
-  return make_float2(x.x > 0.f ? d.x : hh.x, x.y > 0.f ? d.y : hh.y);
+  const float2 t = __fmul2_rn(ax, r);
+  return __ffma2_rn(make_float2(-0.5f, -0.5f), t, make_float2(fmaxf(x.x, 0.f), fmaxf(x.y, 0.f)));
 }
 __device__ __forceinline__ float gelu_quick(float x) { return x / (1.0f + __expf(-1.702f * x)); }
 
@@ -177,6 +194,67 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const 
 __device__ __forceinline__ void tma_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// One warp's share of a 128-row x 64-column fp16 output chunk: 32 accumulator columns of TMEM lane `trow` -> bias / folded
+// LayerNorm / GELU / residual -> fp16 -> 128B-swizzled staging row.  xo = the thread's 32 x_old halfs (EPI_F16_RESID_STATS).
+template <int EPI>
+__device__ __forceinline__ void epi_f16_group(const uint32_t* r, const GemmArgs& g, int col, uint8_t* srow, int sw, int half, float mean, float rstd,
+                                              const uint4* xo, float& ssum, float& ssq) {
+  constexpr bool LN = (EPI == EPI_F16_LN || EPI == EPI_F16_LN_GELU);
+  constexpr bool GELU = (EPI == EPI_F16_BIAS_GELU || EPI == EPI_F16_LN_GELU);
+  const float* bp = g.bias ? g.bias + col : nullptr;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; q4++) {
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
+    if (LN) {
+      const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.sres + col) + q4 * 2), s1 = __ldg(reinterpret_cast<const float4*>(g.sres + col) + q4 * 2 + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+      const float2 nm = make_float2(-mean, -mean), rs = make_float2(rstd, rstd);       // packed FFMA2: two columns per instruction
+      float2 t0 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s0.x, s0.y), make_float2(v[0], v[1])), make_float2(b0.x, b0.y));
+      float2 t1 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s0.z, s0.w), make_float2(v[2], v[3])), make_float2(b0.z, b0.w));
+      float2 t2 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s1.x, s1.y), make_float2(v[4], v[5])), make_float2(b1.x, b1.y));
+      float2 t3 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s1.z, s1.w), make_float2(v[6], v[7])), make_float2(b1.z, b1.w));
+      v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y; v[6] = t3.x; v[7] = t3.y;
+    } else if (bp) {
+      float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+      float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
+      float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
+      v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
+    }
+    if (EPI == EPI_F16_RESID_STATS) {
+      const uint4 x4 = xo[q4];
+      const uint32_t xw[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        const float2 xf = __half22float2(*reinterpret_cast<const __half2*>(&xw[e]));
+        v[2 * e] += xf.x; v[2 * e + 1] += xf.y;
+      }
+    }
+    if (GELU) {
+      if (g.quick_gelu) {
+#pragma unroll
+        for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; e++) { float2 gg = gelu_erf2(make_float2(v[2 * e], v[2 * e + 1])); v[2 * e] = gg.x; v[2 * e + 1] = gg.y; }
+      }
+    }
+    uint32_t pk[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+      pk[e] = *reinterpret_cast<uint32_t*>(&hh);
+      if (EPI == EPI_F16_RESID_STATS) {        // statistics of the values the next GEMM will actually read
+        const float2 hf = __half22float2(hh);
+        ssum += hf.x + hf.y;
+        ssq = fmaf(hf.x, hf.x, fmaf(hf.y, hf.y, ssq));
+      }
+    }
+    *reinterpret_cast<uint4*>(srow + (((half * 4 + q4) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+  }
+}
 
 // Epilogue: 16 warps in two groups of 8 (two warps per TMEM lane quarter).  A group converts one
 // 128-row x 128-byte chunk of the accumulator tile (64 fp16 / 32 fp32 columns) into its own
@@ -264,7 +342,9 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // ===================== epilogue (16 warps) =====================
     // two groups of 8 warps; in a group two warps share each TMEM lane quarter and split the
     // chunk's columns (a warp loads 32 fp32 columns for fp16 output, 16 for fp32 output)
-    constexpr bool F16OUT = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU);
+    constexpr bool F16OUT = (EPI != EPI_F32_RESIDUAL && EPI != EPI_F32_STORE);
+    constexpr bool LN = (EPI == EPI_F16_LN || EPI == EPI_F16_LN_GELU);
+    constexpr bool RESID = (EPI == EPI_F16_RESID_STATS);
     constexpr int CH_COLS = F16OUT ? 64 : 32;       // columns per 128-byte staging row
     constexpr int WCOLS = CH_COLS / 2;              // columns per warp
     constexpr int NCH = BN / CH_COLS;
@@ -280,6 +360,29 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     int as = 0; uint32_t aph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb = tile / n_tiles, nb = tile % n_tiles;
+      const int row0 = mb * BM;
+      const long long grow = (long long)row0 + trow;
+      const bool row_ok = grow < g.M;
+      float mean = 0.f, rstd = 0.f, ssum = 0.f, ssq = 0.f;
+      if (LN && row_ok) {                            // row statistics written by the epilogue that produced x (independent of the accumulator)
+        const float2* sp = g.stats_in + grow * g.stat_stride * g.stat_parts;
+        float sx = 0.f, sy = 0.f;
+        for (int pt = 0; pt < g.stat_parts; pt++) { const float2 st = sp[pt]; sx += st.x; sy += st.y; }
+        mean = sx * g.inv_w;
+        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sy * g.inv_w), 0.f) + g.ln_eps);
+      }
+      uint4 xo[4];
+      if (RESID) {                                   // first chunk's x_old: in flight while the MMAs of this tile finish
+        const int c0 = nb * BN + grp * CH_COLS + half * WCOLS;
+        if (row_ok) {
+          const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + c0);
+#pragma unroll
+          for (int i = 0; i < 4; i++) xo[i] = xp[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) xo[i] = make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
@@ -292,35 +395,17 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         if (F16OUT) tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         tmem_ld_wait();
-        const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
-        if (F16OUT) {
+        if constexpr (F16OUT) {
+          epi_f16_group<EPI>(r, g, col0 + half * WCOLS, srow, sw, half, mean, rstd, xo, ssum, ssq);
+          if (RESID && ch + 2 < NCH) {              // next chunk's x_old: overlaps the staging barrier + TMA store of this one
+            if (row_ok) {
+              const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + col0 + 2 * CH_COLS + half * WCOLS);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; q4++) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
-            if (bp) {
-              float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
-              float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
-              float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
-              v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
+              for (int i = 0; i < 4; i++) xo[i] = xp[i];
             }
-            if (EPI == EPI_F16_BIAS_GELU) {
-              if (g.quick_gelu) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++) { float2 gg = gelu_erf2(make_float2(v[2 * e], v[2 * e + 1])); v[2 * e] = gg.x; v[2 * e + 1] = gg.y; }
-              }
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
-            const int c16 = half * 4 + q4;             // 16-byte chunk index inside the 128-byte row
-            *reinterpret_cast<uint4*>(srow + ((c16 ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         } else {
+          const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
 #pragma unroll
           for (int q8 = 0; q8 < 4; q8++) {
             float4 v;
@@ -333,11 +418,13 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + grp, 256);
         if (issuer) {
-          if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, mb * BM);
-          else tma_store_2d(&tmO, stg, col0, mb * BM);
+          if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, row0);
+          else tma_store_2d(&tmO, stg, col0, row0);
           tma_commit_group();
         }
       }
+      if (RESID && g.stats_out && row_ok)            // this thread's 64 of the row's 256 tile columns = part (nb, grp, half)
+        g.stats_out[grow * g.stat_stride * g.stat_parts + nb * 4 + grp * 2 + half] = make_float2(ssum, ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
@@ -485,63 +572,70 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp >= 4) {
     // ===================== epilogue (16 warps per CTA, own 128 TMEM lanes) =====================
-    constexpr bool F16OUT = (EPI == EPI_F16_BIAS || EPI == EPI_F16_BIAS_GELU);
-    constexpr int CH_COLS = F16OUT ? 64 : 32;
-    constexpr int WCOLS = CH_COLS / 2;
+    constexpr bool F16OUT = (EPI != EPI_F32_RESIDUAL && EPI != EPI_F32_STORE);
+    constexpr bool LN = (EPI == EPI_F16_LN || EPI == EPI_F16_LN_GELU);
+    constexpr bool RESID = (EPI == EPI_F16_RESID_STATS);
+    constexpr int CH_COLS = F16OUT ? 64 : 32;       // columns per 128-byte staging row
+    constexpr int WCOLS = CH_COLS / 2;              // columns per warp
     constexpr int NCH = BN / CH_COLS;
     const int ew = warp - 4;
-    const int q = ew & 3;
+    const int q = ew & 3;                            // == warp % 4: TMEM lane quarter of this warp
     const int half = (ew >> 2) & 1;
     const int grp = ew >> 3;
     uint8_t* stg = sO + grp * OUT_STAGE_BYTES;
-    const int trow = q * 32 + lane;
+    const int trow = q * 32 + lane;                  // row inside the tile == TMEM lane
     const bool issuer = (q == 0 && half == 0 && lane == 0);
     uint8_t* srow = stg + trow * 128;
     const int sw = trow & 7;
     int as = 0; uint32_t aph = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       int mb = tile / n_tiles, nb = tile % n_tiles;
+      const int row0 = mb * 256 + (int)rank * 128;
+      const long long grow = (long long)row0 + trow;
+      const bool row_ok = grow < g.M;
+      float mean = 0.f, rstd = 0.f, ssum = 0.f, ssq = 0.f;
+      if (LN && row_ok) {                            // row statistics written by the epilogue that produced x (independent of the accumulator)
+        const float2* sp = g.stats_in + grow * g.stat_stride * g.stat_parts;
+        float sx = 0.f, sy = 0.f;
+        for (int pt = 0; pt < g.stat_parts; pt++) { const float2 st = sp[pt]; sx += st.x; sy += st.y; }
+        mean = sx * g.inv_w;
+        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sy * g.inv_w), 0.f) + g.ln_eps);
+      }
+      uint4 xo[4];
+      if (RESID) {                                   // first chunk's x_old: in flight while the MMAs of this tile finish
+        const int c0 = nb * BN + grp * CH_COLS + half * WCOLS;
+        if (row_ok) {
+          const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + c0);
+#pragma unroll
+          for (int i = 0; i < 4; i++) xo[i] = xp[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; i++) xo[i] = make_uint4(0, 0, 0, 0);
+        }
+      }
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-      const int row0 = mb * 256 + (int)rank * 128;
 #pragma unroll 1
       for (int ch = grp; ch < NCH; ch += 2) {
-        if (issuer) tma_wait_read0();
+        if (issuer) tma_wait_read0();                // previous store out of this buffer has drained it
         named_bar_sync(1 + grp, 256);
         const int col0 = nb * BN + ch * CH_COLS;
         uint32_t r[WCOLS];
         if (F16OUT) tmem_ld_32x32(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         tmem_ld_wait();
-        const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
-        if (F16OUT) {
+        if constexpr (F16OUT) {
+          epi_f16_group<EPI>(r, g, col0 + half * WCOLS, srow, sw, half, mean, rstd, xo, ssum, ssq);
+          if (RESID && ch + 2 < NCH) {              // next chunk's x_old: overlaps the staging barrier + TMA store of this one
+            if (row_ok) {
+              const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + col0 + 2 * CH_COLS + half * WCOLS);
 #pragma unroll
-          for (int q4 = 0; q4 < 4; q4++) {
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
-            if (bp) {
-              float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
-              float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
-              float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
-              v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
+              for (int i = 0; i < 4; i++) xo[i] = xp[i];
             }
-            if (EPI == EPI_F16_BIAS_GELU) {
-              if (g.quick_gelu) {
-#pragma unroll
-                for (int e = 0; e < 8; e++) v[e] = gelu_quick(v[e]);
-              } else {
-#pragma unroll
-                for (int e = 0; e < 4; e++) { float2 gg = gelu_erf2(make_float2(v[2 * e], v[2 * e + 1])); v[2 * e] = gg.x; v[2 * e + 1] = gg.y; }
-              }
-            }
-            uint32_t pk[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) { __half2 hh = __floats2half2_rn(v[2 * e], v[2 * e + 1]); pk[e] = *reinterpret_cast<uint32_t*>(&hh); }
-            *reinterpret_cast<uint4*>(srow + (((half * 4 + q4) ^ sw) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
           }
         } else {
+          const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
 #pragma unroll
           for (int q8 = 0; q8 < 4; q8++) {
             float4 v;
@@ -551,7 +645,7 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             *reinterpret_cast<float4*>(srow + (((half * 4 + q8) ^ sw) << 4)) = v;
           }
         }
-        fence_proxy_async();
+        fence_proxy_async();                         // generic-proxy smem writes -> visible to the TMA (async proxy)
         named_bar_sync(1 + grp, 256);
         if (issuer) {
           if (EPI == EPI_F32_RESIDUAL) tma_reduce_add_2d(&tmO, stg, col0, row0);
@@ -559,6 +653,8 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_commit_group();
         }
       }
+      if (RESID && g.stats_out && row_ok)            // this thread's 64 of the row's 256 tile columns = part (nb, grp, half)
+        g.stats_out[grow * g.stat_stride * g.stat_parts + nb * 4 + grp * 2 + half] = make_float2(ssum, ssq);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
@@ -699,6 +795,86 @@ __global__ void __launch_bounds__(256) k_layernorm_f16(const float* __restrict__
   float4 v[NV];
 #pragma unroll
   for (int j = 0; j < NV; j++) v[j] = src[lane + 32 * j];
+  ln_row<NV>(v, gam, bet, lane, 1e-5f);
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    __half2 a = __floats2half2_rn(v[j].x, v[j].y), b = __floats2half2_rn(v[j].z, v[j].w);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&b));
+    reinterpret_cast<uint2*>(h + row * W)[lane + 32 * j] = pk;
+  }
+}
+
+// ---- folded LayerNorm (see the EPI_F16_LN comment): one warp per output row n of a Linear [N,K] that follows a LayerNorm
+__global__ void __launch_bounds__(256) k_fold_ln(const float* __restrict__ Wsrc, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                 const float* __restrict__ bias, int N, int K, __half* __restrict__ Wf, float* __restrict__ sres,
+                                                 float* __restrict__ bprime) {
+  int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const float* w = Wsrc + (long long)n * K;
+  double m = 0.0, bb = 0.0;
+  for (int k = lane; k < K; k += 32) { m += (double)gamma[k] * (double)w[k]; bb += (double)beta[k] * (double)w[k]; }
+  for (int o = 16; o > 0; o >>= 1) { m += __shfl_xor_sync(0xffffffffu, m, o); bb += __shfl_xor_sync(0xffffffffu, bb, o); }
+  const double mean = m / (double)K;
+  double rs = 0.0;
+  for (int k = lane; k < K; k += 32) {
+    const __half h = __float2half_rn((float)((double)gamma[k] * (double)w[k] - mean));
+    Wf[(long long)n * K + k] = h;
+    rs += (double)__half2float(h);
+  }
+  for (int o = 16; o > 0; o >>= 1) rs += __shfl_xor_sync(0xffffffffu, rs, o);
+  if (lane == 0) { sres[n] = (float)rs; bprime[n] = (float)((double)bias[n] + bb); }
+}
+
+// tokens -> fp16 residual stream + (sum, sum of squares) of the rounded row for the first folded LayerNorm
+template <int NV>
+__global__ void __launch_bounds__(256) k_embed_lnpre_f16(const float* __restrict__ patch, const float* __restrict__ cls, const float* __restrict__ pos,
+                                                         const float* __restrict__ gam, const float* __restrict__ bet, __half* __restrict__ x,
+                                                         float2* __restrict__ stats, long long rows, int T) {
+  constexpr int W = NV * 128;
+  constexpr int PARTS = W / 64;
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  long long b = row / T; int t = (int)(row % T);
+  const float4* src = (t == 0) ? reinterpret_cast<const float4*>(cls) : reinterpret_cast<const float4*>(patch + (b * (T - 1) + t - 1) * W);
+  const float4* pp = reinterpret_cast<const float4*>(pos + (long long)t * W);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    float4 a = src[lane + 32 * j], p = __ldg(pp + lane + 32 * j);
+    v[j] = make_float4(a.x + p.x, a.y + p.y, a.z + p.z, a.w + p.w);
+  }
+  ln_row<NV>(v, gam, bet, lane, 1e-5f);
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    __half2 a = __floats2half2_rn(v[j].x, v[j].y), c = __floats2half2_rn(v[j].z, v[j].w);
+    const float2 fa = __half22float2(a), fc = __half22float2(c);
+    s += (fa.x + fa.y) + (fc.x + fc.y);
+    q += fa.x * fa.x + fa.y * fa.y + fc.x * fc.x + fc.y * fc.y;
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&c));
+    reinterpret_cast<uint2*>(x + row * W)[lane + 32 * j] = pk;
+  }
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane < PARTS) stats[row * PARTS + lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+}
+
+// h = LN(x) with x in fp16 (ln_post on the class-token rows of the fp16 residual stream)
+template <int NV>
+__global__ void __launch_bounds__(256) k_layernorm_h2h(const __half* __restrict__ x, const float* __restrict__ gam, const float* __restrict__ bet,
+                                                       __half* __restrict__ h, long long rows, long long in_row_stride) {
+  constexpr int W = NV * 128;
+  long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint2* src = reinterpret_cast<const uint2*>(x + row * in_row_stride * W);
+  float4 v[NV];
+#pragma unroll
+  for (int j = 0; j < NV; j++) {
+    const uint2 u = src[lane + 32 * j];
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), c = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    v[j] = make_float4(a.x, a.y, c.x, c.y);
+  }
   ln_row<NV>(v, gam, bet, lane, 1e-5f);
 #pragma unroll
   for (int j = 0; j < NV; j++) {
@@ -1309,6 +1485,9 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 struct LayerW {
   float *ln1_g, *ln1_b, *bqkv, *bo, *ln2_g, *ln2_b, *bfc, *bproj;
   __half *wqkv, *wo, *wfc, *wproj;
+  // ln_1 folded into in_proj, ln_2 folded into c_fc (k_fold_ln)
+  __half *wqkv_f, *wfc_f;
+  float *sres_qkv, *bqkv_f, *sres_fc, *bfc_f;
 };
 
 struct VitState {
@@ -1322,7 +1501,11 @@ struct VitState {
   std::vector<void*> allocs;
   // workspaces for `cap` images
   int cap = 0;
-  float* x = nullptr;       // [cap*T, W] fp32 residual
+  float* x = nullptr;       // [cap*T, W] fp32 residual (ln_fold = 0)
+  __half* xh = nullptr;     // [cap*T, W] fp16 residual (ln_fold = 1)
+  float2* statsA = nullptr; // [cap*T][W/64] partial (sum, sumsq) of the rows of xh for ln_1
+  float2* statsB = nullptr; // ... for ln_2
+  bool ln_fold = true;      // LayerNorm folded into the consuming GEMM, fp16 residual stream
   __half* h = nullptr;      // [cap*T, W]
   __half* qkv = nullptr;    // [cap*T, 3W]   (aliases: patch-embed output fp32 [cap*(T-1), W])
   __half* gbuf = nullptr;   // [cap*T, mlp]  (aliases: im2col A0 fp16 [cap*(T-1), Kpad])
@@ -1400,6 +1583,11 @@ static int32_t launch_gemm2_t(hmsg_ctx* ctx, const CUtensorMap& ta, const CUtens
 static int g_gemm_2sm = -1;
 int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   if (!strcmp(key, "gemm_2sm")) { g_gemm_2sm = value; return HMSG_OK; }
+  if (!strcmp(key, "ln_fold")) {
+    if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(ln_fold): load the encoder first");
+    ctx->vit->ln_fold = value != 0;
+    return HMSG_OK;
+  }
   if (!strcmp(key, "last_layer_cls_only")) {
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(last_layer_cls_only): load the encoder first");
     ctx->vit->last_cls_only = value != 0;
@@ -1413,9 +1601,19 @@ int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   return -1;
 }
 
+// extra operands of the folded-LayerNorm / fp16-residual epilogues
+struct GemmExtra {
+  const float* sres = nullptr;
+  const float2* stats_in = nullptr;
+  float2* stats_out = nullptr;
+  const __half* resid = nullptr;
+  long long ldr = 0;
+  int stat_stride = 1;
+};
+
 // C = A[M,K] * Wt[N,K]^T with epilogue
 static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const __half* Wt, int M, int N, int K, const float* bias, void* out,
-                    int ldo, long long lda = 0) {
+                    int ldo, long long lda = 0, const GemmExtra* ex = nullptr) {
   if (N % BN != 0 || K % BK != 0 || M <= 0) return ctx->fail(HMSG_ERR_ARG, "gemm: N must be a multiple of 256 and K of 64");
   CUtensorMap ta, tb, to;
   int32_t rc;
@@ -1423,14 +1621,22 @@ static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const
   const bool two_sm = g_gemm_2sm != 0 && M > 128;
   if ((rc = make_tmap(ctx, vs, &ta, A, (uint64_t)M, (uint64_t)K, BM, 2, (uint64_t)lda))) return rc;
   if ((rc = make_tmap(ctx, vs, &tb, Wt, (uint64_t)N, (uint64_t)K, two_sm ? 128 : BN))) return rc;
-  const bool f16out = (epi == EPI_F16_BIAS || epi == EPI_F16_BIAS_GELU);
+  const bool f16out = (epi != EPI_F32_RESIDUAL && epi != EPI_F32_STORE);
   if ((rc = make_tmap(ctx, vs, &to, out, (uint64_t)M, (uint64_t)N, BM, f16out ? 2 : 4, (uint64_t)ldo))) return rc;
-  GemmArgs g{M, N, K, bias, vs->desc.quick_gelu};
+  GemmArgs g{};
+  g.M = M; g.N = N; g.K = K; g.bias = bias; g.quick_gelu = vs->desc.quick_gelu;
+  g.stat_stride = 1; g.inv_w = 1.0f / (float)K; g.ln_eps = 1e-5f; g.stat_parts = vs->desc.width / 64;
+  if (ex) { g.sres = ex->sres; g.stats_in = ex->stats_in; g.stats_out = ex->stats_out; g.resid = ex->resid; g.ldr = ex->ldr; g.stat_stride = ex->stat_stride; }
+  if ((epi == EPI_F16_LN || epi == EPI_F16_LN_GELU) && (!g.sres || !g.stats_in || !bias)) return ctx->fail(HMSG_ERR_ARG, "gemm: folded-LN epilogue without operands");
+  if (epi == EPI_F16_RESID_STATS && !g.resid) return ctx->fail(HMSG_ERR_ARG, "gemm: residual epilogue without x");
   if (two_sm) {
     switch (epi) {
       case EPI_F16_BIAS: return launch_gemm2_t<EPI_F16_BIAS>(ctx, ta, tb, to, g);
       case EPI_F16_BIAS_GELU: return launch_gemm2_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, to, g);
       case EPI_F32_RESIDUAL: return launch_gemm2_t<EPI_F32_RESIDUAL>(ctx, ta, tb, to, g);
+      case EPI_F16_LN: return launch_gemm2_t<EPI_F16_LN>(ctx, ta, tb, to, g);
+      case EPI_F16_LN_GELU: return launch_gemm2_t<EPI_F16_LN_GELU>(ctx, ta, tb, to, g);
+      case EPI_F16_RESID_STATS: return launch_gemm2_t<EPI_F16_RESID_STATS>(ctx, ta, tb, to, g);
       default: return launch_gemm2_t<EPI_F32_STORE>(ctx, ta, tb, to, g);
     }
   }
@@ -1438,6 +1644,9 @@ static int32_t gemm(hmsg_ctx* ctx, VitState* vs, int epi, const __half* A, const
     case EPI_F16_BIAS: return launch_gemm_t<EPI_F16_BIAS>(ctx, ta, tb, to, g);
     case EPI_F16_BIAS_GELU: return launch_gemm_t<EPI_F16_BIAS_GELU>(ctx, ta, tb, to, g);
     case EPI_F32_RESIDUAL: return launch_gemm_t<EPI_F32_RESIDUAL>(ctx, ta, tb, to, g);
+    case EPI_F16_LN: return launch_gemm_t<EPI_F16_LN>(ctx, ta, tb, to, g);
+    case EPI_F16_LN_GELU: return launch_gemm_t<EPI_F16_LN_GELU>(ctx, ta, tb, to, g);
+    case EPI_F16_RESID_STATS: return launch_gemm_t<EPI_F16_RESID_STATS>(ctx, ta, tb, to, g);
     default: return launch_gemm_t<EPI_F32_STORE>(ctx, ta, tb, to, g);
   }
 }
@@ -1447,6 +1656,7 @@ int32_t vit_destroy(hmsg_ctx* ctx) {
   if (!vs) return HMSG_OK;
   for (void* p : vs->allocs) cudaFree(p);
   free_dev(vs->x); free_dev(vs->h); free_dev(vs->qkv); free_dev(vs->gbuf); free_dev(vs->pooled); free_dev(vs->proj_out);
+  free_dev(vs->xh); free_dev(vs->statsA); free_dev(vs->statsB);
   free_dev(vs->in_stage); free_dev(vs->out_stage);
   delete vs;
   ctx->vit = nullptr;
@@ -1518,6 +1728,16 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
     if ((rc = to_f16(wo, &L.wo, (size_t)W * W))) return rc;
     if ((rc = to_f16(wfc, &L.wfc, (size_t)d.mlp * W))) return rc;
     if ((rc = to_f16(wpj, &L.wproj, (size_t)W * d.mlp))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.wqkv_f, (size_t)3 * W * W))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.wfc_f, (size_t)d.mlp * W))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.sres_qkv, (size_t)3 * W))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.bqkv_f, (size_t)3 * W))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.sres_fc, (size_t)d.mlp))) return rc;
+    if ((rc = dalloc(ctx, vs, &L.bfc_f, (size_t)d.mlp))) return rc;
+    k_fold_ln<<<(3 * W * 32 + 255) / 256, 256, 0, ctx->stream>>>(wqkv, L.ln1_g, L.ln1_b, L.bqkv, 3 * W, W, L.wqkv_f, L.sres_qkv, L.bqkv_f);
+    HMSG_LAUNCH_CHECK();
+    k_fold_ln<<<(d.mlp * 32 + 255) / 256, 256, 0, ctx->stream>>>(wfc, L.ln2_g, L.ln2_b, L.bfc, d.mlp, W, L.wfc_f, L.sres_fc, L.bfc_f);
+    HMSG_LAUNCH_CHECK();
   }
   vs->lnpost_g = take(W); vs->lnpost_b = take(W);
   {
@@ -1528,6 +1748,7 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
     HMSG_LAUNCH_CHECK();
   }
   HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (const char* e = getenv("HMSG_LN_FOLD")) vs->ln_fold = atoi(e) != 0;
   if (const char* e = getenv("HMSG_ATTN_SIMPLE")) vs->attn_simple = atoi(e) != 0;
   if (const char* e = getenv("HMSG_ATTN_V1")) vs->attn_v1 = atoi(e) != 0;
   return HMSG_OK;
@@ -1536,12 +1757,16 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
 static int32_t ensure_ws(hmsg_ctx* ctx, VitState* vs, int B) {
   if (B <= vs->cap) return HMSG_OK;
   free_dev(vs->x); free_dev(vs->h); free_dev(vs->qkv); free_dev(vs->gbuf); free_dev(vs->pooled); free_dev(vs->proj_out);
+  free_dev(vs->xh); free_dev(vs->statsA); free_dev(vs->statsB);
   vs->cap = 0;
   const hmsg_vit_desc& d = vs->desc;
   size_t R = (size_t)B * vs->T, W = d.width;
   size_t qkv_bytes = std::max(R * 3 * W * 2, (size_t)B * (vs->T - 1) * W * 4);
   size_t g_bytes = std::max(R * (size_t)d.mlp * 2, (size_t)B * (vs->T - 1) * vs->Kpad * 2);
   HMSG_CUDA(cudaMalloc((void**)&vs->x, R * W * 4));
+  HMSG_CUDA(cudaMalloc((void**)&vs->xh, R * W * 2));
+  HMSG_CUDA(cudaMalloc((void**)&vs->statsA, R * 8 * (W / 64)));
+  HMSG_CUDA(cudaMalloc((void**)&vs->statsB, R * 8 * (W / 64)));
   HMSG_CUDA(cudaMalloc((void**)&vs->h, R * W * 2));
   HMSG_CUDA(cudaMalloc((void**)&vs->qkv, qkv_bytes));
   HMSG_CUDA(cudaMalloc((void**)&vs->gbuf, g_bytes));
@@ -1580,26 +1805,10 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     HMSG_LAUNCH_CHECK();
   }
   if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
-  k_embed_lnpre<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->x, R, T);
-  HMSG_LAUNCH_CHECK();
   const float scale = 1.0f / sqrtf(64.0f);
-  for (int l = 0; l < d.layers; l++) {
-    const LayerW& L = vs->layers[l];
-    ctx->prof_begin(PROF_ELTWISE);
-    k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln1_g, L.ln1_b, vs->h, R, 1);
-    ctx->prof_end(PROF_ELTWISE, (double)R * W * 6);
-    HMSG_LAUNCH_CHECK();
-    // The tower's output is ln_post(x[:, 0]) @ proj: in the last block only the class-token row of every image is
-    // consumed.  K and V are still needed for all tokens; Q, attention, out-proj, ln_2 and the MLP run on that row
-    // alone (strided TMA views pick row b*T of h / x in place).  Same values as the full computation.
-    const bool cls_only = vs->last_cls_only && l == d.layers - 1 && T > 1 && !vs->attn_simple && !vs->attn_v1 && !vs->attn_v2;
-    const int q_tiles = cls_only ? 1 : (1 << 30);
-    if (!cls_only) {
-      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
-    } else {
-      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv + (size_t)W * W, (int)R, 2 * W, W, L.bqkv + W, vs->qkv + W, 3 * W))) return rc;
-      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, B, W, W, L.bqkv, vs->qkv, T * 3 * W, (long long)T * W))) return rc;
-    }
+  const bool cls_last = vs->last_cls_only && T > 1 && !vs->attn_simple && !vs->attn_v1 && !vs->attn_v2;
+  // attention launcher shared by both residual-stream forms: qkv [R,3W] -> h [R,W]
+  auto attention = [&](int q_tiles) -> int32_t {
     ctx->prof_begin(PROF_ATTN);
     if (T > 64 || vs->attn_flash) {
       const int Tp = (T + 15) / 16 * 16;
@@ -1649,6 +1858,70 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     }
     ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
     HMSG_LAUNCH_CHECK();
+    return HMSG_OK;
+  };
+  if (vs->ln_fold) {
+    // ---- fp16 residual stream, LayerNorms folded into the consuming GEMMs: per block 4 GEMMs + attention, no LN kernels
+    k_embed_lnpre_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->xh,
+                                                                                       vs->statsA, R, T);
+    HMSG_LAUNCH_CHECK();
+    for (int l = 0; l < d.layers; l++) {
+      const LayerW& L = vs->layers[l];
+      const bool cls_only = cls_last && l == d.layers - 1;
+      GemmExtra ex;
+      if (!cls_only) {
+        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = vs->statsA;
+        if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f, (int)R, 3 * W, W, L.bqkv_f, vs->qkv, 3 * W, 0, &ex))) return rc;
+      } else {   // last block: K, V for every token, Q for the class-token rows only (strided views)
+        ex = GemmExtra(); ex.sres = L.sres_qkv + W; ex.stats_in = vs->statsA;
+        if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f + (size_t)W * W, (int)R, 2 * W, W, L.bqkv_f + W, vs->qkv + W, 3 * W, 0, &ex))) return rc;
+        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = vs->statsA; ex.stat_stride = T;
+        if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f, B, W, W, L.bqkv_f, vs->qkv, T * 3 * W, (long long)T * W, &ex))) return rc;
+      }
+      if ((rc = attention(cls_only ? 1 : (1 << 30)))) return rc;
+      if (cls_only) {
+        ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = (long long)T * W; ex.stats_out = vs->statsB; ex.stat_stride = T;
+        if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->h, L.wo, B, W, W, L.bo, vs->xh, T * W, (long long)T * W, &ex))) return rc;
+        ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = vs->statsB; ex.stat_stride = T;
+        if ((rc = gemm(ctx, vs, EPI_F16_LN_GELU, vs->xh, L.wfc_f, B, d.mlp, W, L.bfc_f, vs->gbuf, d.mlp, (long long)T * W, &ex))) return rc;
+        ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = (long long)T * W;
+        if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->gbuf, L.wproj, B, W, d.mlp, L.bproj, vs->xh, T * W, 0, &ex))) return rc;
+        continue;
+      }
+      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = vs->statsB;
+      if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->h, L.wo, (int)R, W, W, L.bo, vs->xh, W, 0, &ex))) return rc;
+      ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = vs->statsB;
+      if ((rc = gemm(ctx, vs, EPI_F16_LN_GELU, vs->xh, L.wfc_f, (int)R, d.mlp, W, L.bfc_f, vs->gbuf, d.mlp, 0, &ex))) return rc;
+      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = vs->statsA;
+      if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->gbuf, L.wproj, (int)R, W, d.mlp, L.bproj, vs->xh, W, 0, &ex))) return rc;
+    }
+    k_layernorm_h2h<NV><<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->xh, vs->lnpost_g, vs->lnpost_b, vs->pooled, B, T);
+    HMSG_LAUNCH_CHECK();
+    if ((rc = gemm(ctx, vs, EPI_F32_STORE, vs->pooled, vs->wout, B, d.out_dim, W, nullptr, vs->proj_out, d.out_dim))) return rc;
+    k_l2norm_rows<<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->proj_out, dout, B, d.out_dim, normalize);
+    HMSG_LAUNCH_CHECK();
+    return HMSG_OK;
+  }
+  k_embed_lnpre<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->x, R, T);
+  HMSG_LAUNCH_CHECK();
+  for (int l = 0; l < d.layers; l++) {
+    const LayerW& L = vs->layers[l];
+    ctx->prof_begin(PROF_ELTWISE);
+    k_layernorm_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->x, L.ln1_g, L.ln1_b, vs->h, R, 1);
+    ctx->prof_end(PROF_ELTWISE, (double)R * W * 6);
+    HMSG_LAUNCH_CHECK();
+    // The tower's output is ln_post(x[:, 0]) @ proj: in the last block only the class-token row of every image is
+    // consumed.  K and V are still needed for all tokens; Q, attention, out-proj, ln_2 and the MLP run on that row
+    // alone (strided TMA views pick row b*T of h / x in place).  Same values as the full computation.
+    const bool cls_only = cls_last && l == d.layers - 1;
+    const int q_tiles = cls_only ? 1 : (1 << 30);
+    if (!cls_only) {
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, (int)R, 3 * W, W, L.bqkv, vs->qkv, 3 * W))) return rc;
+    } else {
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv + (size_t)W * W, (int)R, 2 * W, W, L.bqkv + W, vs->qkv + W, 3 * W))) return rc;
+      if ((rc = gemm(ctx, vs, EPI_F16_BIAS, vs->h, L.wqkv, B, W, W, L.bqkv, vs->qkv, T * 3 * W, (long long)T * W))) return rc;
+    }
+    if ((rc = attention(q_tiles))) return rc;
     if (cls_only) {
       if ((rc = gemm(ctx, vs, EPI_F32_RESIDUAL, vs->h, L.wo, B, W, W, L.bo, vs->x, T * W, (long long)T * W))) return rc;
       ctx->prof_begin(PROF_ELTWISE);

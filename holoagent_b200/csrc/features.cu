@@ -41,6 +41,17 @@ __global__ void __launch_bounds__(TPB) k_masks_boxes(const uint16_t* depth, long
   }
 }
 
+// label image form: pixel p belongs to mask labels[p] (a panoptic / instance-id image; negative or >= M: no mask)
+__global__ void __launch_bounds__(TPB) k_masks_labels(const int8_t* __restrict__ labels, const uint16_t* __restrict__ depth, long long frame0, float scale,
+                                                      int HW, int M, int MW, uint32_t* __restrict__ maskbits) {
+  int fb = blockIdx.y;
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= HW) return;
+  const int l = labels[(long long)fb * HW + p];
+  const bool ok = l >= 0 && l < M && __fdiv_rn((float)depth[(frame0 + fb) * HW + p], scale) > 0.0f;
+  for (int w = 0; w < MW; w++) maskbits[((long long)fb * HW + p) * MW + w] = (ok && (l >> 5) == w) ? (1u << (l & 31)) : 0u;
+}
+
 __global__ void __launch_bounds__(TPB) k_masks_dense(const uint8_t* seg, int HW, int M, int MW, uint32_t* maskbits) {
   int fb = blockIdx.y;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -288,6 +299,46 @@ __global__ void __launch_bounds__(TPB) k_finalize_feats(const float* __restrict_
   reinterpret_cast<float4*>(out)[i] = v;
 }
 
+// pixel bounding boxes of the masks: rectangles clipped to the frame / min-max over the set bits of dense masks
+__global__ void k_rects_from_boxes(const int32_t* __restrict__ boxes, int n, int H, int W, int32_t* __restrict__ rect) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int32_t* b = boxes + (long long)i * 4;
+  int x0 = max(b[0], 0), y0 = max(b[1], 0), x1 = min(b[0] + b[2], W), y1 = min(b[1] + b[3], H);
+  if (x1 <= x0 || y1 <= y0) { x0 = y0 = x1 = y1 = 0; }
+  rect[i * 4] = x0; rect[i * 4 + 1] = y0; rect[i * 4 + 2] = x1; rect[i * 4 + 3] = y1;
+}
+__global__ void k_rects_init(int32_t* __restrict__ rect, int n, int H, int W) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  rect[i * 4] = W; rect[i * 4 + 1] = H; rect[i * 4 + 2] = 0; rect[i * 4 + 3] = 0;
+}
+__global__ void __launch_bounds__(TPB) k_rects_from_bits(const uint32_t* __restrict__ maskbits, int HW, int W, int M, int MW, int32_t* __restrict__ rect) {
+  const int fb = blockIdx.y;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = p / W, x = p - y * W;
+  for (int w = 0; w < MW; w++) {
+    uint32_t bits = (p < HW) ? maskbits[((long long)fb * HW + p) * MW + w] : 0u;
+    uint32_t uni = __reduce_or_sync(0xffffffffu, bits);
+    while (uni) {
+      const int ml = __ffs(uni) - 1;
+      uni &= uni - 1;
+      const bool has = (bits >> ml) & 1u;
+      const unsigned b = __ballot_sync(0xffffffffu, has);
+      if (has) {
+        const int xmin = __reduce_min_sync(b, x), xmax = __reduce_max_sync(b, x), ymin = __reduce_min_sync(b, y), ymax = __reduce_max_sync(b, y);
+        if ((b & ((1u << (threadIdx.x & 31)) - 1u)) == 0u) {
+          int32_t* r = rect + ((long long)fb * M + w * 32 + ml) * 4;
+          if (xmin < r[0]) atomicMin(&r[0], xmin);
+          if (ymin < r[1]) atomicMin(&r[1], ymin);
+          if (xmax + 1 > r[2]) atomicMax(&r[2], xmax + 1);
+          if (ymax + 1 > r[3]) atomicMax(&r[3], ymax + 1);
+        }
+      }
+    }
+  }
+}
+
 __global__ void k_fill_i32(int32_t* a, int n, int32_t v) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] = v;
@@ -307,6 +358,7 @@ static int32_t ensure_batch(hmsg_ctx* ctx, int n_frames, int M) {
   if ((rc = ctx->reserve(&ctx->maskbits, &ctx->maskbits_bytes, (size_t)n_frames * hw * MW * 4))) return rc;
   if ((rc = ctx->reserve(&ctx->pix_idx, &ctx->pix_idx_bytes, (size_t)n_frames * hw * 4))) return rc;
   if ((rc = ctx->reserve(&ctx->mask_cnt, &ctx->mask_cnt_bytes, (size_t)std::max(n_frames, 64) * 4))) return rc;
+  if ((rc = ctx->reserve(&ctx->mask_rect, &ctx->mask_rect_bytes, (size_t)n_frames * M * 16))) return rc;
   ctx->batch_M = M; ctx->batch_MW = MW; ctx->batch_n = n_frames;
   ctx->pix_idx_for = -1;
   masks3d_invalidate_scratch(ctx);
@@ -349,6 +401,8 @@ extern "C" int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t 
   k_masks_boxes<<<grid, TPB, M * 16, ctx->stream>>>(ctx->depth, frame_begin, ctx->cam.H, ctx->cam.W, ctx->cam.scale, M, ctx->batch_MW, dbox,
                                                     ctx->maskbits);
   HMSG_LAUNCH_CHECK();
+  k_rects_from_boxes<<<(n * M + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(dbox, n * M, ctx->cam.H, ctx->cam.W, ctx->mask_rect);
+  HMSG_LAUNCH_CHECK();
   ctx->batch_begin = frame_begin;
   return HMSG_OK;
 }
@@ -367,6 +421,32 @@ extern "C" int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t 
   }
   dim3 grid((unsigned)((hw + TPB - 1) / TPB), n);
   k_masks_dense<<<grid, TPB, 0, ctx->stream>>>(dseg, (int)hw, M, ctx->batch_MW, ctx->maskbits);
+  HMSG_LAUNCH_CHECK();
+  k_rects_init<<<(n * M + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(ctx->mask_rect, n * M, ctx->cam.H, ctx->cam.W);
+  k_rects_from_bits<<<grid, TPB, 0, ctx->stream>>>(ctx->maskbits, (int)hw, ctx->cam.W, M, ctx->batch_MW, ctx->mask_rect);
+  HMSG_LAUNCH_CHECK();
+  ctx->batch_begin = frame_begin;
+  return HMSG_OK;
+}
+
+extern "C" int32_t hmsg_masks_labels(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, int32_t M, const int8_t* labels, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (frame_begin < 0 || n <= 0 || frame_begin + n > ctx->nframes || !labels || M > 127) return ctx->fail(HMSG_ERR_ARG, "hmsg_masks_labels: bad argument");
+  int32_t rc = ensure_batch(ctx, n, M);
+  if (rc) return rc;
+  size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
+  const int8_t* dl = labels;
+  if (!on_device) {
+    if ((rc = ctx->reserve(&ctx->seg_stage, &ctx->seg_stage_bytes, (size_t)n * hw))) return rc;
+    HMSG_CUDA(cudaMemcpyAsync(ctx->seg_stage, labels, (size_t)n * hw, cudaMemcpyHostToDevice, ctx->stream));
+    dl = (const int8_t*)ctx->seg_stage;
+  }
+  dim3 grid((unsigned)((hw + TPB - 1) / TPB), n);
+  ctx->wait_frames(frame_begin, n);
+  k_masks_labels<<<grid, TPB, 0, ctx->stream>>>(dl, ctx->depth, frame_begin, ctx->cam.scale, (int)hw, M, ctx->batch_MW, ctx->maskbits);
+  HMSG_LAUNCH_CHECK();
+  k_rects_init<<<(n * M + TPB - 1) / TPB, TPB, 0, ctx->stream>>>(ctx->mask_rect, n * M, ctx->cam.H, ctx->cam.W);
+  k_rects_from_bits<<<grid, TPB, 0, ctx->stream>>>(ctx->maskbits, (int)hw, ctx->cam.W, M, ctx->batch_MW, ctx->mask_rect);
   HMSG_LAUNCH_CHECK();
   ctx->batch_begin = frame_begin;
   return HMSG_OK;

@@ -298,6 +298,17 @@ class HmsgEngine:
         if dev:
             self.torch_wait()
 
+    def masks_labels(self, frame_begin, labels, M):
+        """instance-id image form: labels int8 [n,H,W] (numpy or torch CUDA), mask m = pixels with label m and depth > 0"""
+        dev = _is_dev(labels)
+        if not dev:
+            labels = np.ascontiguousarray(labels, dtype=np.int8)
+        if dev:
+            self.wait_torch()
+        self._ck(self.lib.hmsg_masks_labels(self.h, int(frame_begin), int(labels.shape[0]), int(M), ptr(labels), 1 if dev else 0))
+        if dev:
+            self.torch_wait()
+
     def masks_counts(self, frame_begin, counts):
         """ragged SAM output: counts[i] real masks in frame frame_begin + i of the batch just set (slots past it are padding)"""
         counts = np.ascontiguousarray(counts, dtype=np.int32)

@@ -52,7 +52,7 @@ class IngestJob:
 
     def __init__(self, eng, n_frames, frame_batch, M, d, boxes_dev, rank=0, world=1, crops="auto", maskedd_weight=0.4418, bbox_margin=50,
                  nb_points=1000, radius=1.0, a7=True, voxel_size=0.05, max_mask_distance=10000.0, collective="c", gather_fp=False,
-                 total_frames=None):
+                 total_frames=None, labels_dev=None):
         import torch
         self.torch = torch
         self.eng, self.F, self.FB, self.M, self.d = eng, n_frames, frame_batch, M, d
@@ -62,6 +62,7 @@ class IngestJob:
         self.w, self.margin, self.nb, self.radius = maskedd_weight, bbox_margin, nb_points, radius
         self.a7, self.vs, self.max_mask_distance = a7, voxel_size, max_mask_distance
         self.collective, self.gather_fp = collective, gather_fp
+        self.labels_dev = labels_dev          # int8 [n_frames,H,W] instance-id images: masks come from them instead of the rectangles
         self.my_batches = [(f0, min(frame_batch, n_frames - f0)) for f0 in range(0, n_frames, frame_batch)]
         self.n_local = n_frames
         self.nmax_local = -(-self.total // world)
@@ -97,7 +98,9 @@ class IngestJob:
             eng.mask_store_reset()
         for i, (b0, n) in enumerate(self.my_batches):
             B = n * (2 * M + 1)
-            if boxes_host is not None:
+            if self.labels_dev is not None:
+                eng.masks_labels(b0, self.labels_dev[b0:b0 + n], M)
+            elif boxes_host is not None:
                 eng.masks_boxes(b0, boxes_host[b0:b0 + n])          # host XYWH -> staged H2D inside
             else:
                 eng.masks_boxes(b0, self.boxes_dev[b0:b0 + n])

@@ -34,6 +34,31 @@ def _ns(d):
     return d
 
 
+def hierarchical_merge(eng, frames, th, th_factor, down_size, proxy_th):
+    """graph_utils.py:958-1012 on the device merge kernels: `frames` = per frame (offsets, xyz, rgb) ragged host lists.
+    Adjacent lists are merged level by level with a decreasing threshold (each pair = hmsg_objects_begin + two
+    hmsg_objects_add_masks: the first list is taken as is, adding the second merges `A + B`).  The last list is left in
+    the engine under threshold 0.75: the caller's hmsg_objects_finish applies the closing merge_3d_masks(.., 0.75) of
+    :1006-1011 and the `< 10 points` removal of graph.py:444-448."""
+    lists = [tuple(f) for f in frames]
+    while len(lists) > 1:
+        nxt = []
+        for i in range(0, len(lists), 2):
+            if i == len(lists) - 1:
+                nxt.append(lists[i])
+                break
+            eng.objects_begin(th, down_size, proxy_th)
+            eng.objects_add_masks(*lists[i])
+            eng.objects_add_masks(*lists[i + 1])
+            nxt.append(eng.objects_read())
+        lists = nxt
+        if len(lists) > 1:
+            th -= th_factor * (len(lists) - 2) / max(1, len(lists) - 1)
+    eng.objects_begin(0.75, down_size, proxy_th)
+    if lists:
+        eng.objects_add_masks(*lists[0])
+
+
 class _LazyFramesPcd:
     """The reference's local `frames_pcd` (graph.py:371, :401): per frame the list of 3-D mask clouds.  They live in
     the engine's HBM mask store; a frame is copied to the host only when somebody indexes it."""
@@ -119,7 +144,8 @@ class B200HotPath:
         except AttributeError:          # open3d objects do not take attributes: keep the side table on self
             pass
         self._frame_of = frame_of
-        sp = getattr(getattr(self.cfg, "main", None), "save_path", None)
+        main = self.cfg.get("main") if isinstance(self.cfg, dict) else getattr(self.cfg, "main", None)
+        sp = (main.get("save_path") if isinstance(main, dict) else getattr(main, "save_path", None)) if main is not None else None
         if sp:
             self.save_full_pcd(path=sp)         # graph.py:359
         # ---- pass 2 (graph.py:373-411)
@@ -208,28 +234,9 @@ class B200HotPath:
         return self.full_feats_array
 
     def _hierarchical_merge(self, nF, th, th_factor, down_size, proxy_th):
-        """graph.py:425-433 -> graph_utils.py:958-1012: merge adjacent frame lists level by level with a decreasing
-        threshold, then one more merge_3d_masks at 0.75 and the < 10 points removal.  Each pair merge is one
-        hmsg_objects_begin / add_masks / add_masks on the device; the ragged lists of a level cross the host."""
-        eng = self.engine
-        lists = [eng.mask_store_read(f)[:3] for f in range(nF)]
-        while len(lists) > 1:
-            nxt = []
-            for i in range(0, len(lists), 2):
-                if i == len(lists) - 1:
-                    nxt.append(lists[i])
-                    break
-                eng.objects_begin(th, down_size, proxy_th)
-                eng.objects_add_masks(*lists[i])
-                eng.objects_add_masks(*lists[i + 1])
-                nxt.append(eng.objects_read())
-            lists = nxt
-            if len(lists) > 1:
-                th -= th_factor * (len(lists) - 2) / max(1, len(lists) - 1)
-        eng.objects_begin(0.75, down_size, proxy_th)
-        if lists:
-            eng.objects_add_masks(*lists[0])
-        eng.objects_finish(10)
+        """graph.py:425-433 on the frames of the mask store"""
+        hierarchical_merge(self.engine, [self.engine.mask_store_read(f)[:3] for f in range(nF)], th, th_factor, down_size, proxy_th)
+        self.engine.objects_finish(10)
 
     # ------------------------------------------------------------------ retrieval plumbing
     def _text(self, queries: List[str], query_feats=None):

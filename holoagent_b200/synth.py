@@ -88,9 +88,11 @@ def _hash_u32(a: torch.Tensor) -> torch.Tensor:
 
 @torch.no_grad()
 def make_frames(frame_ids, H: int, W: int, depth_cut: float = 10.0, device="cpu",
-                hole_frac: float = 0.05):
+                hole_frac: float = 0.05, return_labels: bool = False):
     """Returns (depth uint16 [F,H,W] as int16-viewed torch.uint16, rgb uint8 [F,H,W,3],
-    poses float64 [F,4,4] numpy, K float64 [3,3] numpy)."""
+    poses float64 [F,4,4] numpy, K float64 [3,3] numpy) and, with return_labels, the surface every pixel sees as
+    int8 [F,H,W]: 0..5 the six room planes, 6..11 the boxes, -1 where depth is 0 (SAM-like instance masks for the
+    object layer: the same surface keeps its label across frames)."""
     frame_ids = np.asarray(frame_ids, dtype=np.int64)
     F = len(frame_ids)
     K = intrinsics(H, W)
@@ -101,6 +103,7 @@ def make_frames(frame_ids, H: int, W: int, depth_cut: float = 10.0, device="cpu"
                             torch.arange(W, device=dev, dtype=torch.float64), indexing="ij")
     dcam = torch.stack([(xs - K[0, 2]) / K[0, 0], (ys - K[1, 2]) / K[1, 1], torch.ones_like(xs)], -1)  # [H,W,3]
     depth_out = torch.empty((F, H, W), dtype=torch.int32, device=dev)
+    label_out = torch.empty((F, H, W), dtype=torch.int8, device=dev) if return_labels else None
     rgb_out = torch.empty((F, H, W, 3), dtype=torch.uint8, device=dev)
     pix = (torch.arange(H, device=dev).view(H, 1) * W + torch.arange(W, device=dev).view(1, W)).to(torch.int64)
     lo_room = torch.zeros(3, dtype=torch.float64, device=dev)
@@ -114,13 +117,18 @@ def make_frames(frame_ids, H: int, W: int, depth_cut: float = 10.0, device="cpu"
         # room: camera is inside -> exit distance
         t1 = (lo_room - o) * inv
         t2 = (hi_room - o) * inv
-        s = torch.maximum(t1, t2).min(-1).values
+        ex = torch.maximum(t1, t2).min(-1)
+        s = ex.values
+        if return_labels:
+            lab = (ex.indices * 2 + (torch.gather(t2, -1, ex.indices[..., None])[..., 0] >= torch.gather(t1, -1, ex.indices[..., None])[..., 0]).long())
         for b in range(boxes.shape[0]):
             ta = (boxes[b, :3] - o) * inv
             tb = (boxes[b, 3:] - o) * inv
             tn = torch.minimum(ta, tb).max(-1).values
             tf = torch.maximum(ta, tb).min(-1).values
             hit = (tn < tf) & (tn > 1e-6)
+            if return_labels:
+                lab = torch.where(hit & (tn < s), torch.full_like(lab, 6 + b), lab)
             s = torch.where(hit & (tn < s), tn, s)
         mm = torch.round(s * 1000.0)
         mm = torch.where((s > depth_cut) | (mm > 65535) | (mm < 1), torch.zeros_like(mm), mm)
@@ -129,12 +137,36 @@ def make_frames(frame_ids, H: int, W: int, depth_cut: float = 10.0, device="cpu"
         hole = (h % 10000) < int(hole_frac * 10000)
         mm = torch.where(hole, torch.zeros_like(mm), mm)
         depth_out[n] = mm.to(torch.int32)
+        if return_labels:
+            label_out[n] = torch.where(mm > 0, lab, torch.full_like(lab, -1)).to(torch.int8)
         h2 = _hash_u32(h + 0x9E3779B9)
         rgb_out[n, :, :, 0] = (h2 & 255).to(torch.uint8)
         rgb_out[n, :, :, 1] = ((h2 >> 8) & 255).to(torch.uint8)
         rgb_out[n, :, :, 2] = ((h2 >> 16) & 255).to(torch.uint8)
     depth_u16 = depth_out.to(torch.uint16) if hasattr(torch, "uint16") else depth_out
+    if return_labels:
+        return depth_u16, rgb_out, T, K, label_out
     return depth_u16, rgb_out, T, K
+
+
+N_INSTANCES = 12
+
+
+@torch.no_grad()
+def instance_masks(labels: torch.Tensor):
+    """labels int8 [F,H,W] (make_frames(return_labels=True)) -> (seg uint8 [F,12,H,W], xywh int32 [F,12,4]): one dense
+    mask per visible surface (what SAM's "segmentation" / "bbox" carry); an invisible surface is an empty mask on a
+    1-pixel box."""
+    F, H, W = labels.shape
+    ids = torch.arange(N_INSTANCES, device=labels.device, dtype=labels.dtype).view(1, -1, 1, 1)
+    seg = (labels[:, None] == ids)
+    rows = seg.any(-1); cols = seg.any(-2)                                  # [F,12,H], [F,12,W]
+    ar_h = torch.arange(H, device=labels.device); ar_w = torch.arange(W, device=labels.device)
+    y0 = torch.where(rows, ar_h, H).amin(-1); y1 = torch.where(rows, ar_h, -1).amax(-1)
+    x0 = torch.where(cols, ar_w, W).amin(-1); x1 = torch.where(cols, ar_w, -1).amax(-1)
+    empty = y1 < 0
+    xywh = torch.stack([torch.where(empty, 0, x0), torch.where(empty, 0, y0), torch.where(empty, 1, x1 - x0 + 1), torch.where(empty, 1, y1 - y0 + 1)], -1)
+    return seg.to(torch.uint8), xywh.to(torch.int32)
 
 
 def make_frames_np(frame_ids, H, W, depth_cut=10.0):

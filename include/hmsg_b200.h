@@ -135,6 +135,10 @@ int32_t hmsg_masks_dense(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, i
                          const uint8_t* seg, int32_t on_device);
 int32_t hmsg_masks_boxes(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
                          const int32_t* xywh, int32_t on_device);
+/* the same masks as ONE label image per frame: int8 [n,H,W], pixel p belongs to mask labels[p] (0 <= label < M <= 127;
+ * other values: no mask) AND (depth > 0) - non-overlapping instance / panoptic masks at 1 byte per pixel */
+int32_t hmsg_masks_labels(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, int32_t M,
+                          const int8_t* labels, int32_t on_device);
 
 /* Ragged SAM output (extractor.py:117-124 returns as many masks as SAM finds): counts [n_frames] int32 HOST,
  * counts[i] <= M real masks in frame frame_begin + i of the batch just set with hmsg_masks_*.  Slots past the count

@@ -581,6 +581,28 @@ def seq_merge(frames_masks, th, down_size, proxy_th):
     return merge_3d_masks(g, th, down_size, proxy_th)
 
 
+def merge_adjacent_frames(frames_masks, th, down_size, proxy_th):
+    """graph_utils.py:958-985: pairs (0,1), (2,3), ...; an odd last frame is carried over unmerged."""
+    out = []
+    for i in range(0, len(frames_masks), 2):
+        if i == len(frames_masks) - 1:
+            out.append(list(frames_masks[i]))
+            break
+        out.append(merge_3d_masks(list(frames_masks[i]) + list(frames_masks[i + 1]), th, down_size, proxy_th))
+    return out
+
+
+def hierarchical_merge(frames_masks, th, th_factor, down_size, proxy_th):
+    """graph_utils.py:989-1012: merge adjacent frame lists level by level, the threshold drops by
+    th_factor * (n - 2) / max(1, n - 1) after every level that leaves n > 1 lists; one more merge at 0.75."""
+    frames_masks = [list(f) for f in frames_masks]
+    while len(frames_masks) > 1:
+        frames_masks = merge_adjacent_frames(frames_masks, th, down_size, proxy_th)
+        if len(frames_masks) > 1:
+            th -= th_factor * (len(frames_masks) - 2) / max(1, len(frames_masks) - 1)
+    return merge_3d_masks(frames_masks[0], 0.75, down_size, proxy_th)
+
+
 def feats_denoise_dbscan(feats, eps=0.01, min_points=100):
     """graph_utils.py:682-728 - sklearn DBSCAN(metric="cosine") is the reference's own call."""
     from sklearn.cluster import DBSCAN

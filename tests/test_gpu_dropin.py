@@ -75,6 +75,8 @@ def test_graph_create_feature_map_and_queries(engine):
             fe = O.get_img_feats_batch_tensor(sd, x)
             Fp = O.fuse_mask_feats(fe[:M], fe[M:2 * M], fe[2 * M:], 0.4418)
             assert np.allclose(g.frames_feats[f].numpy(), Fp, atol=1e-3)
+            # A9b (graph.py:1119-1136): the view embedding room building needs == get_img_feats(full frame) == the F_g row the build kept
+            assert np.allclose(g.frame_global_feats[f], fe[2 * M], atol=1e-3)
             gidx, _ = engine.pixel_to_node(f, want_dist=False)
             O.ingest_frame(sum_f, cnt, tree, n_nodes, ds.depth[f], ds.rgb[f], ds.T[f], ds.K, 1000.0, Fp, np.stack([m["segmentation"] for m in masks]),
                            idx=gidx[(ds.depth[f] > 0).reshape(-1)])
@@ -131,7 +133,9 @@ def test_query_graph_loaded_from_reference_json(engine, tmp_path):
     embs = _write_graph(str(tmp_path), d=512)
     g = Graph({"pipeline": {}}, engine=engine, clip_feat_dim=512).load_hmsg_graph(str(tmp_path))
     assert len(g.objects) == 6 and len(g.rooms) == 2          # object 5 has no embedding
-    keep = [i for i in range(7) if i != 5]
+    # self.objects follows the reference loader: sorted file names = id strings (graph.py:1928-1930)
+    keep = sorted((i for i in range(7) if i != 5), key=lambda i: f"0_{i % 2}_{i}")
+    assert [o.object_id for o in g.objects] == [f"0_{i % 2}_{i}" for i in keep]
     E = embs[keep].astype(np.float32)
     q = (embs[2] * 0.5).astype(np.float32)[None]
     ids, rooms, scores = g.query_hmsg_object("x", top_k=3, query_feats=q)
@@ -162,7 +166,8 @@ def test_view_and_room_retrieval_variants(engine, tmp_path):
     assert np.allclose(sc, sims[top_idx], rtol=1e-5, atol=1e-5)
     # re-match inside a view
     in_view = ["0_0_2", "0_1_3", "0_0_6"]
-    e = np.stack([o.embedding for o in g.objects if o.object_id in in_view]).astype(np.float32)
+    by_id = {o.object_id: o for o in g.objects}
+    e = np.stack([by_id[i].embedding for i in in_view]).astype(np.float32)
     oid, s = g.rematch_in_view("x", in_view, query_feats=q)
     ref = np.dot(q[0], e.T)
     assert oid == in_view[int(np.argmax(ref))] and abs(s - ref.max()) < 1e-5

@@ -39,7 +39,7 @@ def test_flash_attention_agrees_on_vit_b32(engine):
         alt = engine.encode_images(x.numpy())
     finally:
         engine.set_option("attn_variant", 0)
-    assert np.abs(alt - base).max() < 2e-4
+    assert np.abs(alt - base).max() < 5e-4      # fp16 residual stream: see test_vit_variants_agree
     _check(alt[:4], O.get_img_feats_batch_tensor(sd, x[:4]))
 
 

@@ -194,3 +194,18 @@ def test_object_feats_vs_oracle(engine):
     err = np.abs(got[fin] - ref[fin]).max(1)
     assert np.median(err) < 2e-5 and err.max() < 3e-3, err
     assert np.all(got[-1] == 0)                         # the far object: no valid rows -> zeros
+
+
+@pytest.mark.parametrize("seed,n_frames,n_obj,mpf", [(4, 6, 7, 4), (5, 5, 5, 5), (6, 1, 3, 4)])
+def test_hierarchical_merge_vs_oracle(engine, seed, n_frames, n_obj, mpf):
+    """pipeline.merge_type = "hierarchical" (graph.py:425-433 -> graph_utils.py:958-1012) on the same device kernels"""
+    from holoagent_b200.memory.hmsg.graph.graph import hierarchical_merge
+    frames, vs = _blob_scene(seed, n_frames, n_obj, mpf)
+    ref = [o for o in O.hierarchical_merge(frames, 0.75, 0.025, vs, 0.05) if len(o[0]) >= 10]
+    hierarchical_merge(engine, [_ragged(fm) for fm in frames], 0.75, 0.025, vs, 0.05)
+    engine.objects_finish(10)
+    off, xyz, col = engine.objects_read()
+    assert len(off) - 1 == len(ref)
+    for i, (p, c) in enumerate(ref):
+        assert np.array_equal(xyz[off[i]:off[i + 1]], p), i
+        assert np.array_equal(col[off[i]:off[i + 1]], c), i

@@ -212,3 +212,27 @@ def test_config0_plumbing_oracle_end_to_end():
     assert 0 < hit.sum() < n and np.isfinite(full).all() and not full[~hit].any()
     ids, sc = O.query_topk(full[hit][0] * 0.8, full, 5)
     assert sc[0] >= sc[-1] and len(set(ids.tolist())) == 5
+
+
+def test_text_template_shim_matches_reference_formula():
+    """A10 (clip_utils.py:257-349): two templates per label, rows L2-normalised per text, mean over templates WITHOUT
+    re-normalising - the host shim with an injected text tower vs the oracle's template_mean."""
+    import types
+    from holoagent_b200.memory.hmsg.utils.clip_utils import get_text_feats_multiple_templates
+    rs = np.random.RandomState(0)
+    d = 64
+    bank = {}
+
+    def text_encoder(texts):
+        for t in texts:
+            bank.setdefault(t, rs.randn(d).astype(np.float32) * 3.0)
+        return np.stack([bank[t] for t in texts])
+
+    labels = ["chair", "coffee mug", "plant"]
+    out = get_text_feats_multiple_templates(labels, types.SimpleNamespace(text_encoder=text_encoder), d)
+    asked = [t.format(lm) for lm in labels for t in ("{}", "a photo of {} in the scene.")]
+    assert list(bank) == asked                                    # template order of clip_utils.py:272-276, label-major
+    raw = np.stack([bank[t] for t in asked])
+    ref = O.template_mean(raw / np.linalg.norm(raw, axis=-1, keepdims=True), 2)
+    assert out.shape == (3, d) and np.allclose(out, ref, atol=1e-7)
+    assert np.all(np.linalg.norm(out, axis=-1) < 1.0)             # a mean of two unit vectors is not re-normalised (H8)
