@@ -230,11 +230,8 @@ def apply_config(args, world):
     global H, W, M
     c = CONFIGS[args.config]
     H, W = c["H"], c["W"]
-    if args.config == "c5":
-        # the object layer needs masks that mean the same thing in every frame: one dense instance mask per visible
-        # surface of the synthetic scene (6 room planes + 6 boxes) instead of the 32 random rectangles of c2 / c4
-        M = 12
-        args.no_e2e = True
+    if args.config == "c5" and args.merge_frames <= 0:
+        args.merge_frames = 256
     if args.frames <= 0:
         args.frames = c["frames"]
         # the resident frame store must fit: 5 B/pixel/frame, keep it under ~110 GB per GPU
@@ -248,7 +245,8 @@ def apply_config(args, world):
 def workload_config(args, n_gpus):
     return {"workload": f"{args.frames}-frame {W}x{H} RGB-D HMSG build + crop encoder ({CONFIGS[args.config]['name']}); M={M} masks/frame, "
                         f"{2 * M + 1} crops/frame through ViT-B/32 (d=512), voxel 0.05 m; step = A1-A9 incl. A7 (create_3d_masks per frame)" +
-                        ("; masks = one dense instance mask per visible surface of the scene (label images)" if args.config == "c5" else ""),
+                        ("; object layer (c5 key): instance masks of the 6 scene boxes (label images) over the first "
+                         f"{args.merge_frames} frames of every rank" if args.config == "c5" else ""),
             "config": args.config, "frames": args.frames, "frame_batch": args.batch, "masks_per_frame": M,
             "encoder": "ViT-B/32 fp16 operands / fp32 accumulate", "crops": args.crops, "api": args.api,
             "l2_policy": "inputs (GBs of frames, 2 GB kNN table) are larger than the 126 MB L2",
@@ -363,15 +361,14 @@ def main():
     gids = np.arange(g0, g0 + n_local)
     poses_local = synth.poses(gids).reshape(n_local, 16)
     use_labels = args.config == "c5"
-    labels_dev = torch.empty((max(n_local, 1), H, W), dtype=torch.int8, device=dev) if use_labels else None
+    n_lab = min(n_local, args.merge_frames) if use_labels else 0
+    labels_dev = torch.empty((max(n_lab, 1), H, W), dtype=torch.int8, device=dev) if use_labels else None
     boxes_chunks = []
     for f0 in range(0, n_local, 256):
         ids = gids[f0:f0 + 256]
-        if use_labels:
+        if use_labels and f0 < n_lab:
             d, c, T, _, lab = synth.make_frames(ids, H, W, device=dev, return_labels=True)
-            labels_dev[f0:f0 + len(ids)] = lab
-            for q0 in range(0, len(ids), 32):
-                boxes_chunks.append(synth.instance_masks(lab[q0:q0 + 32])[1].cpu().numpy())
+            labels_dev[f0:min(n_lab, f0 + len(ids))] = lab[:max(0, min(n_lab, f0 + len(ids)) - f0)]
         else:
             d, c, T, _ = synth.make_frames(ids, H, W, device=dev)
         d16 = d.view(torch.int16)
@@ -380,14 +377,11 @@ def main():
             host_depth[f0:f0 + len(ids)] = d16.cpu()
             host_rgb[f0:f0 + len(ids)] = c.cpu()
         eng.sync(); torch.cuda.synchronize()
-    if use_labels:
-        boxes_np = np.concatenate(boxes_chunks) if boxes_chunks else np.zeros((0, M, 4), np.int32)
-    else:
-        boxes_np = np.stack([synth.make_mask_boxes(int(i), H, W, M) for i in gids]) if n_local else np.zeros((0, M, 4), np.int32)
+    boxes_np = np.stack([synth.make_mask_boxes(int(i), H, W, M) for i in gids]) if n_local else np.zeros((0, M, 4), np.int32)
     boxes_dev = torch.from_numpy(boxes_np).to(dev)
     eng.encoder_load(synth.make_vit_weights())
     job = ingest.IngestJob(eng, n_local, FB, M, D, boxes_dev, rank=rank, world=world, crops=args.crops, maskedd_weight=0.4418, bbox_margin=50,
-                           a7=True, collective=args.collective, total_frames=F, labels_dev=labels_dev)
+                           a7=True, collective=args.collective, total_frames=F)
     args.crops = job.crops_mode
 
     def barrier():
@@ -479,7 +473,7 @@ def main():
 
     c5 = None
     if args.config == "c5":
-        c5 = run_c5(args, eng, job, dev, torch, dist, world, rank, barrier)
+        c5 = run_c5(args, eng, job, dev, torch, dist, world, rank, barrier, labels_dev)
     job.release()
 
     # ---------------- kNN: 1M x 512, 10k queries ----------------
@@ -523,16 +517,32 @@ def main():
         dist.destroy_process_group()
 
 
-def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier):
-    """BASELINE configs[4]: after the build, the FSR fast path end to end - 3-D mask merging (N1: every rank merges the
-    frames it owns sequentially, graph_utils.py:1015-1038; the per-rank object lists are then merged once more on every
-    rank, the `hierarchical` idea of graph_utils.py:989-1012 across ranks), per-object features (N2, graph.py:451-488),
-    object table -> 1 k query_hmsg_object requests with one negative prompt (graph.py:3126-3151).  Wall clock, host side."""
+def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier, labels_dev):
+    """BASELINE configs[4]: the FSR fast path end to end, wall clock on the host.
+      build        the configs[1] workload over all frames (A1-A9 incl. A7, M = 32 rectangle masks), sharded
+      object layer instance masks (one label image per frame: the 6 boxes of the scene, the same box keeps its label in
+                   every frame - random rectangles never merge into objects) of the first `merge_frames` frames of every
+                   rank -> create_3d_masks (A7) -> seq_merge (N1, graph_utils.py:1015-1038; every rank merges its own frames,
+                   the per-rank object lists are then merged once more on every rank) -> per-object features (N2,
+                   graph.py:451-488).  seq_merge concatenates point clouds without ever down-sampling them, so an object
+                   grows with every frame that sees it and the merge is O(frames^2) by construction - in the reference as
+                   here; that is why the object stage runs on a bounded number of frames
+      queries      `queries` query_hmsg_object requests with one negative prompt (graph.py:3126-3151), one request per call"""
     out = {}
-    nf = job.F if args.merge_frames <= 0 else min(job.F, args.merge_frames)
+    nf = min(job.F, args.merge_frames)
     barrier(); t0 = time.perf_counter()
     job.step_device()
     barrier(); out["build_s"] = time.perf_counter() - t0
+    # ---- object layer
+    t0 = time.perf_counter()
+    MO = 6
+    eng.mask_store_reset()
+    for b0 in range(0, nf, job.FB):
+        n = min(job.FB, nf - b0)
+        lab = labels_dev[b0:b0 + n].to(torch.int16) - 6            # boxes -> 0..5, room planes / holes -> negative (no mask)
+        eng.masks_labels(b0, torch.clamp(lab, min=-1).to(torch.int8).contiguous(), MO)
+        eng.mask_nodes_batch(b0, n, 0.05, 10000.0, keep=True)
+    barrier(); out["masks3d_s"] = time.perf_counter() - t0
     t0 = time.perf_counter()
     eng.objects_begin(0.75, 0.05, 0.05)
     eng.objects_merge_stored(0, nf)
@@ -549,6 +559,7 @@ def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier):
         n_obj, n_pts = eng.objects_finish(10)
     barrier(); out["merge_s"] = time.perf_counter() - t0
     out["merged_frames_per_rank"] = nf
+    out["merge_frames_per_s"] = nf * world / out["merge_s"]
     out["objects"], out["object_points"] = int(n_obj), int(n_pts)
     t0 = time.perf_counter()
     full = eng.node_feats_finalize()
@@ -566,7 +577,7 @@ def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier):
             eng.query_object(Q[i:i + 1], 0, k)
         out["query_s"] = time.perf_counter() - t0
         out["queries_per_s"] = args.queries / out["query_s"] * world
-    out["total_s"] = out["build_s"] + out["merge_s"] + out["object_feats_s"] + out.get("query_s", 0.0)
+    out["total_s"] = out["build_s"] + out["masks3d_s"] + out["merge_s"] + out["object_feats_s"] + out.get("query_s", 0.0)
     out["build_frames_per_s"] = job.total / out["build_s"]
     return out
 

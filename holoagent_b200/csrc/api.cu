@@ -51,7 +51,7 @@ extern "C" int32_t hmsg_ctx_destroy(hmsg_ctx* ctx) {
   masks3d_destroy(ctx);
   comm_destroy(ctx);
   crops_destroy(ctx);
-  free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->d_bounds);
+  free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->frameK); free_dev(ctx->d_bounds);
   free_dev(ctx->bitmap); free_dev(ctx->prefix); free_dev(ctx->blocksums); free_dev(ctx->vox_acc); free_dev(ctx->vox_cnt);
   free_dev(ctx->vox_ijk); free_dev(ctx->rad_cnt); free_dev(ctx->nbitmap); free_dev(ctx->nprefix); free_dev(ctx->node_xyz);
   free_dev(ctx->node_rgb); free_dev(ctx->node_ijk); free_dev(ctx->node_vox); free_dev(ctx->sum_feats); free_dev(ctx->counter);

@@ -88,6 +88,7 @@ struct hmsg_ctx {
   uint16_t* depth = nullptr;   // [cap,H,W]
   uint8_t* rgb = nullptr;      // [cap,H,W,3]
   double* poses = nullptr;     // [cap,16]
+  double* frameK = nullptr;    // [cap,4] per-frame (fx, fy, cx, cy) or nullptr (one K per scene)
 
   // ---- voxel table (A2)
   long long* d_bounds = nullptr;   // 6 ordered-int doubles: min xyz, max xyz

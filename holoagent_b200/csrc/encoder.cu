@@ -124,7 +124,8 @@ constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;   // 32 KB
 constexpr int OUT_STAGE_BYTES = BM * 128;    // 16 KB: 128 rows x one 128-byte swizzle span
 constexpr int GEMM_THREADS = 640;            // 4 control warps + 16 epilogue warps
-constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int COLV_BYTES = 2 * BN * 4;       // per-tile column vectors staged in smem: bias / b' [BN] | sres [BN]
+constexpr int GEMM_SMEM = STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 512 /*align: checked in the kernel*/ + 256 /*barriers*/ + COLV_BYTES;
 
 // EPI_F16_LN / EPI_F16_LN_GELU: the GEMM consumes the fp16 residual stream x directly; LayerNorm is folded in:
 //   LN(x) W^T + b = rstd_r * (x W''^T - mean_r * sres_n) + b'_n,  W''[n,k] = gamma_k W[n,k] - mean_k(gamma W[n,:])  (rows sum to ~0,
@@ -140,7 +141,7 @@ struct GemmArgs {
   int quick_gelu;
   // folded-LayerNorm / fp16-residual epilogues
   const float* sres;     // [N] residual row sums of the folded weight
-  const float2* stats_in;   // [rows * stat_stride][stat_parts] partial (sum, sumsq) of the A rows, summed in part order
+  const float2* stats_in;   // [rows * stat_stride] (mean, rstd) of the A rows (k_rowstats over the parts below)
   float2* stats_out;        // [rows * stat_stride][stat_parts]: every (N tile, column group) owner writes its own part - no
                             // atomics, no zeroing, bit-reproducible; null = not needed
   int stat_parts;           // width / 64
@@ -197,20 +198,21 @@ __device__ __forceinline__ void tma_wait_all0() { asm volatile("cp.async.bulk.wa
 
 // One warp's share of a 128-row x 64-column fp16 output chunk: 32 accumulator columns of TMEM lane `trow` -> bias / folded
 // LayerNorm / GELU / residual -> fp16 -> 128B-swizzled staging row.  xo = the thread's 32 x_old halfs (EPI_F16_RESID_STATS).
+// sb / ss: this warp's 32 entries of the tile's bias (b') and sres vectors in shared memory (null bias: sb == nullptr)
 template <int EPI>
-__device__ __forceinline__ void epi_f16_group(const uint32_t* r, const GemmArgs& g, int col, uint8_t* srow, int sw, int half, float mean, float rstd,
-                                              const uint4* xo, float& ssum, float& ssq) {
+__device__ __forceinline__ void epi_f16_group(const uint32_t* r, const GemmArgs& g, const float* sb, const float* ss, uint8_t* srow, int sw, int half,
+                                              float mean, float rstd, const uint4* xo, float& ssum, float& ssq) {
   constexpr bool LN = (EPI == EPI_F16_LN || EPI == EPI_F16_LN_GELU);
   constexpr bool GELU = (EPI == EPI_F16_BIAS_GELU || EPI == EPI_F16_LN_GELU);
-  const float* bp = g.bias ? g.bias + col : nullptr;
+  const float* bp = sb;
 #pragma unroll
   for (int q4 = 0; q4 < 4; q4++) {
     float v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) v[e] = __uint_as_float(r[q4 * 8 + e]);
     if (LN) {
-      const float4 s0 = __ldg(reinterpret_cast<const float4*>(g.sres + col) + q4 * 2), s1 = __ldg(reinterpret_cast<const float4*>(g.sres + col) + q4 * 2 + 1);
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+      const float4 s0 = reinterpret_cast<const float4*>(ss)[q4 * 2], s1 = reinterpret_cast<const float4*>(ss)[q4 * 2 + 1];   // LDS, warp-uniform address
+      const float4 b0 = reinterpret_cast<const float4*>(bp)[q4 * 2], b1 = reinterpret_cast<const float4*>(bp)[q4 * 2 + 1];
       const float2 nm = make_float2(-mean, -mean), rs = make_float2(rstd, rstd);       // packed FFMA2: two columns per instruction
       float2 t0 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s0.x, s0.y), make_float2(v[0], v[1])), make_float2(b0.x, b0.y));
       float2 t1 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s0.z, s0.w), make_float2(v[2], v[3])), make_float2(b0.z, b0.w));
@@ -218,7 +220,7 @@ __device__ __forceinline__ void epi_f16_group(const uint32_t* r, const GemmArgs&
       float2 t3 = __ffma2_rn(rs, __ffma2_rn(nm, make_float2(s1.z, s1.w), make_float2(v[6], v[7])), make_float2(b1.z, b1.w));
       v[0] = t0.x; v[1] = t0.y; v[2] = t1.x; v[3] = t1.y; v[4] = t2.x; v[5] = t2.y; v[6] = t3.x; v[7] = t3.y;
     } else if (bp) {
-      float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2), b1 = __ldg(reinterpret_cast<const float4*>(bp) + q4 * 2 + 1);
+      float4 b0 = reinterpret_cast<const float4*>(bp)[q4 * 2], b1 = reinterpret_cast<const float4*>(bp)[q4 * 2 + 1];
       float2 s0 = __fadd2_rn(make_float2(v[0], v[1]), make_float2(b0.x, b0.y)), s1 = __fadd2_rn(make_float2(v[2], v[3]), make_float2(b0.z, b0.w));
       float2 s2 = __fadd2_rn(make_float2(v[4], v[5]), make_float2(b1.x, b1.y)), s3 = __fadd2_rn(make_float2(v[6], v[7]), make_float2(b1.z, b1.w));
       v[0] = s0.x; v[1] = s0.y; v[2] = s1.x; v[3] = s1.y; v[4] = s2.x; v[5] = s2.y; v[6] = s3.x; v[7] = s3.y;
@@ -274,6 +276,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
   uint64_t* tfull = bars + 2 * STAGES;    // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  float* scol = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  if (threadIdx.x == 0 && (reinterpret_cast<uint8_t*>(scol) + COLV_BYTES) - smem_raw > GEMM_SMEM) asm volatile("trap;");   // window less aligned than assumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (g.M + BM - 1) / BM, n_tiles = g.N / BN, k_blocks = g.K / BK;
@@ -358,18 +362,37 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     uint8_t* srow = stg + trow * 128;
     const int sw = trow & 7;
     int as = 0; uint32_t aph = 0;
+    const int et = threadIdx.x - 128;                // epilogue thread 0..511: entry of the column-vector buffer it fills
+    constexpr int ROWS_PER_TILE = BM;
+    const int row_in_tile0 = 0;
+    const int tile_step = gridDim.x;
+    auto load_colv = [&](int nbx) -> float {          // et < BN: bias / b'[nbx * BN + et]; else sres[nbx * BN + et - BN]
+      if (et < BN) return g.bias ? __ldg(g.bias + nbx * BN + et) : 0.f;
+      return (LN && g.sres) ? __ldg(g.sres + nbx * BN + et - BN) : 0.f;
+    };
+    float colv = 0.f;
+    float2 ms_cur = make_float2(0.f, 0.f), ms_cur_next = make_float2(0.f, 0.f);
+    if ((int)blockIdx.x < num_tiles) {
+      colv = load_colv((int)blockIdx.x % n_tiles);
+      if (LN) { const long long r0 = (long long)((int)blockIdx.x / n_tiles) * BM + trow; if (r0 < g.M) ms_cur = g.stats_in[r0 * g.stat_stride]; }
+    }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       int mb = tile / n_tiles, nb = tile % n_tiles;
       const int row0 = mb * BM;
       const long long grow = (long long)row0 + trow;
       const bool row_ok = grow < g.M;
-      float mean = 0.f, rstd = 0.f, ssum = 0.f, ssq = 0.f;
-      if (LN && row_ok) {                            // row statistics written by the epilogue that produced x (independent of the accumulator)
-        const float2* sp = g.stats_in + grow * g.stat_stride * g.stat_parts;
-        float sx = 0.f, sy = 0.f;
-        for (int pt = 0; pt < g.stat_parts; pt++) { const float2 st = sp[pt]; sx += st.x; sy += st.y; }
-        mean = sx * g.inv_w;
-        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sy * g.inv_w), 0.f) + g.ln_eps);
+      float ssum = 0.f, ssq = 0.f;
+      const float mean = ms_cur.x, rstd = ms_cur.y;   // LayerNorm statistics of this row (k_rowstats), fetched one tile ahead
+      // column vectors of this tile -> shared memory (fetched one tile ahead into `colv`), next tile's prefetches in flight
+      scol[et] = colv;
+      named_bar_sync(3, 512);
+      {
+        const int ntile = tile + tile_step;
+        if (ntile < num_tiles) {
+          const int nmb = ntile / n_tiles, nnb = ntile % n_tiles;
+          colv = load_colv(nnb);
+          if (LN) { const long long nrow = (long long)nmb * ROWS_PER_TILE + row_in_tile0 + trow; if (nrow < g.M) ms_cur_next = g.stats_in[nrow * g.stat_stride]; }
+        }
       }
       uint4 xo[4];
       if (RESID) {                                   // first chunk's x_old: in flight while the MMAs of this tile finish
@@ -396,7 +419,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         tmem_ld_wait();
         if constexpr (F16OUT) {
-          epi_f16_group<EPI>(r, g, col0 + half * WCOLS, srow, sw, half, mean, rstd, xo, ssum, ssq);
+          epi_f16_group<EPI>(r, g, g.bias ? scol + ch * CH_COLS + half * WCOLS : nullptr, scol + BN + ch * CH_COLS + half * WCOLS, srow, sw, half, mean, rstd,
+                             xo, ssum, ssq);
           if (RESID && ch + 2 < NCH) {              // next chunk's x_old: overlaps the staging barrier + TMA store of this one
             if (row_ok) {
               const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + col0 + 2 * CH_COLS + half * WCOLS);
@@ -405,13 +429,13 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             }
           }
         } else {
-          const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
+          const float* bp = g.bias ? scol + ch * CH_COLS + half * WCOLS : nullptr;
 #pragma unroll
           for (int q8 = 0; q8 < 4; q8++) {
             float4 v;
             v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
             v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
-            if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (bp) { float4 b = reinterpret_cast<const float4*>(bp)[q8]; v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
             *reinterpret_cast<float4*>(srow + (((half * 4 + q8) ^ sw) << 4)) = v;
           }
         }
@@ -429,6 +453,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (++as == 2) { as = 0; aph ^= 1; }
+      ms_cur = ms_cur_next;
+      named_bar_sync(3, 512);                        // every warp is done reading this tile's column vectors
     }
     if (issuer) tma_wait_all0();
   }
@@ -449,7 +475,8 @@ k_gemm_f16(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 constexpr int STAGES2 = 6;
 constexpr int A2_STAGE_BYTES = 128 * BK * 2;   // 16 KB
 constexpr int B2_STAGE_BYTES = 128 * BK * 2;   // 16 KB (this CTA's half of the 256 B rows)
-constexpr int GEMM2_SMEM = STAGES2 * (A2_STAGE_BYTES + B2_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 1024 + 256;
+// 227 KB is the opt-in limit: the alignment slack is 512 B here (the dynamic window starts 1024-aligned in practice; checked below)
+constexpr int GEMM2_SMEM = STAGES2 * (A2_STAGE_BYTES + B2_STAGE_BYTES) + 2 * OUT_STAGE_BYTES + 512 + 256 + COLV_BYTES;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -506,6 +533,8 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* tfull = bars + 2 * STAGES2;    // [2]
   uint64_t* tempty = bars + 2 * STAGES2 + 2;   // [2]  (used in the leader: 32 arrivals = 16 warps x 2 CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES2 + 4);
+  float* scol = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);
+  if (threadIdx.x == 0 && (reinterpret_cast<uint8_t*>(scol) + COLV_BYTES) - smem_raw > GEMM2_SMEM) asm volatile("trap;");   // window less aligned than assumed
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -588,18 +617,37 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* srow = stg + trow * 128;
     const int sw = trow & 7;
     int as = 0; uint32_t aph = 0;
+    const int et = threadIdx.x - 128;                // epilogue thread 0..511: entry of the column-vector buffer it fills
+    constexpr int ROWS_PER_TILE = 256;
+    const int row_in_tile0 = (int)rank * 128;
+    const int tile_step = n_clusters;
+    auto load_colv = [&](int nbx) -> float {          // et < BN: bias / b'[nbx * BN + et]; else sres[nbx * BN + et - BN]
+      if (et < BN) return g.bias ? __ldg(g.bias + nbx * BN + et) : 0.f;
+      return (LN && g.sres) ? __ldg(g.sres + nbx * BN + et - BN) : 0.f;
+    };
+    float colv = 0.f;
+    float2 ms_cur = make_float2(0.f, 0.f), ms_cur_next = make_float2(0.f, 0.f);
+    if (cluster_id < num_tiles) {
+      colv = load_colv(cluster_id % n_tiles);
+      if (LN) { const long long r0 = (long long)(cluster_id / n_tiles) * 256 + row_in_tile0 + trow; if (r0 < g.M) ms_cur = g.stats_in[r0 * g.stat_stride]; }
+    }
     for (int tile = cluster_id; tile < num_tiles; tile += n_clusters) {
       int mb = tile / n_tiles, nb = tile % n_tiles;
       const int row0 = mb * 256 + (int)rank * 128;
       const long long grow = (long long)row0 + trow;
       const bool row_ok = grow < g.M;
-      float mean = 0.f, rstd = 0.f, ssum = 0.f, ssq = 0.f;
-      if (LN && row_ok) {                            // row statistics written by the epilogue that produced x (independent of the accumulator)
-        const float2* sp = g.stats_in + grow * g.stat_stride * g.stat_parts;
-        float sx = 0.f, sy = 0.f;
-        for (int pt = 0; pt < g.stat_parts; pt++) { const float2 st = sp[pt]; sx += st.x; sy += st.y; }
-        mean = sx * g.inv_w;
-        rstd = rsqrtf(fmaxf(fmaf(-mean, mean, sy * g.inv_w), 0.f) + g.ln_eps);
+      float ssum = 0.f, ssq = 0.f;
+      const float mean = ms_cur.x, rstd = ms_cur.y;   // LayerNorm statistics of this row (k_rowstats), fetched one tile ahead
+      // column vectors of this tile -> shared memory (fetched one tile ahead into `colv`), next tile's prefetches in flight
+      scol[et] = colv;
+      named_bar_sync(3, 512);
+      {
+        const int ntile = tile + tile_step;
+        if (ntile < num_tiles) {
+          const int nmb = ntile / n_tiles, nnb = ntile % n_tiles;
+          colv = load_colv(nnb);
+          if (LN) { const long long nrow = (long long)nmb * ROWS_PER_TILE + row_in_tile0 + trow; if (nrow < g.M) ms_cur_next = g.stats_in[nrow * g.stat_stride]; }
+        }
       }
       uint4 xo[4];
       if (RESID) {                                   // first chunk's x_old: in flight while the MMAs of this tile finish
@@ -626,7 +674,8 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         else tmem_ld_32x16(t_addr + (uint32_t)(ch * CH_COLS + half * WCOLS), r);
         tmem_ld_wait();
         if constexpr (F16OUT) {
-          epi_f16_group<EPI>(r, g, col0 + half * WCOLS, srow, sw, half, mean, rstd, xo, ssum, ssq);
+          epi_f16_group<EPI>(r, g, g.bias ? scol + ch * CH_COLS + half * WCOLS : nullptr, scol + BN + ch * CH_COLS + half * WCOLS, srow, sw, half, mean, rstd,
+                             xo, ssum, ssq);
           if (RESID && ch + 2 < NCH) {              // next chunk's x_old: overlaps the staging barrier + TMA store of this one
             if (row_ok) {
               const uint4* xp = reinterpret_cast<const uint4*>(g.resid + grow * g.ldr + col0 + 2 * CH_COLS + half * WCOLS);
@@ -635,13 +684,13 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
           }
         } else {
-          const float* bp = g.bias ? g.bias + col0 + half * WCOLS : nullptr;
+          const float* bp = g.bias ? scol + ch * CH_COLS + half * WCOLS : nullptr;
 #pragma unroll
           for (int q8 = 0; q8 < 4; q8++) {
             float4 v;
             v.x = __uint_as_float(r[q8 * 4 + 0]); v.y = __uint_as_float(r[q8 * 4 + 1]);
             v.z = __uint_as_float(r[q8 * 4 + 2]); v.w = __uint_as_float(r[q8 * 4 + 3]);
-            if (bp) { float4 b = __ldg(reinterpret_cast<const float4*>(bp) + q8); v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
+            if (bp) { float4 b = reinterpret_cast<const float4*>(bp)[q8]; v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w; }
             *reinterpret_cast<float4*>(srow + (((half * 4 + q8) ^ sw) << 4)) = v;
           }
         }
@@ -659,6 +708,8 @@ k_gemm_f16_2sm(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tempty[as], 0);   // the leader's MMA thread waits for both CTAs' epilogues
       if (++as == 2) { as = 0; aph ^= 1; }
+      ms_cur = ms_cur_next;
+      named_bar_sync(3, 512);                        // every warp is done reading this tile's column vectors
     }
     if (issuer) tma_wait_all0();
   }
@@ -831,7 +882,6 @@ __global__ void __launch_bounds__(256) k_embed_lnpre_f16(const float* __restrict
                                                          const float* __restrict__ gam, const float* __restrict__ bet, __half* __restrict__ x,
                                                          float2* __restrict__ stats, long long rows, int T) {
   constexpr int W = NV * 128;
-  constexpr int PARTS = W / 64;
   long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -856,7 +906,22 @@ __global__ void __launch_bounds__(256) k_embed_lnpre_f16(const float* __restrict
     reinterpret_cast<uint2*>(x + row * W)[lane + 32 * j] = pk;
   }
   for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-  if (lane < PARTS) stats[row * PARTS + lane] = lane == 0 ? make_float2(s, q) : make_float2(0.f, 0.f);
+  if (lane == 0) {
+    const float mean = s * (1.0f / (float)W);
+    stats[row] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, q * (1.0f / (float)W)), 0.f) + 1e-5f));
+  }
+}
+
+// (sum, sumsq) parts written by the residual epilogues -> (mean, rstd) per row, summed in part order (bit-reproducible)
+__global__ void __launch_bounds__(256) k_rowstats(const float2* __restrict__ parts, int P, long long rows, long long stride, float inv_w, float eps,
+                                                  float2* __restrict__ ms) {
+  long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
+  const float2* sp = parts + r * stride * P;
+  float sx = 0.f, sy = 0.f;
+  for (int p = 0; p < P; p++) { const float2 v = sp[p]; sx += v.x; sy += v.y; }
+  const float mean = sx * inv_w;
+  ms[r * stride] = make_float2(mean, rsqrtf(fmaxf(fmaf(-mean, mean, sy * inv_w), 0.f) + eps));
 }
 
 // h = LN(x) with x in fp16 (ln_post on the class-token rows of the fp16 residual stream)
@@ -1309,22 +1374,25 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
 // 16 x T score row never exists.  Same mma.sync m16n8k16 fragments as the T <= 64 kernels above.
 // ------------------------------------------------------------------------------------------
 constexpr int ATTF_WARPS = 6;
-static inline int attf_smem_bytes(int Tp) { return (2 * Tp + ATTF_WARPS * 16) * ATT_LD * 2; }
+static inline int attf_smem_bytes(int Tp, int HD = 64) { return (2 * Tp + ATTF_WARPS * 16) * (HD + 8) * 2; }
 
+// HD = head dim: 64 (ViT-B/32, B/16, L/14) or 80 (ViT-H/14, graph.py:105-111)
+template <int HD>
 __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
                                                                     int W, float scale, int Tp, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
+  constexpr int LD = HD + 8, CPR = HD / 8;   // padded row stride (halfs), 16-byte chunks per row
   __half* sK = reinterpret_cast<__half*>(att_smem);
-  __half* sV = sK + (size_t)Tp * ATT_LD;
+  __half* sV = sK + (size_t)Tp * LD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __half* sQ = sV + (size_t)Tp * ATT_LD + (size_t)warp * 16 * ATT_LD;
+  __half* sQ = sV + (size_t)Tp * LD + (size_t)warp * 16 * LD;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int ld = 3 * W;
-  const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
-  for (int i = threadIdx.x; i < Tp * 8; i += ATTF_WARPS * 32) {
-    const int r = i >> 3, ch = i & 7;
-    __half* dk = sK + r * ATT_LD + ch * 8;
-    __half* dv = sV + r * ATT_LD + ch * 8;
+  const __half* src0 = qkv + ((long long)b * T) * ld + h * HD;
+  for (int i = threadIdx.x; i < Tp * CPR; i += ATTF_WARPS * 32) {
+    const int r = i / CPR, ch = i - r * CPR;
+    __half* dk = sK + r * LD + ch * 8;
+    __half* dv = sV + r * LD + ch * 8;
     if (r < T) {
       const __half* src = src0 + (long long)r * ld + ch * 8;
       cp_async16(dk, src + W);
@@ -1342,34 +1410,34 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __hal
   for (int mi = warp; mi < m_tiles; mi += ATTF_WARPS) {
     // stage this warp's 16 query rows
     __syncwarp();
-    for (int i = lane; i < 16 * 8; i += 32) {
-      const int r = i >> 3, ch = i & 7, row = mi * 16 + r;
-      __half* dq = sQ + r * ATT_LD + ch * 8;
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, ch = i - r * CPR, row = mi * 16 + r;
+      __half* dq = sQ + r * LD + ch * 8;
       if (row < T) cp_async16(dq, src0 + (long long)row * ld + ch * 8);
       else *reinterpret_cast<uint4*>(dq) = make_uint4(0, 0, 0, 0);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
-    uint32_t aq[4][4];
+    uint32_t aq[HD / 16][4];
 #pragma unroll
-    for (int ks = 0; ks < 4; ks++) ldsm_x4(aq[ks], sQ + (lane & 15) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+    for (int ks = 0; ks < HD / 16; ks++) ldsm_x4(aq[ks], sQ + (lane & 15) * LD + ks * 16 + (lane >> 4) * 8);
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    float oacc[8][4];
+    float oacc[HD / 8][4];
 #pragma unroll
-    for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+    for (int ni = 0; ni < HD / 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
     for (int kb = 0; kb < Tp; kb += 64) {
       const int nt = min(4, (Tp - kb) >> 4);   // 16-key steps in this block (warp uniform)
       float s[8][4];
 #pragma unroll
       for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
 #pragma unroll
-      for (int ks = 0; ks < 4; ks++) {
+      for (int ks = 0; ks < HD / 16; ks++) {
 #pragma unroll
         for (int np = 0; np < 4; np++) {
           if (np < nt) {
             uint32_t bb[4];
-            ldsm_x4(bb, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
+            ldsm_x4(bb, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
             mma_16816(s[np * 2], aq[ks], bb);
             mma_16816(s[np * 2 + 1], aq[ks], bb + 2);
           }
@@ -1405,7 +1473,7 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __hal
       }
       l0 = l0 * al0 + ps0; l1 = l1 * al1 + ps1;   // per-thread partial row sums (the quad is reduced once at the end)
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) { oacc[ni][0] *= al0; oacc[ni][1] *= al0; oacc[ni][2] *= al1; oacc[ni][3] *= al1; }
+      for (int ni = 0; ni < HD / 8; ni++) { oacc[ni][0] *= al0; oacc[ni][1] *= al0; oacc[ni][2] *= al1; oacc[ni][3] *= al1; }
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
         if (kk < nt) {
@@ -1417,9 +1485,9 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __hal
           a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
           a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
 #pragma unroll
-          for (int np = 0; np < 4; np++) {
+          for (int np = 0; np < HD / 16; np++) {
             uint32_t bb[4];
-            ldsm_x4_t(bb, sV + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + (np * 2 + (lane >> 4)) * 8);
+            ldsm_x4_t(bb, sV + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (np * 2 + (lane >> 4)) * 8);
             mma_16816(oacc[np * 2], a, bb);
             mma_16816(oacc[np * 2 + 1], a, bb + 2);
           }
@@ -1431,8 +1499,8 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __hal
     const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
     const int r0 = mi * 16 + g, r1 = r0 + 8;
 #pragma unroll
-    for (int ni = 0; ni < 8; ni++) {
-      const int col = h * 64 + ni * 8 + 2 * t;
+    for (int ni = 0; ni < HD / 8; ni++) {
+      const int col = h * HD + ni * 8 + 2 * t;
       if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0] * inv0, oacc[ni][1] * inv0);
       if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2] * inv1, oacc[ni][3] * inv1);
     }
@@ -1504,7 +1572,7 @@ struct VitState {
   float* x = nullptr;       // [cap*T, W] fp32 residual (ln_fold = 0)
   __half* xh = nullptr;     // [cap*T, W] fp16 residual (ln_fold = 1)
   float2* statsA = nullptr; // [cap*T][W/64] partial (sum, sumsq) of the rows of xh for ln_1
-  float2* statsB = nullptr; // ... for ln_2
+  float2* statsB = nullptr; // [cap*T] (mean, rstd) of the rows of xh for the next folded LayerNorm (k_rowstats)
   bool ln_fold = true;      // LayerNorm folded into the consuming GEMM, fp16 residual stream
   __half* h = nullptr;      // [cap*T, W]
   __half* qkv = nullptr;    // [cap*T, 3W]   (aliases: patch-embed output fp32 [cap*(T-1), W])
@@ -1674,12 +1742,12 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
   if (!ctx) return HMSG_ERR_ARG;
   if (!desc || !blob) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: null argument");
   const hmsg_vit_desc& d = *desc;
-  if (d.image <= 0 || d.patch <= 0 || d.layers <= 0 || d.heads <= 0 || d.width % 128 != 0 || d.width > 1536 || d.width / d.heads != 64 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
+  if (d.image <= 0 || d.patch <= 0 || d.layers <= 0 || d.heads <= 0 || d.width % 128 != 0 || d.width > 1536 || (d.width / d.heads != 64 && d.width / d.heads != 80) || d.width % d.heads != 0 || d.image % d.patch != 0 || d.mlp % 256 != 0 || d.out_dim % 256 != 0 ||
       (3 * d.width) % 256 != 0 || d.width % 256 != 0)
-    return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: unsupported ViT shape (need head_dim 64, width/mlp/out_dim multiples of 256)");
+    return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: unsupported ViT shape (need head_dim 64 or 80, width/mlp/out_dim multiples of 256)");
   int G = d.image / d.patch, T = G * G + 1;
   if (T > 4096) return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: more than 4096 tokens per image is not supported");
-  if (attf_smem_bytes((T + 15) / 16 * 16) > 220 * 1024)
+  if (attf_smem_bytes((T + 15) / 16 * 16, d.width / d.heads) > 220 * 1024)
     return ctx->fail(HMSG_ERR_ARG, "hmsg_encoder_load: K/V of one head do not fit in shared memory (T too large)");
   vit_destroy(ctx);
   VitState* vs = new VitState();
@@ -1766,7 +1834,7 @@ static int32_t ensure_ws(hmsg_ctx* ctx, VitState* vs, int B) {
   HMSG_CUDA(cudaMalloc((void**)&vs->x, R * W * 4));
   HMSG_CUDA(cudaMalloc((void**)&vs->xh, R * W * 2));
   HMSG_CUDA(cudaMalloc((void**)&vs->statsA, R * 8 * (W / 64)));
-  HMSG_CUDA(cudaMalloc((void**)&vs->statsB, R * 8 * (W / 64)));
+  HMSG_CUDA(cudaMalloc((void**)&vs->statsB, R * 8));
   HMSG_CUDA(cudaMalloc((void**)&vs->h, R * W * 2));
   HMSG_CUDA(cudaMalloc((void**)&vs->qkv, qkv_bytes));
   HMSG_CUDA(cudaMalloc((void**)&vs->gbuf, g_bytes));
@@ -1805,19 +1873,22 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
     HMSG_LAUNCH_CHECK();
   }
   if ((rc = gemm(ctx, vs, EPI_F32_STORE, a0, vs->wconv, (int)RP, W, vs->Kpad, nullptr, patch, W))) return rc;
-  const float scale = 1.0f / sqrtf(64.0f);
+  const int HD = W / d.heads;
+  const float scale = 1.0f / sqrtf((float)HD);
   const bool cls_last = vs->last_cls_only && T > 1 && !vs->attn_simple && !vs->attn_v1 && !vs->attn_v2;
   // attention launcher shared by both residual-stream forms: qkv [R,3W] -> h [R,W]
   auto attention = [&](int q_tiles) -> int32_t {
     ctx->prof_begin(PROF_ATTN);
-    if (T > 64 || vs->attn_flash) {
+    if (T > 64 || vs->attn_flash || HD != 64) {
       const int Tp = (T + 15) / 16 * 16;
-      const int sm = attf_smem_bytes(Tp);
+      const int sm = attf_smem_bytes(Tp, HD);
       if (vs->flash_smem_set != sm) {
-        HMSG_CUDA(cudaFuncSetAttribute(k_attention_flash, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_flash<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_flash<80>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm));
         vs->flash_smem_set = sm;
       }
-      k_attention_flash<<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp, q_tiles);
+      if (HD == 80) k_attention_flash<80><<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp, q_tiles);
+      else k_attention_flash<64><<<(unsigned)(B * d.heads), ATTF_WARPS * 32, sm, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, Tp, q_tiles);
     } else if (vs->attn_simple) {
       k_attention_simple<<<(unsigned)(B * d.heads), 128, 0, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale);
     } else if (vs->attn_v1) {
@@ -1856,44 +1927,57 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
           k_attention_mma3<8, 1, 8><<<grid, 8 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       }
     }
-    ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * 64);
+    ctx->prof_end(PROF_ATTN, 4.0 * B * d.heads * (double)T * T * HD);
     HMSG_LAUNCH_CHECK();
     return HMSG_OK;
   };
   if (vs->ln_fold) {
     // ---- fp16 residual stream, LayerNorms folded into the consuming GEMMs: per block 4 GEMMs + attention, no LN kernels
-    k_embed_lnpre_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->xh,
-                                                                                       vs->statsA, R, T);
+    // vs->statsA: per-tile (sum, sumsq) parts written by the residual epilogues; vs->statsB: (mean, rstd) per row for the next folded LN
+    float2* parts = vs->statsA;
+    float2* ms = vs->statsB;
+    const int P = W / 64;
+    auto rowstats = [&](long long rows, long long stride) -> int32_t {
+      ctx->prof_begin(PROF_ELTWISE);
+      k_rowstats<<<(unsigned)((rows + 255) / 256), 256, 0, ctx->stream>>>(parts, P, rows, stride, 1.0f / (float)W, 1e-5f, ms);
+      ctx->prof_end(PROF_ELTWISE, (double)rows * P * 8);
+      HMSG_LAUNCH_CHECK();
+      return HMSG_OK;
+    };
+    k_embed_lnpre_f16<NV><<<(unsigned)((R * 32 + 255) / 256), 256, 0, ctx->stream>>>(patch, vs->cls, vs->pos, vs->lnpre_g, vs->lnpre_b, vs->xh, ms, R, T);
     HMSG_LAUNCH_CHECK();
     for (int l = 0; l < d.layers; l++) {
       const LayerW& L = vs->layers[l];
       const bool cls_only = cls_last && l == d.layers - 1;
       GemmExtra ex;
       if (!cls_only) {
-        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = vs->statsA;
+        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = ms;
         if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f, (int)R, 3 * W, W, L.bqkv_f, vs->qkv, 3 * W, 0, &ex))) return rc;
       } else {   // last block: K, V for every token, Q for the class-token rows only (strided views)
-        ex = GemmExtra(); ex.sres = L.sres_qkv + W; ex.stats_in = vs->statsA;
+        ex = GemmExtra(); ex.sres = L.sres_qkv + W; ex.stats_in = ms;
         if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f + (size_t)W * W, (int)R, 2 * W, W, L.bqkv_f + W, vs->qkv + W, 3 * W, 0, &ex))) return rc;
-        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = vs->statsA; ex.stat_stride = T;
+        ex = GemmExtra(); ex.sres = L.sres_qkv; ex.stats_in = ms; ex.stat_stride = T;
         if ((rc = gemm(ctx, vs, EPI_F16_LN, vs->xh, L.wqkv_f, B, W, W, L.bqkv_f, vs->qkv, T * 3 * W, (long long)T * W, &ex))) return rc;
       }
       if ((rc = attention(cls_only ? 1 : (1 << 30)))) return rc;
       if (cls_only) {
-        ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = (long long)T * W; ex.stats_out = vs->statsB; ex.stat_stride = T;
+        ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = (long long)T * W; ex.stats_out = parts; ex.stat_stride = T;
         if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->h, L.wo, B, W, W, L.bo, vs->xh, T * W, (long long)T * W, &ex))) return rc;
-        ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = vs->statsB; ex.stat_stride = T;
+        if ((rc = rowstats(B, T))) return rc;
+        ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = ms; ex.stat_stride = T;
         if ((rc = gemm(ctx, vs, EPI_F16_LN_GELU, vs->xh, L.wfc_f, B, d.mlp, W, L.bfc_f, vs->gbuf, d.mlp, (long long)T * W, &ex))) return rc;
         ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = (long long)T * W;
         if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->gbuf, L.wproj, B, W, d.mlp, L.bproj, vs->xh, T * W, 0, &ex))) return rc;
         continue;
       }
-      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = vs->statsB;
+      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = parts;
       if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->h, L.wo, (int)R, W, W, L.bo, vs->xh, W, 0, &ex))) return rc;
-      ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = vs->statsB;
+      if ((rc = rowstats(R, 1))) return rc;
+      ex = GemmExtra(); ex.sres = L.sres_fc; ex.stats_in = ms;
       if ((rc = gemm(ctx, vs, EPI_F16_LN_GELU, vs->xh, L.wfc_f, (int)R, d.mlp, W, L.bfc_f, vs->gbuf, d.mlp, 0, &ex))) return rc;
-      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = vs->statsA;
+      ex = GemmExtra(); ex.resid = vs->xh; ex.ldr = W; ex.stats_out = parts;
       if ((rc = gemm(ctx, vs, EPI_F16_RESID_STATS, vs->gbuf, L.wproj, (int)R, W, d.mlp, L.bproj, vs->xh, W, 0, &ex))) return rc;
+      if ((rc = rowstats(R, 1))) return rc;
     }
     k_layernorm_h2h<NV><<<(unsigned)(((long long)B * 32 + 255) / 256), 256, 0, ctx->stream>>>(vs->xh, vs->lnpost_g, vs->lnpost_b, vs->pooled, B, T);
     HMSG_LAUNCH_CHECK();

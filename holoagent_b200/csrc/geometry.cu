@@ -36,18 +36,27 @@ struct FrameArgs {
   const double* poses;
   long long frame0;   // first frame of this launch
   CamDesc cam;
+  const double* frameK;   // per-frame (fx, fy, cx, cy) [cap,4] or nullptr: one K for the scene (dataloader/iphone.py:290-367 reads K per frame)
 };
 
-__device__ __forceinline__ void load_pose(const double* poses, long long f, double* sT) {
-  if (threadIdx.x < 16) sT[threadIdx.x] = poses[f * 16 + threadIdx.x];
+// sT[0..15] = pose of frame f, sT[16..19] = its intrinsics when the scene carries per-frame K
+__device__ __forceinline__ void load_pose(const FrameArgs& a, long long f, double* sT) {
+  if (threadIdx.x < 16) sT[threadIdx.x] = a.poses[f * 16 + threadIdx.x];
+  else if (threadIdx.x < 20 && a.frameK) sT[threadIdx.x] = a.frameK[f * 4 + threadIdx.x - 16];
   __syncthreads();
+}
+__device__ __forceinline__ CamDesc frame_cam(const FrameArgs& a, const double* sT) {
+  CamDesc c = a.cam;
+  if (a.frameK) { c.fx = sT[16]; c.fy = sT[17]; c.cx = sT[18]; c.cy = sT[19]; }
+  return c;
 }
 
 // ----------------------------------------------------------------------------- A1 dense
 __global__ void __launch_bounds__(TPB) k_unproject_dense(FrameArgs a, double* xyz, double* rgbo, uint8_t* valid) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   long long f = a.frame0;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -57,7 +66,7 @@ __global__ void __launch_bounds__(TPB) k_unproject_dense(FrameArgs a, double* xy
   // generic.py:117  mask = depth_f32 > 0
   bool ok = __fdiv_rn((float)dep, a.cam.scale) > 0.0f;
   if (ok) {
-    unproject_px(dep, x, y, a.cam, sT, wx, wy, wz);
+    unproject_px(dep, x, y, cam, sT, wx, wy, wz);
     const uint8_t* c = a.rgb + (f * HW + p) * 3;
     r = __ddiv_rn((double)c[0], 255.0);
     g = __ddiv_rn((double)c[1], 255.0);
@@ -72,10 +81,11 @@ __global__ void __launch_bounds__(TPB) k_unproject_dense(FrameArgs a, double* xy
 // grid = (blocks_per_frame, n_frames).  Thread handles 4 consecutive pixels (W % 4 == 0 not
 // required: pixels are addressed linearly inside the frame).
 __global__ void __launch_bounds__(TPB) k_bounds(FrameArgs a, long long* bounds) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   __shared__ double red[6][TPB / 32];
   long long f = a.frame0 + blockIdx.y;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   double mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
@@ -94,7 +104,7 @@ __global__ void __launch_bounds__(TPB) k_bounds(FrameArgs a, long long* bounds) 
         int p = p0 + i;
         int y = p / a.cam.W, x = p - y * a.cam.W;
         double w[3];
-        unproject_px(dv[i], x, y, a.cam, sT, w[0], w[1], w[2]);
+        unproject_px(dv[i], x, y, cam, sT, w[0], w[1], w[2]);
 #pragma unroll
         for (int k = 0; k < 3; k++) { mn[k] = fmin(mn[k], w[k]); mx[k] = fmax(mx[k], w[k]); }
       }
@@ -140,9 +150,10 @@ __device__ __forceinline__ void load4_depth(const uint16_t* dp, int p0, int HW, 
 // pass 2a: mark occupancy.  Test-then-set: after the first few frames nearly every bit is
 // already set, so the pass degenerates into cached bitmap reads (no atomics).
 __global__ void __launch_bounds__(TPB) k_mark(FrameArgs a, GridDesc g, uint32_t* bitmap) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   long long f = a.frame0 + blockIdx.y;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (p0 >= HW) return;
@@ -155,7 +166,7 @@ __global__ void __launch_bounds__(TPB) k_mark(FrameArgs a, GridDesc g, uint32_t*
       int p = p0 + i;
       int y = p / a.cam.W, x = p - y * a.cam.W;
       double wx, wy, wz;
-      unproject_px(dv[i], x, y, a.cam, sT, wx, wy, wz);
+      unproject_px(dv[i], x, y, cam, sT, wx, wy, wz);
       int ci, cj, ck;
       if (cell_of(g, wx, wy, wz, ci, cj, ck)) {
         long long lin = cell_lin(g, ci, cj, ck);
@@ -240,9 +251,10 @@ __global__ void __launch_bounds__(TPB) k_prefix_write(const uint32_t* bitmap, lo
 // that one lane per run issues the 7 reductions (neighbouring pixels share voxels heavily).
 __global__ void __launch_bounds__(TPB) k_accumulate(FrameArgs a, GridDesc g, const uint32_t* bitmap, const uint32_t* prefix,
                                                     double* acc, uint32_t* cnt) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   long long f = a.frame0 + blockIdx.y;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
   unsigned short dv[4] = {0, 0, 0, 0};
@@ -262,7 +274,7 @@ __global__ void __launch_bounds__(TPB) k_accumulate(FrameArgs a, GridDesc g, con
       int p = p0 + i;
       int y = p / a.cam.W, x = p - y * a.cam.W;
       double w[3];
-      unproject_px(dv[i], x, y, a.cam, sT, w[0], w[1], w[2]);
+      unproject_px(dv[i], x, y, cam, sT, w[0], w[1], w[2]);
       int ci, cj, ck;
       if (cell_of(g, w[0], w[1], w[2], ci, cj, ck)) {
         long long lin = cell_lin(g, ci, cj, ck);
@@ -533,9 +545,10 @@ __device__ __forceinline__ int nn_search(const GridDesc& g, const uint32_t* __re
 // per-frame API kernel: idx int64 (-1 invalid), dist f64
 __global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const uint32_t* cbm,
                                                        const double* nodes, int64_t* idx, double* dist) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   long long f = a.frame0;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -544,7 +557,7 @@ __global__ void __launch_bounds__(TPB) k_pixel_to_node(FrameArgs a, GridDesc g, 
   if (__fdiv_rn((float)dep, a.cam.scale) > 0.0f) {
     int y = p / a.cam.W, x = p - y * a.cam.W;
     double wx, wy, wz, best;
-    unproject_px(dep, x, y, a.cam, sT, wx, wy, wz);
+    unproject_px(dep, x, y, cam, sT, wx, wy, wz);
     o = nn_search(g, bm, pf, cbm, nodes, wx, wy, wz, best);
     dd = sqrt(best);
   }
@@ -569,10 +582,11 @@ __global__ void __launch_bounds__(TPB) k_points_to_node(const double* pts, long 
 __global__ void __launch_bounds__(TPB) k_nn_winner(FrameArgs a, GridDesc g, const uint32_t* bm, const uint32_t* pf, const double* nodes,
                                                    int32_t* pix_idx, unsigned long long* win, long long n_nodes, uint32_t epoch, int* far_list,
                                                    int* far_count) {
-  __shared__ double sT[16];
+  __shared__ double sT[20];
   int fb = blockIdx.y;
   long long f = a.frame0 + fb;
-  load_pose(a.poses, f, sT);
+  load_pose(a, f, sT);
+  const CamDesc cam = frame_cam(a, sT);
   int HW = a.cam.H * a.cam.W;
   int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= HW) return;
@@ -581,7 +595,7 @@ __global__ void __launch_bounds__(TPB) k_nn_winner(FrameArgs a, GridDesc g, cons
   if (__fdiv_rn((float)dep, a.cam.scale) > 0.0f) {
     int y = p / a.cam.W, x = p - y * a.cam.W;
     double wx, wy, wz, best;
-    unproject_px(dep, x, y, a.cam, sT, wx, wy, wz);
+    unproject_px(dep, x, y, cam, sT, wx, wy, wz);
     o = nn_search_fast(g, bm, pf, nodes, wx, wy, wz, best);
     if (o >= 0) atomicMax(&win[(long long)fb * n_nodes + o], ((unsigned long long)epoch << 32) | (unsigned)p);
     else far_list[atomicAdd(far_count, 1)] = fb * HW + p;
@@ -604,7 +618,9 @@ __global__ void __launch_bounds__(TPB) k_nn_far(FrameArgs a, GridDesc g, const u
     unsigned short dep = a.depth[f * HW + p];
     int y = p / a.cam.W, x = p - y * a.cam.W;
     double wx, wy, wz, best;
-    unproject_px(dep, x, y, a.cam, T, wx, wy, wz);
+    CamDesc cam = a.cam;
+    if (a.frameK) { cam.fx = a.frameK[f * 4]; cam.fy = a.frameK[f * 4 + 1]; cam.cx = a.frameK[f * 4 + 2]; cam.cy = a.frameK[f * 4 + 3]; }
+    unproject_px(dep, x, y, cam, T, wx, wy, wz);
     int o = nn_search_rings(g, bm, pf, cbm, nodes, wx, wy, wz, best);
     if (o >= 0) atomicMax(&win[(long long)fb * n_nodes + o], ((unsigned long long)epoch << 32) | (unsigned)p);
     pix_idx[(long long)fb * HW + p] = o;
@@ -634,7 +650,7 @@ __global__ void __launch_bounds__(TPB) k_coarse_mark(const uint32_t* __restrict_
 // ======================================================================================
 static FrameArgs frame_args(hmsg_ctx* ctx, long long frame0) {
   FrameArgs a;
-  a.depth = ctx->depth; a.rgb = ctx->rgb; a.poses = ctx->poses; a.frame0 = frame0; a.cam = ctx->cam;
+  a.depth = ctx->depth; a.rgb = ctx->rgb; a.poses = ctx->poses; a.frame0 = frame0; a.cam = ctx->cam; a.frameK = ctx->frameK;
   return a;
 }
 
@@ -644,10 +660,12 @@ extern "C" int32_t hmsg_scene_begin(hmsg_ctx* ctx, int32_t H, int32_t W, const d
   if (H <= 0 || W <= 0 || !K || depth_scale <= 0 || voxel_size <= 0 || frame_capacity <= 0)
     return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_begin: bad argument");
   HMSG_CUDA(cudaSetDevice(ctx->device));
-  free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses);
+  free_dev(ctx->depth); free_dev(ctx->rgb); free_dev(ctx->poses); free_dev(ctx->frameK);
   ctx->cam.H = H; ctx->cam.W = W; ctx->cam.fx = K[0]; ctx->cam.fy = K[4]; ctx->cam.cx = K[2]; ctx->cam.cy = K[5];
   ctx->cam.scale = depth_scale; ctx->vs = voxel_size;
   ctx->cap = frame_capacity; ctx->nframes = 0;
+  if (!ctx->uploads.empty()) HMSG_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+  ctx->uploads.clear(); ctx->upload_events_used = 0;
   size_t hw = (size_t)H * W;
   HMSG_CUDA(cudaMalloc((void**)&ctx->depth, hw * 2 * frame_capacity));
   HMSG_CUDA(cudaMalloc((void**)&ctx->rgb, hw * 3 * frame_capacity));
@@ -655,6 +673,25 @@ extern "C" int32_t hmsg_scene_begin(hmsg_ctx* ctx, int32_t H, int32_t W, const d
   if (!ctx->d_bounds) HMSG_CUDA(cudaMalloc((void**)&ctx->d_bounds, 6 * sizeof(long long)));
   ctx->voxels_built = false; ctx->nodes_built = false; ctx->n_voxels = 0; ctx->n_nodes = 0;
   ctx->batch_begin = -1;
+  return HMSG_OK;
+}
+
+// per-frame intrinsics (dataloader/iphone.py:290-367: `camera_matrix = np.array(self.frames[image_id - 1]["K"])` inside create_pcd)
+extern "C" int32_t hmsg_scene_set_intrinsics(hmsg_ctx* ctx, int64_t frame_begin, int32_t n, const double* K) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->depth) return ctx->fail(HMSG_ERR_STATE, "hmsg_scene_set_intrinsics: call hmsg_scene_begin first");
+  if (!K || n <= 0 || frame_begin < 0 || frame_begin + n > ctx->cap) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_set_intrinsics: bad argument");
+  if (!ctx->frameK) {   // every frame starts with the scene's K
+    HMSG_CUDA(cudaMalloc((void**)&ctx->frameK, (size_t)ctx->cap * 32));
+    std::vector<double> init((size_t)ctx->cap * 4);
+    for (int64_t f = 0; f < ctx->cap; f++) { init[f * 4] = ctx->cam.fx; init[f * 4 + 1] = ctx->cam.fy; init[f * 4 + 2] = ctx->cam.cx; init[f * 4 + 3] = ctx->cam.cy; }
+    HMSG_CUDA(cudaMemcpy(ctx->frameK, init.data(), init.size() * 8, cudaMemcpyHostToDevice));
+  }
+  std::vector<double> k4((size_t)n * 4);
+  for (int i = 0; i < n; i++) { k4[i * 4] = K[i * 9]; k4[i * 4 + 1] = K[i * 9 + 4]; k4[i * 4 + 2] = K[i * 9 + 2]; k4[i * 4 + 3] = K[i * 9 + 5]; }
+  HMSG_CUDA(cudaMemcpyAsync(ctx->frameK + frame_begin * 4, k4.data(), k4.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  HMSG_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->voxels_built = false; ctx->nodes_built = false;
   return HMSG_OK;
 }
 

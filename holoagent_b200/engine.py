@@ -152,6 +152,11 @@ class HmsgEngine:
         if dev:
             self.torch_wait()     # torch may recycle the (possibly temporary) input tensors only after our copy
 
+    def set_intrinsics(self, frame_begin, K):
+        """per-frame depth intrinsics: K float64 [n,3,3] for frames frame_begin.. (iphone.py:325 reads K per frame)"""
+        K = np.ascontiguousarray(K, dtype=np.float64).reshape(-1, 9)
+        self._ck(self.lib.hmsg_scene_set_intrinsics(self.h, int(frame_begin), int(len(K)), ptr(K)))
+
     @property
     def num_frames(self):
         return int(self.lib.hmsg_scene_num_frames(self.h))

@@ -130,6 +130,12 @@ class B200HotPath:
                 dd[k], cc[k], pp[k] = depth, rgb, np.asarray(pose, dtype=np.float64).reshape(16)
                 rgbs.append(rgb)
             eng.put_frames_host(b0, dd, cc, pp)
+            # datasets whose create_pcd reads the intrinsics per frame (dataloader/iphone.py:325: frames[image_id - 1]["K"])
+            ds = self.dataset
+            if hasattr(ds, "frame_K"):
+                eng.set_intrinsics(b0, np.stack([np.asarray(ds.frame_K(i), dtype=np.float64) for i in chunk]))
+            elif hasattr(ds, "frames") and hasattr(ds, "indices"):
+                eng.set_intrinsics(b0, np.stack([np.asarray(ds.frames[ds.indices[i] - 1]["K"], dtype=np.float64) for i in chunk]))
         eng.set_num_frames(nF)
         # ---- graph.py:348-358: voxel_down_sample, dbscan (identity), remove_radius_outlier
         eng.voxel_build()

@@ -78,6 +78,9 @@ int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, const uint16_t
                               const uint8_t* rgb, const double* poses, int32_t n_frames,
                               int32_t on_device);
 int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n_frames);
+/* per-frame depth intrinsics (dataloader/iphone.py:290-367 overrides create_pcd with `K = frames[image_id - 1]["K"]`): K float64
+ * [n,9] row-major HOST for the frames [frame_begin, frame_begin + n); frames without an entry keep the K of hmsg_scene_begin */
+int32_t hmsg_scene_set_intrinsics(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, const double* K);
 int64_t hmsg_scene_num_frames(const hmsg_ctx* ctx);
 /* forget the stored frames (capacity and intrinsics stay): the next add starts at frame id 0 */
 int32_t hmsg_scene_reset_frames(hmsg_ctx* ctx);
@@ -187,7 +190,7 @@ int32_t hmsg_mask_store_read(hmsg_ctx* ctx, int64_t frame, int32_t* n_masks, int
                              double* rgb, int32_t* ijk);
 
 /* ---- A9 encoder: open_clip ViT visual tower ------------------------------------------ */
-/* Supported: head dim 64 (width / heads), width / mlp / out_dim multiples of 256, image a multiple of patch,
+/* Supported: head dim 64 or 80 (width / heads; 80 = ViT-H-14, graph.py:105-111), width / mlp / out_dim multiples of 256, image a multiple of patch,
  * up to 4096 tokens: ViT-B-32 (graph.py:112-119, clip_feat_dim 512; values in the comments below), ViT-B-16 and the
  * config default ViT-L/14 (graph.py:98-104: image 224, patch 14, width 1024, 24 layers, 16 heads, mlp 4096, out 768). */
 typedef struct hmsg_vit_desc {

@@ -74,9 +74,18 @@ def test_vit_l14_full_size(engine):
     _check(out, ref)
 
 
+@pytest.mark.parametrize("image,B", [(56, 5), (112, 3)])
+def test_head_dim_80_tower(engine, image, B):
+    """ViT-H/14 geometry (graph.py:105-111: width 1280, 16 heads of 80, patch 14) on a 2-layer tower: 17 and 65 tokens"""
+    shape = synth.VitB32Shape(image=image, patch=14, width=1280, layers=2, heads=16, mlp=1280, out_dim=1024)
+    sd = _load(engine, shape, seed=80)
+    x = torch.randn(B, 3, image, image, generator=torch.Generator().manual_seed(B)) * 1.2
+    _check(engine.encode_images(x.numpy()), O.get_img_feats_batch_tensor(sd, x, heads=shape.heads))
+
+
 def test_encoder_load_rejects_unsupported_shapes(engine):
     sd = synth.make_vit_weights(synth.VitB32Shape(width=256, layers=1, heads=4, mlp=1024, out_dim=256))
-    with pytest.raises(RuntimeError):      # head dim must be 64
+    with pytest.raises(RuntimeError):      # head dim must be 64 or 80
         engine.encoder_load(sd, image=224, patch=32, width=256, layers=1, heads=8, mlp=1024, out_dim=256)
     with pytest.raises(RuntimeError):      # image not a multiple of the patch
         engine.encoder_load(sd, image=230, patch=32, width=256, layers=1, heads=4, mlp=1024, out_dim=256)

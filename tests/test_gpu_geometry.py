@@ -142,3 +142,33 @@ def test_staged_voxel_build_equals_monolithic(engine, built):
     assert nv == len(a[0]) and np.array_equal(mb, built["mb"])
     assert np.array_equal(a[2], b[2]) and np.array_equal(a[3], b[3])
     assert np.allclose(a[0], b[0], rtol=1e-12, atol=1e-12) and np.allclose(a[1], b[1], rtol=1e-12, atol=1e-12)
+
+
+def test_per_frame_intrinsics(engine):
+    """dataloader/iphone.py:290-367: create_pcd with the frame's own K - unprojection bit-exact, voxel table and NN follow"""
+    sc = scene(4, 120, 160, 5)
+    load_scene(engine, sc)
+    Ks = np.stack([sc["K"] * np.array([[1 + 0.01 * f, 1, 1 + 0.003 * f], [1, 1 - 0.008 * f, 1 - 0.002 * f], [1, 1, 1]]) for f in range(4)])
+    engine.set_intrinsics(1, Ks[1:])                      # frame 0 keeps the scene K
+    Ks[0] = sc["K"]
+    P, C = [], []
+    for f in range(4):
+        xyz, rgb, valid = engine.unproject_frame(f)
+        p, c, m = O.create_pcd(sc["rgb"][f], sc["depth"][f], Ks[f], sc["scale"], sc["poses"][f])
+        assert np.array_equal(valid, m.reshape(-1)) and np.array_equal(xyz[valid], p)
+        P.append(p); C.append(c)
+    nv, mb = engine.voxel_build()
+    ovx, _, oijk, inv = O.voxel_down_sample(np.concatenate(P), np.concatenate(C), sc["vs"])
+    vx, _, vijk, cnt = engine.voxels_read()
+    assert nv == len(ovx) and np.array_equal(vijk, oijk) and np.array_equal(cnt, np.bincount(inv, minlength=nv))
+    n = engine.radius_filter(40, 0.3)
+    nxyz, _, _, _ = engine.nodes_read()
+    from scipy.spatial import cKDTree
+    idx, dist = engine.pixel_to_node(2)
+    od, oi = cKDTree(nxyz).query(P[2], k=1)
+    v = (sc["depth"][2] > 0).reshape(-1)
+    assert np.allclose(dist[v], od, rtol=1e-12, atol=1e-14) and (idx[v] != oi).mean() < 1e-3
+    load_scene(engine, sc)                                # a new scene forgets the per-frame K
+    xyz, _, valid = engine.unproject_frame(2)
+    p, _, _ = O.create_pcd(sc["rgb"][2], sc["depth"][2], sc["K"], sc["scale"], sc["poses"][2])
+    assert np.array_equal(xyz[valid], p)
