@@ -208,10 +208,16 @@ class IngestJob:
             if self.a7:
                 eng.mask_nodes_batch(b0, n, self.vs, self.max_mask_distance, keep=True)
         self._merge()
-        if self.host_out is None or self.host_out.shape[0] != eng.n_nodes:
-            self.host_out = torch.empty((eng.n_nodes, d), dtype=torch.float32).pin_memory()
-        eng.node_feats_finalize_host(self.host_out)
-        self.d2h_bytes = self.host_out.numel() * 4
+        if self.rank == 0:                     # the build's result (full_feats_array) lands on ONE host process, as in the reference
+            if self.host_out is None or self.host_out.shape[0] != eng.n_nodes:
+                self.host_out = torch.empty((eng.n_nodes, d), dtype=torch.float32).pin_memory()
+            eng.node_feats_finalize_host(self.host_out)
+            self.d2h_bytes = self.host_out.numel() * 4
+        else:                                  # the other ranks keep their (identical) copy in HBM for retrieval
+            if self.full_feats is None or self.full_feats.shape[0] != eng.n_nodes:
+                self.full_feats = torch.empty((eng.n_nodes, d), dtype=torch.float32, device=self.boxes_dev.device)
+            eng.node_feats_finalize(self.full_feats)
+            self.d2h_bytes = 0
 
     def release(self):
         self.syn_crops = None

@@ -1,6 +1,7 @@
 """torchrun --nproc-per-node N scripts/check_multigpu.py [--collective c|torch] [--frames F]: the frame-sharded ingest
-(geometry collectives + node-embedding merge) must give the same node table and node features as the single-GPU job
-(fp32 sums differ only by summation order) and the same 3-D mask store for the frames each rank owns."""
+(every rank holds only its contiguous frame block; geometry collectives + node-embedding merge) must give the same node
+table and node features as the single-GPU job over all frames (fp32 sums differ only by summation order) and the same
+3-D mask store for the frames each rank owns."""
 import argparse, os, sys
 import numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -16,24 +17,35 @@ args = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+dev = f"cuda:{local}"
 F, H, W, M, FB = args.frames, args.H, args.W, 32, 16
 eng = HmsgEngine(local)
-d, c, T, K = synth.make_frames(np.arange(F), H, W, device=f"cuda:{local}")
-eng.scene_begin(H, W, K, 1000.0, 0.05, F)
-eng.add_frames(d.view(torch.int16), c, torch.from_numpy(T.reshape(F, 16)).cuda()); eng.sync()
-boxes = torch.from_numpy(np.stack([synth.make_mask_boxes(i, H, W, M) for i in range(F)])).cuda()
 eng.encoder_load(synth.make_vit_weights())
-job = ingest.IngestJob(eng, F, FB, M, 512, boxes, rank=rank, world=world, collective=args.collective)
+K = synth.intrinsics(H, W)
+
+
+def load(ids):
+    d, c, T, _ = synth.make_frames(ids, H, W, device=dev)
+    eng.scene_begin(H, W, K, 1000.0, 0.05, max(len(ids), 1))
+    eng.add_frames(d.view(torch.int16), c, torch.from_numpy(T.reshape(len(ids), 16)).to(dev)); eng.sync()
+    return torch.from_numpy(np.stack([synth.make_mask_boxes(int(i), H, W, M) for i in ids])).to(dev)
+
+
+# ---- sharded: this rank's block only
+g0, cnt = ingest.frame_block(F, world, rank)
+boxes = load(np.arange(g0, g0 + cnt))
+job = ingest.IngestJob(eng, cnt, FB, M, 512, boxes, rank=rank, world=world, collective=args.collective, total_frames=F)
 job.step_device(); eng.sync()
 multi = job.full_feats.clone()
 nodes_multi = eng.nodes_read()
-b0, cnt = ingest.frame_block(F, world, rank)
-mine = eng.mask_store_read(b0 + cnt - 1)
-single_job = ingest.IngestJob(eng, F, FB, M, 512, boxes, rank=0, world=1)
+mine = eng.mask_store_read(cnt - 1)                       # local frame id of the last frame of the block
+# ---- single GPU over all frames (every rank repeats it)
+boxes_all = load(np.arange(F))
+single_job = ingest.IngestJob(eng, F, FB, M, 512, boxes_all, rank=0, world=1)
 single_job.step_device(); eng.sync()
 single = single_job.full_feats
 nodes_single = eng.nodes_read()
-ref = eng.mask_store_read(b0 + cnt - 1)
+ref = eng.mask_store_read(g0 + cnt - 1)
 err = (multi - single).abs().max().item()
 same_nodes = np.array_equal(nodes_multi[2], nodes_single[2]) and np.allclose(nodes_multi[0], nodes_single[0], rtol=1e-12, atol=1e-12)
 same_masks = np.array_equal(mine[0], ref[0]) and np.array_equal(mine[3], ref[3]) and np.allclose(mine[1], ref[1], rtol=1e-9, atol=1e-9)

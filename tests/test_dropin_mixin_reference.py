@@ -19,10 +19,11 @@ NS = types.SimpleNamespace
 D = 128
 
 
-@pytest.fixture(scope="module")
-def ref_graph():
+def _ref_graph():
+    """import the reference behind the fixture harness (patches sys.modules / torch: only ever called in the child process)"""
     here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
     sys.path.insert(0, here)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     import ref_shims
     ref_shims.install()
     import memory.hmsg.graph.graph as rg
@@ -41,7 +42,22 @@ def _populate(g, rs, table):
     g.clip_model, g.clip_feat_dim, g.cfg = None, D, None
 
 
-def test_reference_glue_reaches_b200_cores(ref_graph, tmp_path, monkeypatch):
+def test_reference_glue_reaches_b200_cores(tmp_path):
+    """runs `_check` in a child process: the import harness replaces open3d / faiss / torch.Tensor.cuda process-wide"""
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), str(tmp_path)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MIXIN_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-3000:]
+
+
+class _Patch:
+    def setattr(self, obj, name, val):
+        setattr(obj, name, val)
+
+    def chdir(self, p):
+        os.chdir(str(p))
+
+
+def _check(ref_graph, tmp_path, monkeypatch):
     from holoagent_b200.memory.hmsg.graph.graph import B200HotPath, dropin_graph_class
     from tests.fake_engine import OracleRetrievalEngine
     rs = np.random.RandomState(7)
@@ -83,3 +99,8 @@ def test_reference_glue_reaches_b200_cores(ref_graph, tmp_path, monkeypatch):
                 assert [r.room_id for r in a[1]] == [r.room_id for r in b[1]], (ins, fn)
                 assert [o.object_id for o in a[2]] == [o.object_id for o in b[2]], (ins, fn)
                 assert np.allclose(a[3].get("object_scores", []), b[3].get("object_scores", []), atol=1e-6)
+
+
+if __name__ == "__main__":
+    _check(_ref_graph(), sys.argv[1], _Patch())
+    print("MIXIN_OK")

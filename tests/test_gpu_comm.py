@@ -59,5 +59,5 @@ def test_multi_gpu_ingest_equals_single(collective):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", "29631", os.path.join(ROOT, "scripts", "check_multigpu.py"), "--collective", collective, "--frames", "48"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0, (r.stdout[-1500:] + "\n" + "\n".join(l for l in r.stderr.splitlines() if "Error" in l or "error" in l or "assert" in l.lower())[-2500:])
     assert "identical_across_ranks=True" in r.stdout

@@ -172,3 +172,36 @@ def test_per_frame_intrinsics(engine):
     xyz, _, valid = engine.unproject_frame(2)
     p, _, _ = O.create_pcd(sc["rgb"][2], sc["depth"][2], sc["K"], sc["scale"], sc["poses"][2])
     assert np.array_equal(xyz[valid], p)
+
+
+def test_far_outlier_pixels_do_not_break_the_voxel_index(engine):
+    """One stray 60 m depth sample and one frame posed 150 m away inflate the scene's bounding box ~2000x: the dense
+    occupancy index (1 bit per cell of the box) must still build and match the oracle (graph.py:344-348 has no extent
+    limit; the limit here is 2^37 cells, stated in DESIGN.md)."""
+    sc = scene(4, 120, 160, 5)
+    depth = sc["depth"].copy(); poses = sc["poses"].copy()
+    depth[1, 60, 80] = 60000                                # 60 m along the optical axis
+    poses[3, :3, 3] += np.array([150.0, 0.0, -40.0])        # a badly posed frame
+    engine.scene_begin(sc["H"], sc["W"], sc["K"], sc["scale"], sc["vs"], 4)
+    engine.add_frames(depth, sc["rgb"], poses.reshape(-1, 16))
+    nv, mb = engine.voxel_build()
+    P, C = [], []
+    for f in range(4):
+        p, c, _ = O.create_pcd(sc["rgb"][f], depth[f], sc["K"], sc["scale"], poses[f])
+        P.append(p); C.append(c)
+    P = np.concatenate(P); C = np.concatenate(C)
+    ovx, ovc, oijk, inv = O.voxel_down_sample(P, C, sc["vs"])
+    vx, _, vijk, cnt = engine.voxels_read()
+    assert nv == len(ovx) and np.array_equal(mb, P.min(axis=0))
+    assert np.array_equal(vijk, oijk) and np.array_equal(cnt, np.bincount(inv, minlength=nv))
+    assert np.allclose(vx, ovx, rtol=1e-12, atol=1e-12)
+    assert vijk.max() > 2500                                # the grid really is thousands of cells wide
+    n = engine.radius_filter(40, 0.3)
+    keep = O.radius_outlier_keep(ovx, 40, 0.3)
+    assert n == len(keep) and np.array_equal(engine.nodes_read()[3], keep)
+    idx, dist = engine.pixel_to_node(1)
+    from scipy.spatial import cKDTree
+    p1, _, m1 = O.create_pcd(sc["rgb"][1], depth[1], sc["K"], sc["scale"], poses[1])
+    od, oi = cKDTree(ovx[keep]).query(p1, k=1)
+    v = m1.reshape(-1)
+    assert np.allclose(dist[v], od, rtol=1e-12, atol=1e-14) and (idx[v] != oi).mean() < 1e-3
