@@ -98,12 +98,31 @@ class B200HotPath:
         self.exact_mask_sums = False     # True: per-frame create_3d_masks with Open3D's ordered float64 sums (bit-identical, slower)
         self.views = getattr(self, "views", [])
 
+    def _ensure_encoder(self):
+        """Drop-in mode: the reference constructor built `self.clip_model` with open_clip (graph.py:98-119).  Its visual
+        tower is copied into the engine once; the text tower stays where it is."""
+        eng = self.engine
+        if getattr(eng, "vit", None) is not None:
+            return
+        cm = getattr(self, "clip_model", None)
+        v = getattr(cm, "visual", None)
+        if v is None or not hasattr(v, "state_dict"):
+            raise RuntimeError("no encoder loaded: pass a B200ClipModel (or an open_clip model with a .visual tower) as clip_model")
+        sd = {k: t.float() for k, t in v.state_dict().items()}
+        width = sd["conv1.weight"].shape[0]
+        layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
+        image = v.image_size[0] if hasattr(v.image_size, "__len__") else v.image_size
+        heads = getattr(getattr(v.transformer.resblocks[0], "attn", None), "num_heads", width // 64)
+        eng.encoder_load(sd, image=int(image), patch=int(sd["conv1.weight"].shape[-1]), width=int(width), layers=int(layers), heads=int(heads),
+                         mlp=int(sd["transformer.resblocks.0.mlp.c_fc.weight"].shape[0]), out_dim=int(sd["proj"].shape[1]))
+
     # ------------------------------------------------------------------ build (graph.py:262-415)
     def create_feature_map(self, save_path=None):
         if self.dataset is None:
             print("No dataset loaded")          # graph.py:267-269
             return
         import torch
+        self._ensure_encoder()
         eng, p = self.engine, self.cfg.pipeline
         g = lambda k, dflt: getattr(p, k, dflt) if not isinstance(p, dict) else p.get(k, dflt)
         skip = int(p.skip_frames)

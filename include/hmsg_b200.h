@@ -51,7 +51,11 @@ int32_t     hmsg_version(void);
  *                         kernel, 4 double-buffered tiles, 5 any-T online-softmax kernel (always used for T > 64)
  *   "last_layer_cls_only" 0|1  last transformer block computes only the class-token row past K/V (default 1)
  *   "crops_mma"           0|1  PIL passes of the mask crops as int8 tensor-core MMAs (default 1) or scalar kernels
- *   "knn_bq"              queries per pass, 0 = auto */
+ *   "knn_bq"              queries per pass, 0 = auto
+ *   "ln_fold"             0|1  encoder: LayerNorms folded into the QKV / FC GEMM epilogues over an fp16 residual stream (default 1)
+ *                              or fp32 residual stream + LayerNorm kernels (0); both within 1e-3 of the fp32 oracle
+ *   "mask3d_path"         1 global (mask, node) hash + radix sort (default), 0 per-mask on-chip kernels (masks <= 8 k nodes,
+ *                              falls back to 1 on overflow) */
 int32_t     hmsg_set_option(hmsg_ctx* ctx, const char* key, int32_t value);
 /* Per-kernel-class device timing with CUDA events on the ctx stream (bench.py roofline).
  * class: 0 gemm (work = flops), 1 attention, 2 elementwise/LN, 3 knn pass (work = bytes of E
