@@ -34,6 +34,7 @@ SIGNATURES = {
     "hmsg_scene_put_frames": (_i32, [_vp, _i64, _vp, _vp, _vp, _i32, _i32]),
     "hmsg_scene_set_num_frames": (_i32, [_vp, _i64]),
     "hmsg_scene_set_intrinsics": (_i32, [_vp, _i64, _i32, _vp]),
+    "hmsg_scene_put_rgb": (_i32, [_vp, _i64, _vp, _i32, _i32]),
     "hmsg_scene_num_frames": (_i64, [_vp]),
     "hmsg_unproject_frame": (_i32, [_vp, _i64, _vp, _vp, _vp]),
     "hmsg_voxel_build": (_i32, [_vp, C.POINTER(_i64), _vp]),

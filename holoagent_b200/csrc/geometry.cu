@@ -746,6 +746,19 @@ extern "C" int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, con
   return HMSG_OK;
 }
 
+extern "C" int32_t hmsg_scene_put_rgb(hmsg_ctx* ctx, int64_t frame_begin, const uint8_t* rgb, int32_t n, int32_t on_device) {
+  if (!ctx) return HMSG_ERR_ARG;
+  if (!ctx->rgb) return ctx->fail(HMSG_ERR_STATE, "hmsg_scene_put_rgb: call hmsg_scene_begin first");
+  if (!rgb || n < 0 || frame_begin < 0) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_put_rgb: bad argument");
+  if (frame_begin + n > ctx->nframes) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_put_rgb: frames not stored yet");
+  // ordered on the compute stream after every kernel that still reads the old colours (the voxel accumulation); the frames'
+  // own uploads must have landed first
+  ctx->wait_frames(frame_begin, n);
+  size_t hw = (size_t)ctx->cam.H * ctx->cam.W;
+  HMSG_CUDA(cudaMemcpyAsync(ctx->rgb + hw * 3 * frame_begin, rgb, hw * 3 * n, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  return HMSG_OK;
+}
+
 extern "C" int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n) {
   if (!ctx) return HMSG_ERR_ARG;
   if (n < 0 || n > ctx->cap) return ctx->fail(HMSG_ERR_ARG, "hmsg_scene_set_num_frames: out of range");

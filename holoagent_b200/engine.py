@@ -514,6 +514,12 @@ class HmsgEngine:
         poses_np = np.ascontiguousarray(poses_np, dtype=np.float64)
         self._ck(self.lib.hmsg_scene_put_frames(self.h, int(frame_begin), ptr(depth_t), ptr(rgb_t), ptr(poses_np), int(depth_t.shape[0]), 0))
 
+    def put_rgb_host(self, frame_begin, rgb):
+        """swap the colour images of stored frames (geometry stays valid): hmsg_scene_put_rgb"""
+        rgb = np.ascontiguousarray(rgb, dtype=np.uint8)
+        self._ck(self.lib.hmsg_scene_put_rgb(self.h, int(frame_begin), ptr(rgb), int(rgb.shape[0]), 0))
+        self.sync()          # pageable source: the copy must be done before `rgb` can go away
+
     def node_feats_finalize_host(self, out_t):
         self._ck(self.lib.hmsg_node_feats_finalize(self.h, ptr(out_t), 0))
 

@@ -82,6 +82,12 @@ int32_t hmsg_scene_put_frames(hmsg_ctx* ctx, int64_t frame_begin, const uint16_t
                               const uint8_t* rgb, const double* poses, int32_t n_frames,
                               int32_t on_device);
 int32_t hmsg_scene_set_num_frames(hmsg_ctx* ctx, int64_t n_frames);
+/* replace ONLY the colour image of stored frames; depth, poses and everything built from them (voxel / node table, pixel->node
+ * indices) stay valid.  For datasets whose rgb and depth sizes differ the reference uses two different resized images: point
+ * colours come from cv2.resize(..., INTER_AREA) inside create_pcd (dataloader/generic.py:98-104), the crops of the feature pass
+ * from PIL `rgb_image.resize(depth_image.size)` (bicubic, graph.py:378-379).  Upload the first with hmsg_scene_put_frames, build
+ * the geometry, then swap in the second before hmsg_masks_* / hmsg_encode_crops.  rgb uint8 [n,H,W,3]; ctx stream */
+int32_t hmsg_scene_put_rgb(hmsg_ctx* ctx, int64_t frame_begin, const uint8_t* rgb, int32_t n_frames, int32_t on_device);
 /* per-frame depth intrinsics (dataloader/iphone.py:290-367 overrides create_pcd with `K = frames[image_id - 1]["K"]`): K float64
  * [n,9] row-major HOST for the frames [frame_begin, frame_begin + n); frames without an entry keep the K of hmsg_scene_begin */
 int32_t hmsg_scene_set_intrinsics(hmsg_ctx* ctx, int64_t frame_begin, int32_t n_frames, const double* K);
