@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fail |= p.returncode != 0
     if fail:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart", "-ldl"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -116,6 +116,12 @@ class B200HotPath:
         eng.encoder_load(sd, image=int(image), patch=int(sd["conv1.weight"].shape[-1]), width=int(width), layers=int(layers), heads=int(heads),
                          mlp=int(sd["transformer.resblocks.0.mlp.c_fc.weight"].shape[0]), out_dim=int(sd["proj"].shape[1]))
 
+    @staticmethod
+    def _resize_for_points(rgb, depth_shape):
+        """generic.py:98-104: create_pcd brings the colour image to the depth size with cv2.resize(..., INTER_AREA)"""
+        import cv2
+        return cv2.resize(rgb, (int(depth_shape[1]), int(depth_shape[0])), interpolation=cv2.INTER_AREA)
+
     # ------------------------------------------------------------------ build (graph.py:262-415)
     def create_feature_map(self, save_path=None):
         if self.dataset is None:
@@ -133,6 +139,7 @@ class B200HotPath:
         H, W = np.array(first[1]).shape
         eng.scene_begin(H, W, np.asarray(self.dataset.depth_intrinsics, dtype=np.float64), float(self.dataset.scale), float(p.voxel_size), nF)
         rgbs = []
+        resized = False                          # rgb and depth sizes differ somewhere: two resized colour images per frame
         for b0 in range(0, nF, FB):
             chunk = ids[b0:b0 + FB]
             dd = np.empty((len(chunk), H, W), np.uint16); cc = np.empty((len(chunk), H, W, 3), np.uint8); pp = np.empty((len(chunk), 16), np.float64)
@@ -140,13 +147,15 @@ class B200HotPath:
                 rgb_image, depth_image, pose, _, _ = self.dataset[i]
                 depth = np.array(depth_image).astype(np.uint16)
                 rgb = np.array(rgb_image).astype(np.uint8)
+                cc[k] = rgb if rgb.shape[:2] == depth.shape[:2] else self._resize_for_points(rgb, depth.shape)
                 if rgb.shape[:2] != depth.shape[:2]:
-                    # graph.py:378-379: the feature pass uses PIL `rgb_image.resize(depth_image.size)` (bicubic); the colours of
-                    # create_pcd come from a cv2 INTER_AREA resize (generic.py:98-104).  One image per frame is stored: the
-                    # feature-pass one (crops / embeddings match the reference; node colours differ slightly for such datasets)
+                    # graph.py:378-379: the feature pass (SAM + crops) sees PIL `rgb_image.resize(depth_image.size)` (bicubic);
+                    # the point colours of create_pcd come from a cv2 INTER_AREA resize (generic.py:98-104).  Geometry is built
+                    # from the second, then hmsg_scene_put_rgb swaps in the first for the crops.
                     from PIL import Image
                     rgb = np.asarray(Image.fromarray(rgb).resize((depth.shape[1], depth.shape[0])))
-                dd[k], cc[k], pp[k] = depth, rgb, np.asarray(pose, dtype=np.float64).reshape(16)
+                    resized = True
+                dd[k], pp[k] = depth, np.asarray(pose, dtype=np.float64).reshape(16)
                 rgbs.append(rgb)
             eng.put_frames_host(b0, dd, cc, pp)
             # datasets whose create_pcd reads the intrinsics per frame (dataloader/iphone.py:325: frames[image_id - 1]["K"])
@@ -174,6 +183,9 @@ class B200HotPath:
         if sp:
             self.save_full_pcd(path=sp)         # graph.py:359
         # ---- pass 2 (graph.py:373-411)
+        if resized:
+            for b0 in range(0, nF, FB):
+                eng.put_rgb_host(b0, np.stack(rgbs[b0:b0 + FB]))
         d = self.clip_feat_dim
         eng.features_begin(d)
         merge_type = g("merge_type", "sequential")

@@ -179,3 +179,39 @@ def test_view_and_room_retrieval_variants(engine, tmp_path):
     # floor by name
     fl = rs.randn(3, 512).astype(np.float32)
     assert g.query_floor("x", fl, query_feats=q) == int(np.argsort(np.dot(q, fl.T)[0])[::-1][0])
+
+
+def test_rgb_larger_than_depth_uses_both_resizes(engine):
+    """Datasets whose colour image is larger than the depth image: the point colours come from cv2 INTER_AREA
+    (generic.py:98-104), the feature pass from PIL bicubic (graph.py:378-379).  Limit (2) of round 1 is gone."""
+    import cv2
+    from PIL import Image
+    from holoagent_b200.memory.hmsg.graph.graph import Graph
+    from holoagent_b200.memory.hmsg.utils.clip_utils import B200ClipModel
+    base = _DS()
+    rs = np.random.RandomState(5)
+    big = [np.clip(cv2.resize(base.rgb[i], (2 * W, 2 * H), interpolation=cv2.INTER_CUBIC).astype(np.int32) + rs.randint(-20, 21, (2 * H, 2 * W, 3)), 0, 255).astype(np.uint8)
+           for i in range(NF)]
+
+    class _DS2(_DS):
+        def __getitem__(self, i):
+            return Image.fromarray(big[i]), Image.fromarray(self.depth[i]), self.T[i], self.K, self.K
+
+    ds = _DS2()
+    area = np.stack([cv2.resize(big[i], (W, H), interpolation=cv2.INTER_AREA) for i in range(NF)])
+    cubic = np.stack([np.asarray(Image.fromarray(big[i]).resize((W, H))) for i in range(NF)])
+    assert (area != cubic).mean() > 0.2                      # the two images really differ
+    sd = synth.make_vit_weights()
+    cfg = {"pipeline": {"voxel_size": 0.05, "skip_frames": 1, "clip_bbox_margin": 50, "clip_masked_weight": 0.4418, "max_mask_distance": 10000}}
+    g = Graph(cfg, dataset=ds, clip_model=B200ClipModel(engine, sd), mask_generator=_SAM(base), clip_feat_dim=D)
+    g.merge_objects = False
+    g.create_feature_map()
+    geo = O.build_geometry(base.depth, area, base.T, base.K, 1000.0, 0.05, 1000, 1.0)
+    assert np.allclose(np.asarray(g.full_pcd.points), geo["node_xyz"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(np.asarray(g.full_pcd.colors), geo["node_rgb"], rtol=1e-12, atol=1e-12)
+    sam = _SAM(base)
+    for f in range(2):
+        masks = sam.generate(cubic[f])
+        crops = O.crop_all_bounding_boxs(cubic[f], masks, True, 50) + O.crop_all_bounding_boxs(cubic[f], masks, False, 50) + [cubic[f]]
+        fe = O.get_img_feats_batch_tensor(sd, torch.stack([O.clip_preprocess(c) for c in crops]))
+        assert np.allclose(g.frames_feats[f].numpy(), O.fuse_mask_feats(fe[:M], fe[M:2 * M], fe[2 * M:], 0.4418), atol=1e-3)
