@@ -120,3 +120,46 @@ def test_two_graphs_sharing_one_engine_do_not_see_each_others_index():
     g.objects[3].embedding = q[0] * 10.0
     g.invalidate_index()
     assert g.query_hmsg_object("x", top_k=1, query_feats=q)[0] == [3]
+
+
+def test_dropin_mode_reads_the_visual_tower_of_the_reference_clip_model():
+    """Drop-in mode: the reference constructor leaves an open_clip model in self.clip_model (graph.py:98-119); the first
+    build hands its visual tower to the engine with the shape read off the state dict."""
+    import torch
+    from holoagent_b200 import synth
+    shape = synth.VitB32Shape(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, out_dim=64)
+    sd = synth.make_vit_weights(shape)
+
+    class _Attn:
+        num_heads = 2
+
+    class _Block:
+        attn = _Attn()
+
+    class _Visual:
+        image_size = (64, 64)
+        transformer = types.SimpleNamespace(resblocks=[_Block(), _Block()])
+
+        def state_dict(self):
+            return {k: v.half() for k, v in sd.items()}      # precision='fp16' checkpoints
+
+    got = {}
+
+    class _Eng:
+        vit = None
+
+        def encoder_load(self, state, **kw):
+            got["kw"] = kw
+            got["sd"] = state
+
+    g = Graph({"pipeline": {}}, engine=_Eng(), clip_feat_dim=64)
+    g.clip_model = types.SimpleNamespace(visual=_Visual())
+    g._ensure_encoder()
+    assert got["kw"] == dict(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, out_dim=64)
+    assert all(t.dtype == torch.float32 for t in got["sd"].values()) and torch.equal(got["sd"]["proj"], sd["proj"])
+    g.clip_model = types.SimpleNamespace()                    # no visual tower and nothing loaded: loud failure
+    try:
+        g._ensure_encoder()
+        assert False
+    except RuntimeError as e:
+        assert "no encoder loaded" in str(e)
