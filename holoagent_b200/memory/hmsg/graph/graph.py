@@ -108,13 +108,9 @@ class B200HotPath:
         v = getattr(cm, "visual", None)
         if v is None or not hasattr(v, "state_dict"):
             raise RuntimeError("no encoder loaded: pass a B200ClipModel (or an open_clip model with a .visual tower) as clip_model")
-        sd = {k: t.float() for k, t in v.state_dict().items()}
-        width = sd["conv1.weight"].shape[0]
-        layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
-        image = v.image_size[0] if hasattr(v.image_size, "__len__") else v.image_size
-        heads = getattr(getattr(v.transformer.resblocks[0], "attn", None), "num_heads", width // 64)
-        eng.encoder_load(sd, image=int(image), patch=int(sd["conv1.weight"].shape[-1]), width=int(width), layers=int(layers), heads=int(heads),
-                         mlp=int(sd["transformer.resblocks.0.mlp.c_fc.weight"].shape[0]), out_dim=int(sd["proj"].shape[1]))
+        from holoagent_b200.memory.hmsg.utils.clip_utils import visual_tower_shape
+        sd, shape = visual_tower_shape(v)
+        eng.encoder_load(sd, **shape)
 
     @staticmethod
     def _resize_for_points(rgb, depth_shape):

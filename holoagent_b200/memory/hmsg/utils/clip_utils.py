@@ -8,6 +8,23 @@ from __future__ import annotations
 import numpy as np
 
 
+def visual_tower_shape(v):
+    """(fp32 state dict, encoder_load keyword arguments) of an open_clip VisionTransformer (graph.py:98-119 builds ViT-L/14,
+    ViT-H-14 or ViT-B-32).  The head count comes from the attention module (ViT-H/14: 16 heads of 80, not width / 64), the
+    activation from the block's MLP (open_clip's `*-quickgelu` configs / OpenAI weights use QuickGELU)."""
+    sd = {k: t.float() for k, t in v.state_dict().items()}
+    width = int(sd["conv1.weight"].shape[0])
+    layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
+    image = v.image_size[0] if hasattr(v.image_size, "__len__") else v.image_size
+    blocks = getattr(getattr(v, "transformer", None), "resblocks", None)
+    blk = blocks[0] if blocks is not None and len(blocks) else None
+    heads = getattr(getattr(blk, "attn", None), "num_heads", None) or max(1, width // 64)
+    act = getattr(getattr(blk, "mlp", None), "gelu", None)
+    quick = type(act).__name__ == "QuickGELU"
+    return sd, dict(image=int(image), patch=int(sd["conv1.weight"].shape[-1]), width=width, layers=int(layers), heads=int(heads),
+                    mlp=int(sd["transformer.resblocks.0.mlp.c_fc.weight"].shape[0]), out_dim=int(sd["proj"].shape[1]), quick_gelu=quick)
+
+
 class B200ClipModel:
     """Holds the encoder loaded into an HmsgEngine.  ``encode_text`` is delegated to a user
     supplied callable (the text tower is outside the hot path: queries enter as vectors)."""
@@ -18,14 +35,11 @@ class B200ClipModel:
         self.text_encoder = text_encoder
 
     @classmethod
-    def from_open_clip(cls, engine, open_clip_model, text_encoder=None, quick_gelu=False):
-        v = open_clip_model.visual
-        sd = {k: t.float() for k, t in v.state_dict().items()}
-        width = sd["conv1.weight"].shape[0]
-        layers = 1 + max(int(k.split(".")[2]) for k in sd if k.startswith("transformer.resblocks."))
-        return cls(engine, sd, text_encoder, image=v.image_size[0] if hasattr(v.image_size, "__len__") else v.image_size,
-                   patch=sd["conv1.weight"].shape[-1], width=width, layers=layers, heads=width // 64,
-                   mlp=sd["transformer.resblocks.0.mlp.c_fc.weight"].shape[0], out_dim=sd["proj"].shape[1], quick_gelu=quick_gelu)
+    def from_open_clip(cls, engine, open_clip_model, text_encoder=None, quick_gelu=None):
+        sd, shape = visual_tower_shape(open_clip_model.visual)
+        if quick_gelu is not None:
+            shape["quick_gelu"] = bool(quick_gelu)
+        return cls(engine, sd, text_encoder, **shape)
 
     def encode_image_normalized(self, x):
         """x: torch tensor [B,3,S,S] (CPU or CUDA) -> np.float32 [B,d] unit rows."""

@@ -101,3 +101,22 @@ def test_vit_device_path_matches_host_path(engine, vit):
     a = engine.encode_images(x.numpy())
     b = engine.encode_images(x.cuda()).cpu().numpy()
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("ln_fold", [1, 0])
+def test_quick_gelu_tower(engine, ln_fold):
+    """open_clip's `*-quickgelu` configs (OpenAI weights): x * sigmoid(1.702 x) in the FC epilogue, both residual-stream forms"""
+    import dataclasses
+    shape = synth.VitB32Shape(width=256, layers=2, heads=4, mlp=1024, out_dim=256)
+    sd = synth.make_vit_weights(shape, seed=17)
+    engine.encoder_load(sd, quick_gelu=True, **dataclasses.asdict(shape))
+    engine.set_option("ln_fold", ln_fold)
+    try:
+        x = torch.randn(9, 3, 224, 224, generator=torch.Generator().manual_seed(4)) * 1.2
+        out = engine.encode_images(x.numpy())
+    finally:
+        engine.set_option("ln_fold", 1)
+    ref = O.get_img_feats_batch_tensor(sd, x, heads=4, quick_gelu=True)
+    assert np.abs(out - ref).max() <= 1e-3 and np.all(np.sum(out * ref, -1) > 1 - 1e-5)
+    plain = O.get_img_feats_batch_tensor(sd, x, heads=4)
+    assert np.abs(plain - ref).max() > 1e-3          # (1.45e-3 on these seeds) the activation matters at this size

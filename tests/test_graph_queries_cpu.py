@@ -155,8 +155,16 @@ def test_dropin_mode_reads_the_visual_tower_of_the_reference_clip_model():
     g = Graph({"pipeline": {}}, engine=_Eng(), clip_feat_dim=64)
     g.clip_model = types.SimpleNamespace(visual=_Visual())
     g._ensure_encoder()
-    assert got["kw"] == dict(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, out_dim=64)
+    assert got["kw"] == dict(image=64, patch=16, width=128, layers=2, heads=2, mlp=256, out_dim=64, quick_gelu=False)
     assert all(t.dtype == torch.float32 for t in got["sd"].values()) and torch.equal(got["sd"]["proj"], sd["proj"])
+    # OpenAI / *-quickgelu towers and ViT-H/14 (16 heads of 80) are recognised from the modules, not guessed from the width
+    class QuickGELU:
+        pass
+
+    _Block.mlp = types.SimpleNamespace(gelu=QuickGELU())
+    _Attn.num_heads = 4
+    g._ensure_encoder()
+    assert got["kw"]["quick_gelu"] is True and got["kw"]["heads"] == 4
     g.clip_model = types.SimpleNamespace()                    # no visual tower and nothing loaded: loud failure
     try:
         g._ensure_encoder()
