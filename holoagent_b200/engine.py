@@ -443,6 +443,8 @@ class HmsgEngine:
         self.vit = desc
 
     def encode_images(self, x, normalize=True, out=None):
+        if self.vit is None:
+            raise HmsgError("[3] encoder: call hmsg_encoder_load first")     # same status / text as the library's own check
         dev = _is_dev(x)
         B = x.shape[0]
         if not dev:
