@@ -1275,6 +1275,17 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
       cp_async_wait<0>();
     }
     named_bar_sync(1 + grp, 64);       // both warps' cp.async data is visible to both
+    if (NBUF == 1 && pair + tw < npairs) {
+      // single-buffered form: the group's next tile cannot be staged while this one is in use, but its 3 x T row segments
+      // (128 B each) can already be pulled into L2, so the next cp.async round pays L2 latency instead of DRAM latency
+      const long long np = pair + tw;
+      const int nb = (int)(np / heads), nh = (int)(np % heads);
+      const __half* nsrc = qkv + ((long long)nb * T) * ld + nh * 64;
+      for (int i = l64; i < 3 * T; i += 64) {
+        const int which = i / T, r = i - which * T;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (long long)r * ld + which * W));
+      }
+    }
     const __half* sQ = wbase + cur * 3 * ATT2_TILE;
     const __half* sK = sQ + ATT2_TILE;
     const __half* sV = sK + ATT2_TILE;

@@ -37,7 +37,7 @@ def test_calls_out_of_order_fail_with_state_errors():
         _raises(ARG, eng.put_rgb_host, 1, np.zeros((2, 60, 80, 3), np.uint8))              # frames 1..2: frame 2 is not stored
         _raises(STATE, eng.nodes_read)
         _raises(STATE, eng.pixel_to_node, 0)
-        _raises(STATE, eng.features_begin, 64)
+        _raises(STATE, eng.features_begin, 128)
         # ... and the ctx still works after all of that
         nv, _ = eng.voxel_build()
         eng.radius_filter(0, 0.5)
@@ -55,11 +55,11 @@ def test_mask_batch_misuse(engine):
     sc = scene(n_frames=3, H=60, W=80)
     load_scene(engine, sc)
     engine.voxel_build(); engine.radius_filter(0, 0.5)
-    engine.features_begin(64)
+    engine.features_begin(128)
     boxes = np.tile(np.array([[5, 5, 20, 20]], np.int32), (2, 3, 1))
     _raises(ARG, engine.masks_boxes, 2, boxes)                      # frames 2..3 of a 3-frame scene
     engine.masks_boxes(0, boxes)
     _raises(ARG, engine.masks_counts, 0, np.array([1, 4], np.int32))    # count above M
     import torch
-    feats = torch.zeros((2, 7, 64), device="cuda")
+    feats = torch.zeros((2, 7, 128), device="cuda")
     _raises(STATE, engine.fuse_scatter, 1, 2, 3, feats, 0.4418)    # batch 1..2 was never set
