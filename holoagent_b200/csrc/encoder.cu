@@ -1244,8 +1244,10 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
   const long long npairs = (long long)B * heads;
   const long long gw = (long long)blockIdx.x * ATT3_GROUPS + grp, tw = (long long)gridDim.x * ATT3_GROUPS;
   const int ld = 3 * W;
+  // (image, head) of a pair index: 32-bit division (B * heads < 2^31 is checked by the launcher; the 64-bit form is a
+  // ~100-instruction subroutine that sat at the head of every tile's load chain)
   auto issue = [&](long long pair, int bi) {
-    int b = (int)(pair / heads), h = (int)(pair % heads);
+    const int b = (int)((unsigned)pair / (unsigned)heads), h = (int)((unsigned)pair - (unsigned)b * (unsigned)heads);
     __half* sQ = wbase + bi * 3 * ATT2_TILE;
     const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
     for (int i = l64; i < T * 8; i += 64) {
@@ -1275,21 +1277,10 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
       cp_async_wait<0>();
     }
     named_bar_sync(1 + grp, 64);       // both warps' cp.async data is visible to both
-    if (NBUF == 1 && pair + tw < npairs) {
-      // single-buffered form: the group's next tile cannot be staged while this one is in use, but its 3 x T row segments
-      // (128 B each) can already be pulled into L2, so the next cp.async round pays L2 latency instead of DRAM latency
-      const long long np = pair + tw;
-      const int nb = (int)(np / heads), nh = (int)(np % heads);
-      const __half* nsrc = qkv + ((long long)nb * T) * ld + nh * 64;
-      for (int i = l64; i < 3 * T; i += 64) {
-        const int which = i / T, r = i - which * T;
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(nsrc + (long long)r * ld + which * W));
-      }
-    }
     const __half* sQ = wbase + cur * 3 * ATT2_TILE;
     const __half* sK = sQ + ATT2_TILE;
     const __half* sV = sK + ATT2_TILE;
-    const int b = (int)(pair / heads), h = (int)(pair % heads);
+    const int b = (int)((unsigned)pair / (unsigned)heads), h = (int)((unsigned)pair - (unsigned)b * (unsigned)heads);
     for (int mi = wsub; mi < m_tiles; mi += 2) {
       float s[8][4];
 #pragma unroll
@@ -1927,6 +1918,7 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
         vs->smem_attr_set = true;
       }
       long long pairs = (long long)B * d.heads;
+      if (pairs >= (1ll << 31)) return ctx->fail(HMSG_ERR_ARG, "attention: B * heads must be below 2^31");
       if (vs->attn_v3_db) {
         int grid = (int)std::min<long long>((pairs + 3) / 4, ctx->sm_count);
         k_attention_mma3<4, 2, 8><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);

@@ -69,6 +69,7 @@ class HmsgEngine:
         self.device = device
         self.H = self.W = 0
         self.d = 0
+        self.n_voxels = self.n_nodes = 0
         self.vit = None
 
     def close(self):
@@ -137,6 +138,7 @@ class HmsgEngine:
         K = np.ascontiguousarray(K, dtype=np.float64).reshape(9)
         self._ck(self.lib.hmsg_scene_begin(self.h, H, W, ptr(K), float(depth_scale), float(voxel_size), int(frame_capacity)))
         self.H, self.W = H, W
+        self.n_voxels = self.n_nodes = 0          # tables of the previous scene are gone
 
     def add_frames(self, depth, rgb, poses):
         dev = _is_dev(depth)
