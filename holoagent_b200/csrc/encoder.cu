@@ -1229,18 +1229,19 @@ __global__ void __launch_bounds__(ATT2_WARPS * 32, 1) k_attention_mma2(const __h
 // NBUF = 1 trades the prefetch for twice as many resident warps.
 // KT = number of 8-key tiles that hold valid keys (7 for the 50 tokens of ViT-B/32): score MMAs, softmax terms and
 // P fragments of the all-padding tile are not computed at all.
-template <int ATT3_GROUPS, int NBUF, int KT>
-__global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
+template <int ATT3_GROUPS, int NBUF, int KT, int WPG = 2>
+__global__ void __launch_bounds__(ATT3_GROUPS * WPG * 32, 1) k_attention_mma3(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
                                                                        int W, float scale, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   // two warps share one (image, head) tile: 8 warps per SM (2 per scheduler) hide ldmatrix / HMMA latency,
   // and each warp handles every other 16-row query tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = warp >> 1, wsub = warp & 1, l64 = wsub * 32 + lane;
+  constexpr int GT = WPG * 32;    // threads of a group: WPG warps share one (image, head) tile (4: one 16-row query tile each at T <= 64)
+  const int grp = warp / WPG, wsub = warp % WPG, l64 = wsub * 32 + lane;
   __half* wbase = reinterpret_cast<__half*>(att_smem) + (size_t)grp * NBUF * 3 * ATT2_TILE;
   // zero both buffers once: rows >= T are never written by cp.async and V padding rows must be finite (P = 0 there)
-  for (int i = l64; i < NBUF * 3 * ATT2_TILE / 8; i += 64) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
-  named_bar_sync(1 + grp, 64);
+  for (int i = l64; i < NBUF * 3 * ATT2_TILE / 8; i += GT) reinterpret_cast<uint4*>(wbase)[i] = make_uint4(0, 0, 0, 0);
+  named_bar_sync(1 + grp, GT);
   const long long npairs = (long long)B * heads;
   const long long gw = (long long)blockIdx.x * ATT3_GROUPS + grp, tw = (long long)gridDim.x * ATT3_GROUPS;
   const int ld = 3 * W;
@@ -1250,7 +1251,7 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
     const int b = (int)((unsigned)pair / (unsigned)heads), h = (int)((unsigned)pair - (unsigned)b * (unsigned)heads);
     __half* sQ = wbase + bi * 3 * ATT2_TILE;
     const __half* src0 = qkv + ((long long)b * T) * ld + h * 64;
-    for (int i = l64; i < T * 8; i += 64) {
+    for (int i = l64; i < T * 8; i += GT) {
       int r = i >> 3, ch = i & 7;
       const __half* src = src0 + (long long)r * ld + ch * 8;
       __half* dst = sQ + r * ATT_LD + ch * 8;
@@ -1276,12 +1277,12 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
       cp_async_commit();
       cp_async_wait<0>();
     }
-    named_bar_sync(1 + grp, 64);       // both warps' cp.async data is visible to both
+    named_bar_sync(1 + grp, GT);       // both warps' cp.async data is visible to both
     const __half* sQ = wbase + cur * 3 * ATT2_TILE;
     const __half* sK = sQ + ATT2_TILE;
     const __half* sV = sK + ATT2_TILE;
     const int b = (int)((unsigned)pair / (unsigned)heads), h = (int)((unsigned)pair - (unsigned)b * (unsigned)heads);
-    for (int mi = wsub; mi < m_tiles; mi += 2) {
+    for (int mi = wsub; mi < m_tiles; mi += WPG) {
       float s[8][4];
 #pragma unroll
       for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
@@ -1362,7 +1363,7 @@ __global__ void __launch_bounds__(ATT3_GROUPS * 64, 1) k_attention_mma3(const __
         if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2], oacc[ni][3]);
       }
     }
-    named_bar_sync(1 + grp, 64);       // both warps are done with buf[cur] before it is refilled
+    named_bar_sync(1 + grp, GT);       // both warps are done with buf[cur] before it is refilled
     if (NBUF == 2) cur ^= 1;
   }
   cp_async_wait<0>();
@@ -1587,6 +1588,7 @@ struct VitState {
   bool attn_v1 = false;
   bool attn_v2 = false;
   bool attn_v3_db = false;   // v3 with 4 double-buffered tiles per SM instead of 8 single-buffered ones
+  int attn_v3_wide = 0;      // 5 / 6: that many tiles per SM with FOUR warps each (one query tile per warp)
   bool attn_flash = false;   // force the any-T kernel (always used when T > 64)
   bool last_cls_only = true; // last layer: only the class-token row feeds ln_post/proj, so only that row is computed past K/V
   int flash_smem_set = 0;
@@ -1665,7 +1667,7 @@ int32_t vit_set_option(hmsg_ctx* ctx, const char* key, int value) {
   }
   if (!strcmp(key, "attn_variant")) {   // 0: v3 (2 warps per tile, cp.async + ldmatrix), 1: v1, 2: fp32 reference kernel, 3: v2, 4: v3 double buffered, 5: any-T online-softmax kernel
     if (!ctx->vit) return ctx->fail(HMSG_ERR_STATE, "hmsg_set_option(attn_variant): load the encoder first");
-    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->attn_flash = value == 5; ctx->vit->smem_attr_set = false;
+    ctx->vit->attn_v1 = value == 1; ctx->vit->attn_simple = value == 2; ctx->vit->attn_v2 = value == 3; ctx->vit->attn_v3_db = value == 4; ctx->vit->attn_flash = value == 5; ctx->vit->attn_v3_wide = value == 6 ? 5 : (value == 7 ? 6 : 0); ctx->vit->smem_attr_set = false;
     return HMSG_OK;
   }
   return -1;
@@ -1821,6 +1823,7 @@ extern "C" int32_t hmsg_encoder_load(hmsg_ctx* ctx, const hmsg_vit_desc* desc, c
   if (const char* e = getenv("HMSG_LN_FOLD")) vs->ln_fold = atoi(e) != 0;
   if (const char* e = getenv("HMSG_ATTN_SIMPLE")) vs->attn_simple = atoi(e) != 0;
   if (const char* e = getenv("HMSG_ATTN_V1")) vs->attn_v1 = atoi(e) != 0;
+  if (const char* e = getenv("HMSG_ATTN_WIDE")) { int v = atoi(e); vs->attn_v3_wide = (v == 5 || v == 6) ? v : 0; }
   return HMSG_OK;
 }
 
@@ -1915,11 +1918,18 @@ static int32_t forward_chunk_t(hmsg_ctx* ctx, VitState* vs, const float* dx, int
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<4, 2, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
         HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<8, 1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<5, 1, 7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
+        HMSG_CUDA(cudaFuncSetAttribute(k_attention_mma3<6, 1, 7, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM3));
         vs->smem_attr_set = true;
       }
       long long pairs = (long long)B * d.heads;
       if (pairs >= (1ll << 31)) return ctx->fail(HMSG_ERR_ARG, "attention: B * heads must be below 2^31");
-      if (vs->attn_v3_db) {
+      if (vs->attn_v3_wide && T > 48 && T <= 56) {
+        const int G = vs->attn_v3_wide;
+        int grid = (int)std::min<long long>((pairs + G - 1) / G, ctx->sm_count);
+        if (G == 5) k_attention_mma3<5, 1, 7, 4><<<grid, 5 * 128, 5 * 3 * ATT2_TILE * 2, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
+        else        k_attention_mma3<6, 1, 7, 4><<<grid, 6 * 128, 6 * 3 * ATT2_TILE * 2, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
+      } else if (vs->attn_v3_db) {
         int grid = (int)std::min<long long>((pairs + 3) / 4, ctx->sm_count);
         k_attention_mma3<4, 2, 8><<<grid, 4 * 64, SM3, ctx->stream>>>(vs->qkv, vs->h, B, T, d.heads, W, scale, q_tiles);
       } else {
