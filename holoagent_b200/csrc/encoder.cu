@@ -1282,85 +1282,133 @@ __global__ void __launch_bounds__(ATT3_GROUPS * WPG * 32, 1) k_attention_mma3(co
     const __half* sK = sQ + ATT2_TILE;
     const __half* sV = sK + ATT2_TILE;
     const int b = (int)((unsigned)pair / (unsigned)heads), h = (int)((unsigned)pair - (unsigned)b * (unsigned)heads);
-    for (int mi = wsub; mi < m_tiles; mi += WPG) {
-      float s[8][4];
+    // A warp owns the query tiles mi0 = wsub and mi1 = wsub + WPG (T <= 64: at most 4 tiles, so two per warp at WPG = 2) and
+    // computes them TOGETHER: every K fragment (scores) and every V fragment (output) is fetched from shared memory once and
+    // feeds the MMAs of both tiles.  ncu (r2t): the LSU data pipe was the busiest unit of this kernel (75 % of peak), 576 of
+    // its 1146 wavefronts per (image, head) were ldmatrix reads, half of them the second tile re-reading the same K and V.
+    const int mi0 = wsub, mi1 = wsub + WPG;
+    const bool two = WPG < 4 && mi1 < m_tiles;      // m_tiles <= 4: with four warps per tile the second tile never exists
+    if (mi0 < m_tiles) {
+      float s[2][8][4];
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) { s[q][ni][0] = s[q][ni][1] = s[q][ni][2] = s[q][ni][3] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < 4; ks++) {
-        uint32_t a[4];
-        ldsm_x4(a, sQ + (mi * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+        uint32_t a0[4], a1[4];
+        ldsm_x4(a0, sQ + (mi0 * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
+        if (two) ldsm_x4(a1, sQ + (mi1 * 16 + (lane & 15)) * ATT_LD + ks * 16 + (lane >> 4) * 8);
 #pragma unroll
         for (int np = 0; np < 4; np++) {     // two key tiles per ldmatrix.x4
           if (np * 2 < KT) {
             uint32_t bb[4];
             ldsm_x4(bb, sK + ((np * 2 + (lane >> 4)) * 8 + (lane & 7)) * ATT_LD + ks * 16 + ((lane >> 3) & 1) * 8);
-            mma_16816(s[np * 2], a, bb);
-            if (np * 2 + 1 < KT) mma_16816(s[np * 2 + 1], a, bb + 2);
+            mma_16816(s[0][np * 2], a0, bb);
+            if (np * 2 + 1 < KT) mma_16816(s[0][np * 2 + 1], a0, bb + 2);
+            if (two) {
+              mma_16816(s[1][np * 2], a1, bb);
+              if (np * 2 + 1 < KT) mma_16816(s[1][np * 2 + 1], a1, bb + 2);
+            }
           }
         }
       }
       // softmax over the raw scores: exp((s - max) * scale) = exp2(s * c - max * c), c = scale * log2(e); only the last
-      // valid tile can hold padding keys when KT == ceil(T / 8)
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int ni = 0; ni < KT; ni++) {
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          if (KT == 8 || ni == KT - 1) {   // KT < 8 is chosen only when T > 8 (KT - 1); the generic KT = 8 checks every tile
-            const int col = ni * 8 + 2 * t + e;
-            if (col >= T) { s[ni][e] = -INFINITY; s[ni][2 + e] = -INFINITY; }
-          }
-          mx0 = fmaxf(mx0, s[ni][e]); mx1 = fmaxf(mx1, s[ni][2 + e]);
-        }
-      }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      // valid tile can hold padding keys when KT == ceil(T / 8).  The normalised probabilities are packed to the fp16 A
+      // fragments of the second MMA right away (16 registers per query tile instead of 28 floats).
+      uint32_t pf[2][4][4];
       const float cexp = scale * 1.4426950408889634f;
-      const float nm0 = -mx0 * cexp, nm1 = -mx1 * cexp;
-      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-      for (int ni = 0; ni < KT; ni++) {
+      for (int q = 0; q < 2; q++) {
+        if (q == 0 || two) {
+          float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-          float p0 = ex2_approx(fmaf(s[ni][e], cexp, nm0)), p1 = ex2_approx(fmaf(s[ni][2 + e], cexp, nm1));
-          s[ni][e] = p0; s[ni][2 + e] = p1;
-          sum0 += p0; sum1 += p1;
+          for (int ni = 0; ni < KT; ni++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              if (KT == 8 || ni == KT - 1) {   // KT < 8 is chosen only when T > 8 (KT - 1); the generic KT = 8 checks every tile
+                const int col = ni * 8 + 2 * t + e;
+                if (col >= T) { s[q][ni][e] = -INFINITY; s[q][ni][2 + e] = -INFINITY; }
+              }
+              mx0 = fmaxf(mx0, s[q][ni][e]); mx1 = fmaxf(mx1, s[q][ni][2 + e]);
+            }
+          }
+          mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+          mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+          const float nm0 = -mx0 * cexp, nm1 = -mx1 * cexp;
+          float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+          for (int ni = 0; ni < KT; ni++) {
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+              float p0 = ex2_approx(fmaf(s[q][ni][e], cexp, nm0)), p1 = ex2_approx(fmaf(s[q][ni][2 + e], cexp, nm1));
+              s[q][ni][e] = p0; s[q][ni][2 + e] = p1;
+              sum0 += p0; sum1 += p1;
+            }
+          }
+          sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+          sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+          const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
+#pragma unroll
+          for (int kk = 0; kk < (KT + 1) / 2; kk++) {
+            __half2 h0 = __floats2half2_rn(s[q][2 * kk][0] * inv0, s[q][2 * kk][1] * inv0);
+            __half2 h1 = __floats2half2_rn(s[q][2 * kk][2] * inv1, s[q][2 * kk][3] * inv1);
+            pf[q][kk][0] = *reinterpret_cast<uint32_t*>(&h0); pf[q][kk][1] = *reinterpret_cast<uint32_t*>(&h1);
+            if (2 * kk + 1 < KT) {
+              __half2 h2 = __floats2half2_rn(s[q][2 * kk + 1][0] * inv0, s[q][2 * kk + 1][1] * inv0);
+              __half2 h3 = __floats2half2_rn(s[q][2 * kk + 1][2] * inv1, s[q][2 * kk + 1][3] * inv1);
+              pf[q][kk][2] = *reinterpret_cast<uint32_t*>(&h2); pf[q][kk][3] = *reinterpret_cast<uint32_t*>(&h3);
+            } else {
+              pf[q][kk][2] = 0u; pf[q][kk][3] = 0u;     // the all-padding tile: P = 0
+            }
+          }
         }
       }
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1); sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1); sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-      const float inv0 = 1.0f / sum0, inv1 = 1.0f / sum1;
-      float oacc[8][4];
+      float oacc[2][8][4];
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
+      for (int q = 0; q < 2; q++)
+#pragma unroll
+        for (int ni = 0; ni < 8; ni++) { oacc[q][ni][0] = oacc[q][ni][1] = oacc[q][ni][2] = oacc[q][ni][3] = 0.f; }
 #pragma unroll
       for (int kk = 0; kk < (KT + 1) / 2; kk++) {
-        uint32_t a[4];
-        __half2 h0 = __floats2half2_rn(s[2 * kk][0] * inv0, s[2 * kk][1] * inv0);
-        __half2 h1 = __floats2half2_rn(s[2 * kk][2] * inv1, s[2 * kk][3] * inv1);
-        a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
-        if (2 * kk + 1 < KT) {
-          __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0] * inv0, s[2 * kk + 1][1] * inv0);
-          __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2] * inv1, s[2 * kk + 1][3] * inv1);
-          a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
-        } else {
-          a[2] = 0u; a[3] = 0u;     // the all-padding tile: P = 0
-        }
 #pragma unroll
         for (int np = 0; np < 4; np++) {     // two d-column tiles per ldmatrix.x4.trans
           uint32_t bb[4];
           ldsm_x4_t(bb, sV + (kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_LD + (np * 2 + (lane >> 4)) * 8);
-          mma_16816(oacc[np * 2], a, bb);
-          mma_16816(oacc[np * 2 + 1], a, bb + 2);
+          mma_16816(oacc[0][np * 2], pf[0][kk], bb);
+          mma_16816(oacc[0][np * 2 + 1], pf[0][kk], bb + 2);
+          if (two) {
+            mma_16816(oacc[1][np * 2], pf[1][kk], bb);
+            mma_16816(oacc[1][np * 2 + 1], pf[1][kk], bb + 2);
+          }
         }
       }
-      const int r0 = mi * 16 + g, r1 = r0 + 8;
+      // The warp's own Q rows are dead now (nobody else reads them): the output tile goes there as fp16 and leaves as
+      // whole 128-byte rows (16 B per lane) instead of 16 half-filled 32-byte sectors per store instruction.
+      __half* sO = const_cast<__half*>(sQ);
 #pragma unroll
-      for (int ni = 0; ni < 8; ni++) {
-        int col = h * 64 + ni * 8 + 2 * t;
-        if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0], oacc[ni][1]);
-        if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2], oacc[ni][3]);
+      for (int q = 0; q < 2; q++) {
+        if (q == 0 || two) {
+          const int mi = q ? mi1 : mi0;
+#pragma unroll
+          for (int ni = 0; ni < 8; ni++) {
+            *reinterpret_cast<__half2*>(sO + (mi * 16 + g) * ATT_LD + ni * 8 + 2 * t) = __floats2half2_rn(oacc[q][ni][0], oacc[q][ni][1]);
+            *reinterpret_cast<__half2*>(sO + (mi * 16 + g + 8) * ATT_LD + ni * 8 + 2 * t) = __floats2half2_rn(oacc[q][ni][2], oacc[q][ni][3]);
+          }
+        }
+      }
+      __syncwarp();
+      __half* obase = o + ((long long)b * T) * W + h * 64;
+#pragma unroll
+      for (int q = 0; q < 2; q++) {
+        if (q == 0 || two) {
+          const int mi = q ? mi1 : mi0;
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const int r = mi * 16 + j * 4 + (lane >> 3), ch = lane & 7;
+            if (r < T) *reinterpret_cast<uint4*>(obase + (long long)r * W + ch * 8) = *reinterpret_cast<const uint4*>(sO + r * ATT_LD + ch * 8);
+          }
+        }
       }
     }
     named_bar_sync(1 + grp, GT);       // both warps are done with buf[cur] before it is refilled
