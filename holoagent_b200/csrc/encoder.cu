@@ -1425,26 +1425,18 @@ __global__ void __launch_bounds__(ATT3_GROUPS * WPG * 32, 1) k_attention_mma3(co
 // 16 x T score row never exists.  Same mma.sync m16n8k16 fragments as the T <= 64 kernels above.
 // ------------------------------------------------------------------------------------------
 constexpr int ATTF_WARPS = 6;
-// head dim 64: a warp walks the keys for TWO query tiles at once (32-row Q slab per warp), see the kernel
-static inline int attf_smem_bytes(int Tp, int HD = 64) { return (2 * Tp + ATTF_WARPS * (HD == 64 ? 32 : 16)) * (HD + 8) * 2; }
+static inline int attf_smem_bytes(int Tp, int HD = 64) { return (2 * Tp + ATTF_WARPS * 16) * (HD + 8) * 2; }
 
-// HD = head dim: 64 (ViT-B/32, B/16, L/14) or 80 (ViT-H/14, graph.py:105-111).
-// HD == 64: a warp owns the query tiles mi and mi + ATTF_WARPS TOGETHER - every K fragment (scores) and V fragment (output)
-// read from shared memory feeds the MMAs of both tiles, and the Q fragments are re-read from the warp's slab per key block
-// instead of living in registers (40 ldmatrix.x4 per 64-key block and tile pair instead of 64; the T <= 64 kernel showed
-// the LSU data pipe, not DRAM, to be the bound of this fragment pattern: profiles/r2t_attention_full).  Same arithmetic
-// per tile as the single-tile form that HD == 80 keeps (its accumulators would not fit the register budget twice).
+// HD = head dim: 64 (ViT-B/32, B/16, L/14) or 80 (ViT-H/14, graph.py:105-111)
 template <int HD>
-__global__ void __launch_bounds__(ATTF_WARPS * 32, HD == 64 ? 2 : 1) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
+__global__ void __launch_bounds__(ATTF_WARPS * 32) k_attention_flash(const __half* __restrict__ qkv, __half* __restrict__ o, int B, int T, int heads,
                                                                     int W, float scale, int Tp, int q_tiles) {
   extern __shared__ __align__(16) unsigned char att_smem[];
   constexpr int LD = HD + 8, CPR = HD / 8;   // padded row stride (halfs), 16-byte chunks per row
-  constexpr bool PAIR = HD == 64;
-  constexpr int NQ = PAIR ? 2 : 1;
   __half* sK = reinterpret_cast<__half*>(att_smem);
   __half* sV = sK + (size_t)Tp * LD;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  __half* sQ = sV + (size_t)Tp * LD + (size_t)warp * NQ * 16 * LD;
+  __half* sQ = sV + (size_t)Tp * LD + (size_t)warp * 16 * LD;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int ld = 3 * W;
   const __half* src0 = qkv + ((long long)b * T) * ld + h * HD;
@@ -1466,145 +1458,102 @@ __global__ void __launch_bounds__(ATTF_WARPS * 32, HD == 64 ? 2 : 1) k_attention
   __syncthreads();
   const int g = lane >> 2, t = lane & 3;
   const int m_tiles = min((T + 15) / 16, q_tiles);
-  for (int mi = warp; mi < m_tiles; mi += NQ * ATTF_WARPS) {
-    const int mi1 = mi + ATTF_WARPS;
-    const bool two = PAIR && mi1 < m_tiles;
-    // stage this warp's query rows: tile mi in slab rows 0..15, tile mi1 in rows 16..31
+  for (int mi = warp; mi < m_tiles; mi += ATTF_WARPS) {
+    // stage this warp's 16 query rows
     __syncwarp();
-    for (int i = lane; i < NQ * 16 * CPR; i += 32) {
-      const int r = i / CPR, ch = i - r * CPR, row = (r < 16 ? mi * 16 : mi1 * 16 - 16) + r;
+    for (int i = lane; i < 16 * CPR; i += 32) {
+      const int r = i / CPR, ch = i - r * CPR, row = mi * 16 + r;
       __half* dq = sQ + r * LD + ch * 8;
-      if (row < T && (r < 16 || two)) cp_async16(dq, src0 + (long long)row * ld + ch * 8);
+      if (row < T) cp_async16(dq, src0 + (long long)row * ld + ch * 8);
       else *reinterpret_cast<uint4*>(dq) = make_uint4(0, 0, 0, 0);
     }
     cp_async_commit();
     cp_async_wait<0>();
     __syncwarp();
-    uint32_t aq[PAIR ? 1 : HD / 16][4];
-    if constexpr (!PAIR) {
+    uint32_t aq[HD / 16][4];
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ks++) ldsm_x4(aq[ks], sQ + (lane & 15) * LD + ks * 16 + (lane >> 4) * 8);
-    }
-    float mrow[NQ][2], lrow[NQ][2];
-    float oacc[NQ][HD / 8][4];
+    for (int ks = 0; ks < HD / 16; ks++) ldsm_x4(aq[ks], sQ + (lane & 15) * LD + ks * 16 + (lane >> 4) * 8);
+    float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+    float oacc[HD / 8][4];
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      mrow[q][0] = mrow[q][1] = -INFINITY; lrow[q][0] = lrow[q][1] = 0.f;
-#pragma unroll
-      for (int ni = 0; ni < HD / 8; ni++) { oacc[q][ni][0] = oacc[q][ni][1] = oacc[q][ni][2] = oacc[q][ni][3] = 0.f; }
-    }
+    for (int ni = 0; ni < HD / 8; ni++) { oacc[ni][0] = oacc[ni][1] = oacc[ni][2] = oacc[ni][3] = 0.f; }
     for (int kb = 0; kb < Tp; kb += 64) {
       const int nt = min(4, (Tp - kb) >> 4);   // 16-key steps in this block (warp uniform)
-      float s[NQ][8][4];
+      float s[8][4];
 #pragma unroll
-      for (int q = 0; q < NQ; q++)
-#pragma unroll
-        for (int ni = 0; ni < 8; ni++) { s[q][ni][0] = s[q][ni][1] = s[q][ni][2] = s[q][ni][3] = 0.f; }
+      for (int ni = 0; ni < 8; ni++) { s[ni][0] = s[ni][1] = s[ni][2] = s[ni][3] = 0.f; }
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ks++) {
-        uint32_t a0[4], a1[4];
-        if constexpr (PAIR) {
-          ldsm_x4(a0, sQ + (lane & 15) * LD + ks * 16 + (lane >> 4) * 8);
-          if (two) ldsm_x4(a1, sQ + (16 + (lane & 15)) * LD + ks * 16 + (lane >> 4) * 8);
-        } else {
-          a0[0] = aq[ks][0]; a0[1] = aq[ks][1]; a0[2] = aq[ks][2]; a0[3] = aq[ks][3];
-        }
 #pragma unroll
         for (int np = 0; np < 4; np++) {
           if (np < nt) {
             uint32_t bb[4];
             ldsm_x4(bb, sK + (kb + (np * 2 + (lane >> 4)) * 8 + (lane & 7)) * LD + ks * 16 + ((lane >> 3) & 1) * 8);
-            mma_16816(s[0][np * 2], a0, bb);
-            mma_16816(s[0][np * 2 + 1], a0, bb + 2);
-            if constexpr (PAIR) {
-              if (two) {
-                mma_16816(s[NQ - 1][np * 2], a1, bb);
-                mma_16816(s[NQ - 1][np * 2 + 1], a1, bb + 2);
-              }
-            }
+            mma_16816(s[np * 2], aq[ks], bb);
+            mma_16816(s[np * 2 + 1], aq[ks], bb + 2);
           }
         }
       }
-      uint32_t pf[NQ][4][4];
+      float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
-      for (int q = 0; q < NQ; q++) {
-        if (q == 0 || two) {
-          float bm0 = -INFINITY, bm1 = -INFINITY;
+      for (int ni = 0; ni < 8; ni++) {
 #pragma unroll
-          for (int ni = 0; ni < 8; ni++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const int col = kb + ni * 8 + 2 * t + e;
-              const float v0 = (col < T) ? s[q][ni][e] * scale : -INFINITY;
-              const float v1 = (col < T) ? s[q][ni][2 + e] * scale : -INFINITY;
-              s[q][ni][e] = v0; s[q][ni][2 + e] = v1;
-              bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1);
-            }
-          }
-          bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
-          bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
-          // every block holds at least one valid key (kb < T), so the new maxima are finite
-          const float n0 = fmaxf(mrow[q][0], bm0), n1 = fmaxf(mrow[q][1], bm1);
-          const float al0 = __expf(mrow[q][0] - n0), al1 = __expf(mrow[q][1] - n1);   // exp(-inf) = 0 on the first block
-          mrow[q][0] = n0; mrow[q][1] = n1;
-          float ps0 = 0.f, ps1 = 0.f;
-#pragma unroll
-          for (int ni = 0; ni < 8; ni++) {
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-              const float p0 = __expf(s[q][ni][e] - n0), p1 = __expf(s[q][ni][2 + e] - n1);
-              s[q][ni][e] = p0; s[q][ni][2 + e] = p1;
-              ps0 += p0; ps1 += p1;
-            }
-          }
-          lrow[q][0] = lrow[q][0] * al0 + ps0; lrow[q][1] = lrow[q][1] * al1 + ps1;   // per-thread partial row sums (the quad is reduced once at the end)
-#pragma unroll
-          for (int ni = 0; ni < HD / 8; ni++) { oacc[q][ni][0] *= al0; oacc[q][ni][1] *= al0; oacc[q][ni][2] *= al1; oacc[q][ni][3] *= al1; }
-#pragma unroll
-          for (int kk = 0; kk < 4; kk++) {
-            __half2 h0 = __floats2half2_rn(s[q][2 * kk][0], s[q][2 * kk][1]);
-            __half2 h1 = __floats2half2_rn(s[q][2 * kk][2], s[q][2 * kk][3]);
-            __half2 h2 = __floats2half2_rn(s[q][2 * kk + 1][0], s[q][2 * kk + 1][1]);
-            __half2 h3 = __floats2half2_rn(s[q][2 * kk + 1][2], s[q][2 * kk + 1][3]);
-            pf[q][kk][0] = *reinterpret_cast<uint32_t*>(&h0); pf[q][kk][1] = *reinterpret_cast<uint32_t*>(&h1);
-            pf[q][kk][2] = *reinterpret_cast<uint32_t*>(&h2); pf[q][kk][3] = *reinterpret_cast<uint32_t*>(&h3);
-          }
+        for (int e = 0; e < 2; e++) {
+          const int col = kb + ni * 8 + 2 * t + e;
+          const float v0 = (col < T) ? s[ni][e] * scale : -INFINITY;
+          const float v1 = (col < T) ? s[ni][2 + e] * scale : -INFINITY;
+          s[ni][e] = v0; s[ni][2 + e] = v1;
+          bm0 = fmaxf(bm0, v0); bm1 = fmaxf(bm1, v1);
         }
       }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1)); bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1)); bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      // every block holds at least one valid key (kb < T), so the new maxima are finite
+      const float n0 = fmaxf(m0, bm0), n1 = fmaxf(m1, bm1);
+      const float al0 = __expf(m0 - n0), al1 = __expf(m1 - n1);   // exp(-inf) = 0 on the first block
+      m0 = n0; m1 = n1;
+      float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+      for (int ni = 0; ni < 8; ni++) {
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const float p0 = __expf(s[ni][e] - n0), p1 = __expf(s[ni][2 + e] - n1);
+          s[ni][e] = p0; s[ni][2 + e] = p1;
+          ps0 += p0; ps1 += p1;
+        }
+      }
+      l0 = l0 * al0 + ps0; l1 = l1 * al1 + ps1;   // per-thread partial row sums (the quad is reduced once at the end)
+#pragma unroll
+      for (int ni = 0; ni < HD / 8; ni++) { oacc[ni][0] *= al0; oacc[ni][1] *= al0; oacc[ni][2] *= al1; oacc[ni][3] *= al1; }
 #pragma unroll
       for (int kk = 0; kk < 4; kk++) {
         if (kk < nt) {
+          uint32_t a[4];
+          __half2 h0 = __floats2half2_rn(s[2 * kk][0], s[2 * kk][1]);
+          __half2 h1 = __floats2half2_rn(s[2 * kk][2], s[2 * kk][3]);
+          __half2 h2 = __floats2half2_rn(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+          __half2 h3 = __floats2half2_rn(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+          a[0] = *reinterpret_cast<uint32_t*>(&h0); a[1] = *reinterpret_cast<uint32_t*>(&h1);
+          a[2] = *reinterpret_cast<uint32_t*>(&h2); a[3] = *reinterpret_cast<uint32_t*>(&h3);
 #pragma unroll
           for (int np = 0; np < HD / 16; np++) {
             uint32_t bb[4];
             ldsm_x4_t(bb, sV + (kb + kk * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * LD + (np * 2 + (lane >> 4)) * 8);
-            mma_16816(oacc[0][np * 2], pf[0][kk], bb);
-            mma_16816(oacc[0][np * 2 + 1], pf[0][kk], bb + 2);
-            if constexpr (PAIR) {
-              if (two) {
-                mma_16816(oacc[NQ - 1][np * 2], pf[NQ - 1][kk], bb);
-                mma_16816(oacc[NQ - 1][np * 2 + 1], pf[NQ - 1][kk], bb + 2);
-              }
-            }
+            mma_16816(oacc[np * 2], a, bb);
+            mma_16816(oacc[np * 2 + 1], a, bb + 2);
           }
         }
       }
     }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
+    const int r0 = mi * 16 + g, r1 = r0 + 8;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      if (q == 0 || two) {
-        float l0 = lrow[q][0], l1 = lrow[q][1];
-        l0 += __shfl_xor_sync(0xffffffffu, l0, 1); l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-        l1 += __shfl_xor_sync(0xffffffffu, l1, 1); l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-        const float inv0 = 1.0f / l0, inv1 = 1.0f / l1;
-        const int r0 = (q ? mi1 : mi) * 16 + g, r1 = r0 + 8;
-#pragma unroll
-        for (int ni = 0; ni < HD / 8; ni++) {
-          const int col = h * HD + ni * 8 + 2 * t;
-          if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[q][ni][0] * inv0, oacc[q][ni][1] * inv0);
-          if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[q][ni][2] * inv1, oacc[q][ni][3] * inv1);
-        }
-      }
+    for (int ni = 0; ni < HD / 8; ni++) {
+      const int col = h * HD + ni * 8 + 2 * t;
+      if (r0 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r0) * W + col) = __floats2half2_rn(oacc[ni][0] * inv0, oacc[ni][1] * inv0);
+      if (r1 < T) *reinterpret_cast<__half2*>(o + ((long long)b * T + r1) * W + col) = __floats2half2_rn(oacc[ni][2] * inv1, oacc[ni][3] * inv1);
     }
   }
 }
