@@ -59,6 +59,22 @@ def hierarchical_merge(eng, frames, th, th_factor, down_size, proxy_th):
         eng.objects_add_masks(*lists[0])
 
 
+def _feats_denoise_dbscan(feats, eps=0.02, min_points=2):
+    """graph_utils.py:682-728 with the defaults room.py:299 uses: sklearn cosine DBSCAN, mean of the largest cluster, mean of
+    all rows when every row is noise (host side, a handful of rows per room)"""
+    from collections import Counter
+    from sklearn.cluster import DBSCAN
+    feats = np.asarray(feats)
+    labels = DBSCAN(eps=eps, min_samples=min_points, metric="cosine").fit(feats).labels_
+    counter = Counter(labels)
+    counter.pop(-1, None)
+    if not counter:
+        return np.mean(feats, axis=0)
+    label, _ = counter.most_common(1)[0]
+    kept = feats[labels == label]
+    return np.mean(kept, axis=0) if len(kept) > 1 else kept
+
+
 class _LazyFramesPcd:
     """The reference's local `frames_pcd` (graph.py:371, :401): per frame the list of 3-D mask clouds.  They live in
     the engine's HBM mask store; a frame is copied to the host only when somebody indexes it."""
@@ -482,6 +498,56 @@ class B200Standalone:
         return self
 
     load_graph = load_hmsg_graph
+
+    # ------------------------------------------------------------------ room names (graph.py:2129-2186; Appendix A: room.py:160-168, :303-306)
+    def set_room_names(self, room_names: List[str]):
+        """graph.py:2129-2144: one name per room, room_center_pos = mean of the room's vertices"""
+        assert len(room_names) == len(self.rooms), "The length of room_names should be the same as the number of rooms in the graph"
+        for room, name in zip(self.rooms, room_names):
+            room.name = name
+            v = np.asarray(getattr(room, "vertices", []), dtype=np.float64)
+            if v.size:
+                room.room_center_pos = np.mean(v.reshape(-1, v.shape[-1]), axis=0)
+
+    def generate_room_names(self, generate_method: str = "label", default_room_types: List[str] = None, room_type_feats=None):
+        """graph.py:2146-2186.  "view_embedding": every stored view embedding of a room votes for its best room type, the
+        type with most votes names the room (room.py:148-168; ties -> the lower type index, as np.unique + argmax give);
+        "obj_embedding": cosine-DBSCAN(eps 0.02, min 2) mean of the room's object embeddings against the type texts
+        (room.py:286-303, graph_utils.py:682-728).  The dot products run on the device like every other retrieval site;
+        `room_type_feats` [len(default_room_types), d] replaces the text tower.  "label" asks an LLM about the object
+        names (llm_utils.infer_room_type_from_object_list_chat): outside the hot path - use the reference Graph through
+        `dropin_graph_class` for it."""
+        if generate_method == "label":
+            raise NotImplementedError('generate_room_names("label") calls an LLM (room.py:262-283); use dropin_graph_class(<reference Graph>)')
+        if generate_method not in ("obj_embedding", "view_embedding"):
+            return NotImplementedError                        # sic: the reference returns the class (graph.py:2185)
+        assert default_room_types is not None, "You should provide a list of default room types"
+        text = self._text(list(default_room_types), room_type_feats)
+        for room in self.rooms:
+            if generate_method == "view_embedding":
+                if len(room.embeddings) == 0:
+                    print("empty embeddings")                  # room.py:143-145: the name stays as it was
+                    continue
+                eng = self._set_index(("roomtypes", len(default_room_types)), text)
+                sim = eng.query_scores(np.asarray(np.stack(room.embeddings), dtype=np.float32))      # [views, types]
+                col_ids = np.argmax(sim, axis=1)
+                unique, counts = np.unique(col_ids, return_counts=True)
+                room.name = default_room_types[int(unique[int(np.argmax(counts))])]
+            else:
+                embs = [np.asarray(o.embedding, dtype=np.float64) for o in room.objects]
+                if not embs:
+                    continue
+                rep = _feats_denoise_dbscan(np.stack(embs)).reshape(1, -1)
+                eng = self._set_index(("roomtypes", len(default_room_types)), text)
+                room.name = default_room_types[int(np.argmax(eng.query_scores(np.asarray(rep, dtype=np.float32))))]
+
+    def build_hier_multimodal_scene_graph(self, save_path=None):
+        """graph.py:2033-2127: floor / room segmentation, room views, navigation graph - once-per-scene CPU heuristics and
+        model calls outside SURVEY §8's path.  In drop-in mode this is the reference's own method."""
+        raise NotImplementedError("floors / rooms / navigation graph construction is outside the B200 hot path: build the class with "
+                                  "dropin_graph_class(<reference Graph>) to keep the reference's build_hier_multimodal_scene_graph")
+
+    build_graph = build_hier_multimodal_scene_graph
 
     # ------------------------------------------------------------------ artefacts on disk (graph.py:3769-3990)
     def save_full_pcd(self, path):

@@ -64,3 +64,31 @@ def check_retrieval_against_reference_run(engine):
     label_feats = np.stack([tf[words.index(c)] for c in classes])
     assert [g.identify_object(emb[i], label_feats, classes) for i in range(0, len(emb), 7)] == json.loads(str(z["identify"]))
     return n_checked
+
+
+def check_room_names_against_reference_run(engine):
+    """generate_room_names("view_embedding" / "obj_embedding") and set_room_names must name the rooms exactly as the UNMODIFIED
+    reference did (tests/golden/ref_roomnames.npz, made by tests/golden/make_reference_golden_roomnames.py)."""
+    z = np.load(os.path.join(GOLD, "ref_roomnames.npz"))
+    types_ = json.loads(str(z["types"])); tf = z["type_feats"]
+    vc, oc = z["view_counts"], z["obj_counts"]
+    voff = np.concatenate([[0], np.cumsum(vc)]); ooff = np.concatenate([[0], np.cumsum(oc)])
+    verts = json.loads(str(z["vertices"]))
+    g = Graph({"pipeline": {}}, engine=engine, clip_feat_dim=tf.shape[1])
+    g.rooms = [NS(room_id="0_%d" % r, name="room %d" % r, embeddings=list(z["room_embs"][voff[r]:voff[r + 1]]), vertices=np.asarray(verts[r]),
+                  objects=[NS(embedding=e) for e in z["obj_embs"][ooff[r]:ooff[r + 1]]]) for r in range(len(vc))]
+    g.generate_room_names("view_embedding", types_, room_type_feats=tf)
+    assert [r.name for r in g.rooms] == json.loads(str(z["names_view"]))      # incl. the room without views keeping its name
+    for r in g.rooms:
+        r.name = "room"
+    g.generate_room_names("obj_embedding", types_, room_type_feats=tf)
+    want = json.loads(str(z["names_obj"]))                                    # None: no objects (the reference raises inside sklearn there)
+    assert [r.name for r in g.rooms] == [w if w is not None else "room" for w in want]
+    g.set_room_names(["n%d" % i for i in range(len(g.rooms))])
+    assert [r.name for r in g.rooms] == ["n%d" % i for i in range(len(g.rooms))]
+    assert np.allclose(np.stack([r.room_center_pos for r in g.rooms]), z["centers"], rtol=0, atol=1e-12)
+    import pytest
+    with pytest.raises(NotImplementedError):
+        g.generate_room_names("label", types_)
+    with pytest.raises(NotImplementedError):
+        g.build_hier_multimodal_scene_graph()

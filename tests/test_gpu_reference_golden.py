@@ -111,3 +111,9 @@ def test_room_and_object_retrieval_match_reference_run(engine):
     outputs (tests/golden/ref_retrieval.npz)."""
     from tests.retrieval_golden_cases import check_retrieval_against_reference_run
     assert check_retrieval_against_reference_run(engine) >= 20
+
+
+def test_room_names_match_reference_run(engine):
+    """Appendix A sites room.py:160-168 / :303-306 through generate_room_names on the B200"""
+    from tests.retrieval_golden_cases import check_room_names_against_reference_run
+    check_room_names_against_reference_run(engine)

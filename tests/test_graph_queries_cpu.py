@@ -99,6 +99,11 @@ def test_room_and_object_retrieval_match_reference_run():
     assert check_retrieval_against_reference_run(OracleRetrievalEngine()) >= 20
 
 
+def test_room_names_match_reference_run():
+    from tests.retrieval_golden_cases import check_room_names_against_reference_run
+    check_room_names_against_reference_run(OracleRetrievalEngine())
+
+
 def test_two_graphs_sharing_one_engine_do_not_see_each_others_index():
     rs = np.random.RandomState(5)
     eng = OracleRetrievalEngine()
