@@ -560,11 +560,13 @@ def run_c5(args, eng, job, dev, torch, dist, world, rank, barrier, labels_dev):
     barrier(); out["merge_s"] = time.perf_counter() - t0
     out["merged_frames_per_rank"] = nf
     out["merge_frames_per_s"] = nf * world / out["merge_s"]
+    out["masks_offered_per_s"] = nf * world * MO / out["merge_s"]          # N1: MO instance masks per frame go through seq_merge
     out["objects"], out["object_points"] = int(n_obj), int(n_pts)
     t0 = time.perf_counter()
     full = eng.node_feats_finalize()
     feats = eng.object_feats(full, 0.05, 0.8, 0.01, 100) if n_obj else np.zeros((0, D), np.float32)
     barrier(); out["object_feats_s"] = time.perf_counter() - t0
+    out["object_feats_per_s"] = int(n_obj) / max(out["object_feats_s"], 1e-9)    # N2: gather + cosine DBSCAN + mean per object
     if n_obj:
         E = feats / np.maximum(np.linalg.norm(feats, axis=1, keepdims=True), 1e-6)
         eng.index_set(E.astype(np.float32))
