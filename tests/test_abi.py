@@ -86,3 +86,25 @@ def test_sass_carries_the_blackwell_instructions_the_design_claims():
     for need in ("UTCHMMA", "UTCHMMA.2CTA", "UTMALDG.2D", "UTMALDG.2D.2CTA", "UTMASTG.2D", "UTMAREDG.2D.ADD", "LDTM",
                  "IMMA.16832.U8.S8", "IMMA.16832.U8.U8", "FFMA2", "HMMA.16816.F32"):
         assert ops[need] > 0, (need, dict(ops))
+
+
+def test_header_is_plain_c_and_the_c_example_links(tmp_path):
+    """include/hmsg_b200.h must be usable from C (cgo / JNI / ctypes bind C, not C++): examples/hmsg_from_c.c compiles as
+    pedantic C99 and links against the built library.  Without a GPU the program has to stop at hmsg_ctx_create with the
+    library's own message - there is no CPU path to fall into."""
+    import shutil
+    import subprocess
+    import torch
+    from holoagent_b200 import build as _b
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    libdir = os.path.dirname(_b.LIB)
+    exe = str(tmp_path / "hmsg_from_c")
+    cmd = ["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "hmsg_from_c.c"),
+           "-o", exe, "-L", libdir, "-lhmsg_b200", "-Wl,-rpath," + libdir]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    if torch.cuda.is_available():
+        return                      # running it is the GPU suite's business
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 2 and "no CPU fallback" in r.stderr, (r.returncode, r.stderr)
