@@ -3,6 +3,7 @@ fixtures (tests/golden/, made by tests/golden/make_golden.py)."""
 import os
 
 import numpy as np
+import pytest
 import torch
 
 from holoagent_b200 import synth
@@ -236,3 +237,21 @@ def test_text_template_shim_matches_reference_formula():
     ref = O.template_mean(raw / np.linalg.norm(raw, axis=-1, keepdims=True), 2)
     assert out.shape == (3, d) and np.allclose(out, ref, atol=1e-7)
     assert np.all(np.linalg.norm(out, axis=-1) < 1.0)             # a mean of two unit vectors is not re-normalised (H8)
+
+
+def test_clip_preprocess_equals_the_torchvision_pipeline_open_clip_builds():
+    """open_clip's eval `image_transform` (un-vendored; what the reference's `preprocess` is, clip_utils.py:72-73, :88-89) is a
+    torchvision Compose: Resize(224, BICUBIC) -> CenterCrop(224) -> RGB -> ToTensor -> Normalize(CLIP mean / std).  torchvision
+    is installed here, so the oracle's restatement is held to the real thing bit for bit - at the 512x512 size every mask crop
+    has (sam_utils.py:144), at full-frame shapes (wide, tall) and at odd sizes that exercise the rounding of the resize / crop."""
+    tv = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+    pipe = tv.Compose([tv.Resize(224, interpolation=tv.InterpolationMode.BICUBIC), tv.CenterCrop(224), lambda im: im.convert("RGB"),
+                       tv.ToTensor(), tv.Normalize(mean=O.CLIP_MEAN, std=O.CLIP_STD)])
+    rs = np.random.RandomState(8)
+    for (h, w) in [(512, 512), (480, 640), (640, 480), (720, 1280), (224, 224), (301, 517), (517, 301), (225, 999)]:
+        img = rs.randint(0, 256, (h, w, 3)).astype(np.uint8)
+        ref = pipe(Image.fromarray(img))
+        got = O.clip_preprocess(img)
+        assert got.shape == ref.shape == (3, 224, 224)
+        assert torch.equal(got, ref), (h, w, float((got - ref).abs().max()))
